@@ -1,0 +1,144 @@
+/*
+ * onephase_b200.h -- C ABI of libonephase_b200.so, the B200-native (sm_100a)
+ * replacement for the per-iteration KKT solve of ohinder/OnePhase.jl.
+ *
+ * Every entry point replaces a method of the reference's two plugin interfaces
+ * (paths relative to the reference's src/):
+ *   abstract_linear_system_solver   linear_system_solvers/linear_system_solvers.jl:11,40-46
+ *   abstract_KKT_system_solver      kkt_system_solver/kkt_system_solver.jl:10-19
+ * The Julia shim that binds them with ccall is in julia/ (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - all pointers are HOST pointers owned by the caller; the library copies in /
+ *     out during the call and never retains them;
+ *   - sparse matrices are CSC with int64 indices, `index_base` 1 (Julia) or 0;
+ *   - every function returns 0 on success or a negative OPB_ERR_* code; the text
+ *     is available from opb_last_error(h).  "Not positive definite" is a RESULT
+ *     (inertia_ok == 0), never an error (julia.jl:39-45);
+ *   - a handle is bound to one CUDA device and one stream; calls on a handle are
+ *     synchronous with respect to the host and must not be issued concurrently;
+ *   - there is no CPU fallback: numeric calls on a handle created with
+ *     device_id < 0 return OPB_ERR_NO_DEVICE.
+ */
+#ifndef ONEPHASE_B200_H
+#define ONEPHASE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct opb_handle opb_handle;
+
+#define OPB_OK 0
+#define OPB_ERR_INVALID (-1)    /* bad argument / malformed pattern            */
+#define OPB_ERR_STATE (-2)      /* call order violates the `ready` state machine (kkt_system_solver.jl:181-199) */
+#define OPB_ERR_CUDA (-3)       /* CUDA runtime error (incl. out of memory)    */
+#define OPB_ERR_NO_DEVICE (-4)  /* numeric call on a host-only handle          */
+#define OPB_ERR_INTERNAL (-5)
+
+#define OPB_MODE_CHOLESKY 0     /* sym == :definite  (julia.jl:28-46)  */
+#define OPB_MODE_LDLT 1         /* sym == :symmetric (julia.jl:47-90)  */
+
+/* status_out of opb_factor_delta_loop (delta_strategy.jl:37-114) */
+#define OPB_DELTA_SUCCESS 1     /* :success                                  */
+#define OPB_DELTA_FAILURE 0     /* :failure, delta > delta.max -> :MAX_DELTA */
+#define OPB_DELTA_MAX_IT (-1)   /* error("max it")                           */
+
+/* initialize! / finalize!  (linear_system_solvers.jl:40-46, kkt_system_solver.jl:21-25).
+ * device_id >= 0 selects the CUDA device; device_id < 0 creates a host-only
+ * handle (symbolic analysis + introspection only). */
+int opb_create(opb_handle** h, int device_id, unsigned flags);
+int opb_destroy(opb_handle* h);
+const char* opb_last_error(const opb_handle* h);
+
+/* Run all kernels of this handle on an existing cudaStream_t (e.g. the host
+ * framework's current stream) instead of the handle's own stream. */
+int opb_set_stream(opb_handle* h, void* cuda_stream);
+
+/* Options (before opb_set_structure): "nd_leaf", "ordering" (0 ND+MD, 1 natural),
+ * "relax" (0/1), "attempts_per_sync". */
+int opb_set_option(opb_handle* h, const char* key, double value);
+/* Optional fill-reducing permutation supplied by the caller (0-based, perm[new] = old). */
+int opb_set_permutation(opb_handle* h, int64_t n, const int64_t* perm);
+
+/* Sparsity of the iterate's cached matrices: J (m x n CSC, Class_iterate.jl:334-355)
+ * and H (n x n CSC, lower triangular incl. diagonal, eval.jl:132-134).  Runs the
+ * symbolic analysis once per pattern (cached by pattern hash per process): pattern
+ * of tril(J'DJ + H) with full diagonal, gather map, ordering, supernodes, level
+ * sets.  CHOLMOD redoes this on every ls_factor! (julia.jl:34, recycle=false). */
+int opb_set_structure(opb_handle* h, int64_t n, int64_t m,
+                      const int64_t* J_colptr, const int64_t* J_rowval,
+                      const int64_t* H_colptr, const int64_t* H_rowval, int index_base);
+
+/* form_system!  (schur.jl:47-62): Q = J' diag(y./s) J + H, schur_diag = diag(Q);
+ * also returns diag_min(kkt_solver) (kkt_system_solver.jl:291-294).
+ * schur_diag_out (n) and diag_min_out may be NULL. */
+int opb_form(opb_handle* h, const double* J_nzval, const double* H_nzval,
+             const double* y, const double* s, double* schur_diag_out, double* diag_min_out);
+
+/* Lower triangle of Q as assembled on the device: pattern (0-based) and values,
+ * for is_diag_dom (delta_strategy.jl:95) and for tests. */
+int opb_get_M_pattern(opb_handle* h, int64_t* colptr_out, int64_t* rowval_out);
+int opb_get_M_values(opb_handle* h, double* nzval_out);
+
+/* ipopt_strategy!  (delta_strategy.jl:37-114) with update_delta_vecs! + ls_factor!
+ * (schur.jl:64-87, julia.jl:28-46) inside: the whole delta loop runs on the
+ * device, the PD check never returns to the host between attempts. */
+int opb_factor_delta_loop(opb_handle* h, double delta_prev, double delta_zero, double delta_min,
+                          double delta_max, double delta_start, double inc, double dec, int max_it,
+                          double* delta_out, int* num_fac_out, int* status_out);
+
+/* factor!(kkt_solver, delta, timer)  (kkt_system_solver.jl:98-107,190-204): one
+ * attempt with a given shift (one_phase.jl:241, test/kkt_system_solvers.jl:78). */
+int opb_factor(opb_handle* h, double delta, int* inertia_ok);
+
+/* compute_direction_implementation!  (schur.jl:89-128) with solver_schur_rhs's
+ * iterative refinement (schur.jl:131-182) and update_kkt_error!
+ * (kkt_system_solver.jl:67-96).  kkt_err_out = [error_D, error_P, error_mu,
+ * overall, rhs_norm, ratio] (Class_kkt_error; ratio is the log's "N err"). */
+int opb_direction(opb_handle* h, const double* dual_r, const double* primal_r, const double* comp_r,
+                  int n_refine, double* dx_out, double* dy_out, double* ds_out, double* kkt_err_out);
+
+/* ls_factor!(solver, Q, n, m, timer)  (julia.jl:21-97) for an arbitrary
+ * SparseMatrixCSC: only entries with row >= col are read.  mode CHOLESKY:
+ * inertia_ok = 1 iff PD; mode LDLT: inertia_ok = inertia_status(pos, neg, zero,
+ * n_pos_expected, m_neg_expected) (linear_system_solvers.jl:48-91). */
+int opb_ls_factor_csc(opb_handle* h, int64_t dim, const int64_t* colptr, const int64_t* rowval,
+                      const double* nzval, int index_base, int mode,
+                      int64_t n_pos_expected, int64_t m_neg_expected, int* inertia_ok);
+/* ls_solve! / ls_solve  (julia.jl:99-113): sol = F \ rhs with the last factor. */
+int opb_ls_solve(opb_handle* h, const double* rhs, double* sol);
+
+/* --- device-resident variants used by bench.py's `value` leg: inputs are uploaded
+ *     once, the timed region launches kernels only. --- */
+int opb_upload_values(opb_handle* h, const double* J_nzval, const double* H_nzval,
+                      const double* y, const double* s);
+int opb_upload_rhs(opb_handle* h, const double* dual_r, const double* primal_r, const double* comp_r);
+int opb_form_resident(opb_handle* h);
+int opb_delta_loop_resident(opb_handle* h, double delta_prev, double delta_zero, double delta_min,
+                            double delta_max, double delta_start, double inc, double dec, int max_it);
+int opb_direction_resident(opb_handle* h, int n_refine);
+int opb_solve_resident(opb_handle* h, int nsolves);   /* triangular solves only, on the residual vector */
+/* blocks until the stream is idle and reads the controller state */
+int opb_sync_state(opb_handle* h, double* delta_out, int* num_fac_out, int* status_out, double* kkt_err_out);
+
+/* --- introspection --- */
+/* keys: n, m, nnzJ, nnzH, nnzM, npairs, nnzL, nnzL_true, flops, nsuper, nlevels,
+ *       max_front, cb_total, n_tiny, n_small, n_big, device_bytes, symbolic_cached */
+int opb_get_info(opb_handle* h, const char* key, double* out);
+/* symbolic arrays for tests: perm, sfirst, sparent, rowptr, rowidx, rel, Loff, CBoff,
+ * level, amap, dpos, Mp, Mi, pair_ptr, pairA, pairB, hmap.  Values are widened to
+ * int64.  Returns the element count (or a negative error); copies min(count, cap). */
+int64_t opb_get_symbolic(opb_handle* h, const char* name, int64_t* out, int64_t cap);
+/* factor values of supernode panels as stored on the device (tests) */
+int opb_get_L_values(opb_handle* h, double* out, int64_t cap);
+/* kernels launched by the library since process start */
+long long opb_launch_count(void);
+const char* opb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

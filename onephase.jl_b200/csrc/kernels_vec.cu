@@ -1,0 +1,135 @@
+// Vector-level pieces of compute_direction_implementation! (schur.jl:89-128),
+// the refinement residual of solver_schur_rhs (schur.jl:165-169) and
+// update_kkt_error! (kkt_system_solver.jl:67-96).  All products use the cached
+// matrices of the factorisation iterate: J by rows (CSR copy of the values), J by
+// columns (the caller's CSC values) and the symmetric view of the lower-triangular
+// H (eval.jl:221-230: L v + L' v - diag(L) v).
+#include "opb_internal.h"
+
+namespace opb {
+
+namespace {
+
+__device__ __forceinline__ void max_abs_to(unsigned long long* slot, double v) {
+    // |v| as an ordered unsigned key; NaN (0x7ff8...) sorts above +inf so it propagates
+    unsigned long long key = (unsigned long long)__double_as_longlong(fabs(v));
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    if ((threadIdx.x & 31) == 0 && key) atomicMax(slot, key);
+}
+
+__global__ void rhs_m_kernel(DirBuffers B) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < B.m) B.tm[k] = B.primal_r[k] * B.sigma[k] + B.comp_r[k] / B.s[k];
+}
+
+__device__ __forceinline__ double jt_dot(const DirBuffers& B, int j, const double* v) {
+    double acc = 0.0;
+    for (int64_t p = B.Jp[j]; p < B.Jp[j + 1]; p++) acc += B.Jv[p] * v[B.Jrow[p]];
+    return acc;
+}
+__device__ __forceinline__ double j_dot(const DirBuffers& B, int k, const double* v) {
+    double acc = 0.0;
+    for (int64_t q = B.Rp[k]; q < B.Rp[k + 1]; q++) acc += B.Rval[q] * v[B.Rcol[q]];
+    return acc;
+}
+__device__ __forceinline__ double h_dot(const DirBuffers& B, int i, const double* v) {
+    double acc = 0.0;
+    for (int64_t q = B.Sp[i]; q < B.Sp[i + 1]; q++) acc += B.Hv[B.Spos[q]] * v[B.Scol[q]];
+    return acc;
+}
+
+__global__ void rhs_n_kernel(DirBuffers B) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= B.n) return;
+    double v = B.dual_r[j] + jt_dot(B, j, B.tm);
+    B.b[j] = v; B.res[j] = v; B.dx[j] = 0.0;
+}
+
+__global__ void res_m_kernel(DirBuffers B) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < B.m) B.tm[k] = B.sigma[k] * j_dot(B, k, B.dx);
+}
+
+__global__ void res_n_kernel(DirBuffers B) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= B.n) return;
+    const double delta = B.st_d->delta;
+    double jac_res = jt_dot(B, j, B.tm);
+    double hess_res = h_dot(B, j, B.dx) + delta * B.dx[j];
+    B.res[j] = B.b[j] - (jac_res + hess_res);
+}
+
+__global__ void red_reset_kernel(unsigned long long* red) { if (threadIdx.x < 8) red[threadIdx.x] = 0ull; }
+
+__global__ void recover_m_kernel(DirBuffers B) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    double eP = 0.0, eM = 0.0, rP = 0.0, rC = 0.0;
+    if (k < B.m) {
+        const double jd = j_dot(B, k, B.dx);
+        const double pr = B.primal_r[k], cr = B.comp_r[k], yk = B.y[k], sk = B.s[k];
+        const double sym_p = pr + cr / yk;
+        const double dy = -(jd - sym_p) * B.sigma[k];
+        const double ds = jd - pr;
+        B.dy[k] = dy; B.ds[k] = ds;
+        eP = jd - ds - pr;
+        eM = sk * dy + yk * ds - cr;
+        rP = pr; rC = cr;
+    }
+    max_abs_to(B.red + 1, eP);
+    max_abs_to(B.red + 2, eM);
+    max_abs_to(B.red + 4, rP);
+    max_abs_to(B.red + 5, rC);
+}
+
+__global__ void recover_n_kernel(DirBuffers B) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double eD = 0.0, rD = 0.0;
+    if (j < B.n) {
+        const double delta = B.st_d->delta;
+        const double dxj = B.dx[j];
+        const double delta_err = delta * dxj;
+        const double H_err = h_dot(B, j, B.dx);
+        const double J_err = jt_dot(B, j, B.dy);
+        rD = B.dual_r[j];
+        eD = (delta_err + H_err - J_err) - rD;
+    }
+    max_abs_to(B.red + 0, eD);
+    max_abs_to(B.red + 3, rD);
+}
+
+__global__ void kkt_err_finish_kernel(DirBuffers B) {
+    auto val = [&](int i) { return __longlong_as_double((long long)B.red[i]); };
+    auto mx = [](double a, double b) { return (a != a || b != b) ? __longlong_as_double(0x7ff8000000000000ll) : (a > b ? a : b); };
+    double eD = val(0), eP = val(1), eM = val(2);
+    double overall = mx(mx(eD, eP), eM);
+    double rhs_norm = mx(mx(val(3), val(4)), val(5));
+    double* o = B.st_d->kkt_err;
+    o[0] = eD; o[1] = eP; o[2] = eM; o[3] = overall; o[4] = rhs_norm; o[5] = overall / rhs_norm;
+}
+
+inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+}  // namespace
+
+void launch_schur_rhs(const DirBuffers& B, cudaStream_t st) {
+    if (B.m > 0) { rhs_m_kernel<<<nblk(B.m), 256, 0, st>>>(B); count_launch(); }
+    rhs_n_kernel<<<nblk(B.n), 256, 0, st>>>(B); count_launch();
+}
+
+void launch_residual(const DirBuffers& B, cudaStream_t st) {
+    if (B.m > 0) { res_m_kernel<<<nblk(B.m), 256, 0, st>>>(B); count_launch(); }
+    res_n_kernel<<<nblk(B.n), 256, 0, st>>>(B); count_launch();
+}
+
+void launch_recover_and_error(const DirBuffers& B, cudaStream_t st) {
+    red_reset_kernel<<<1, 32, 0, st>>>(B.red);
+    if (B.m > 0) recover_m_kernel<<<nblk(B.m), 256, 0, st>>>(B);
+    recover_n_kernel<<<nblk(B.n), 256, 0, st>>>(B);
+    kkt_err_finish_kernel<<<1, 1, 0, st>>>(B);
+    count_launch(4);
+}
+
+}  // namespace opb

@@ -1,0 +1,693 @@
+// C ABI of libonephase_b200.so (include/onephase_b200.h).  Host orchestration
+// only: symbolic cache, device buffers, kernel sequencing.  No numeric work is
+// done on the host; without a CUDA device the numeric entry points fail.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+
+#include "../../include/onephase_b200.h"
+#include "opb_internal.h"
+
+namespace opb {
+std::atomic<long long> g_launches{0};
+
+// Immutable per-pattern data (host + device), shared between handles.
+struct Bundle {
+    bool schur = false;          // built from (J,H) patterns; else from a user CSC matrix
+    SchurPattern P;              // schur only
+    std::vector<int64_t> Mp;     // pattern of the lower triangle that is factorised
+    std::vector<int> Mi;
+    std::vector<int64_t> src;    // csc path: position in the caller's nzval (or -1)
+    Symbolic S;
+    std::vector<LevelPlan> plan;
+    std::vector<int> sched;
+    int n_tiny = 0, n_small = 0, n_big = 0;
+    int device = -1;
+    size_t device_bytes = 0;
+    // device copies
+    DBuf<int> d_sfirst, d_rowidx, d_rel, d_sparent, d_child_ptr, d_child_list, d_perm, d_sched;
+    DBuf<int64_t> d_rowptr, d_Loff, d_CBoff, d_amap, d_dpos, d_Mp, d_src;
+    DBuf<int64_t> d_pair_ptr, d_Jp, d_Rp, d_Sp;
+    DBuf<int> d_pairA, d_pairB, d_hmap, d_Jrow, d_Rcol, d_Rpos, d_Scol, d_Spos;
+    DevSym dev{};
+    ~Bundle() {
+        if (device >= 0) cudaSetDevice(device);
+        d_sfirst.release(); d_rowidx.release(); d_rel.release(); d_sparent.release();
+        d_child_ptr.release(); d_child_list.release(); d_perm.release(); d_sched.release();
+        d_rowptr.release(); d_Loff.release(); d_CBoff.release(); d_amap.release(); d_dpos.release();
+        d_Mp.release(); d_src.release(); d_pair_ptr.release(); d_Jp.release(); d_Rp.release(); d_Sp.release();
+        d_pairA.release(); d_pairB.release(); d_hmap.release(); d_Jrow.release(); d_Rcol.release();
+        d_Rpos.release(); d_Scol.release(); d_Spos.release();
+    }
+};
+
+static std::mutex g_cache_mu;
+static std::map<std::string, std::shared_ptr<Bundle>> g_cache;
+static std::vector<std::string> g_cache_order;
+constexpr size_t CACHE_MAX = 8;
+
+static void build_plan(Bundle& B) {
+    const Symbolic& S = B.S;
+    B.plan.assign(S.nlevels, LevelPlan());
+    B.sched.clear();
+    B.n_tiny = B.n_small = B.n_big = 0;
+    for (int l = 0; l < S.nlevels; l++) {
+        LevelPlan& L = B.plan[l];
+        std::vector<int> tiny, small, big;
+        for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
+            int s = S.level_list[t];
+            int c = S.sfirst[s + 1] - S.sfirst[s];
+            int N = c + (int)(S.rowptr[s + 1] - S.rowptr[s]);
+            L.all_maxN = std::max(L.all_maxN, N);
+            if (N <= TINY_N) { tiny.push_back(s); L.tiny_maxN = std::max(L.tiny_maxN, N); }
+            else if (N <= SMALL_N) { small.push_back(s); L.small_maxN = std::max(L.small_maxN, N); }
+            else { big.push_back(s); L.big_maxN = std::max(L.big_maxN, N); L.big_maxC = std::max(L.big_maxC, c); }
+        }
+        L.all_begin = L.tiny_begin = (int)B.sched.size();
+        L.tiny_count = (int)tiny.size();
+        B.sched.insert(B.sched.end(), tiny.begin(), tiny.end());
+        L.small_begin = (int)B.sched.size();
+        L.small_count = (int)small.size();
+        B.sched.insert(B.sched.end(), small.begin(), small.end());
+        L.big_begin = (int)B.sched.size();
+        L.big_count = (int)big.size();
+        B.sched.insert(B.sched.end(), big.begin(), big.end());
+        L.all_count = L.tiny_count + L.small_count + L.big_count;
+        B.n_tiny += L.tiny_count; B.n_small += L.small_count; B.n_big += L.big_count;
+    }
+}
+
+}  // namespace opb
+
+using namespace opb;
+
+struct opb_handle {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    SymOptions opt;
+    std::vector<int64_t> user_perm;
+    int attempts_per_sync = 2;
+    std::shared_ptr<Bundle> B;
+    bool cached_hit = false;
+    // numeric state
+    enum Ready { NOT_READY, SYSTEM_FORMED, FACTORED } ready = NOT_READY;
+    int mode = OPB_MODE_CHOLESKY;
+    DBuf<double> Jv, Hv, y, s, sigma, T, Rval, Mval, sdiag, Lval, CB;
+    DBuf<double> dual_r, primal_r, comp_r, b, res, dx, dy, ds, tm, xw, uw, userval;
+    DBuf<unsigned long long> red;
+    char* d_state_raw = nullptr;
+    DeltaState* d_state = nullptr;
+    DeltaState h_state{};
+    size_t numeric_bytes = 0;
+    uint64_t csc_hash = 0;
+
+    int fail(int code, const std::string& msg) { err = msg; return code; }
+    int cuda_fail(cudaError_t e, const char* where) {
+        err = std::string(where) + ": " + cudaGetErrorString(e);
+        cudaGetLastError();
+        return OPB_ERR_CUDA;
+    }
+};
+
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return h->cuda_fail(e__, #call); \
+    } while (0)
+
+static const char* kVersion = "onephase_b200 0.1 (sm_100a)";
+
+extern "C" {
+
+const char* opb_version(void) { return kVersion; }
+long long opb_launch_count(void) { return g_launches.load(); }
+
+int opb_create(opb_handle** out, int device_id, unsigned flags) {
+    (void)flags;
+    if (!out) return OPB_ERR_INVALID;
+    opb_handle* h = new opb_handle();
+    *out = h;
+    h->device = device_id;
+    if (device_id >= 0) {
+        cudaError_t e = cudaSetDevice(device_id);
+        if (e != cudaSuccess) return h->cuda_fail(e, "cudaSetDevice");
+        e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return h->cuda_fail(e, "cudaStreamCreate");
+        h->own_stream = true;
+        e = cudaMalloc((void**)&h->d_state_raw, sizeof(DeltaState) + 128);
+        if (e != cudaSuccess) return h->cuda_fail(e, "cudaMalloc(state)");
+        h->d_state = reinterpret_cast<DeltaState*>(h->d_state_raw);
+        e = cudaMemsetAsync(h->d_state_raw, 0, sizeof(DeltaState) + 128, h->stream);
+        if (e != cudaSuccess) return h->cuda_fail(e, "cudaMemset(state)");
+        e = factor_configure();
+        if (e != cudaSuccess) return h->cuda_fail(e, "factor_configure (is this an sm_100a device?)");
+        e = h->red.alloc(8);
+        if (e != cudaSuccess) return h->cuda_fail(e, "cudaMalloc(red)");
+    }
+    return OPB_OK;
+}
+
+int opb_destroy(opb_handle* h) {
+    if (!h) return OPB_OK;
+    if (h->device >= 0) {
+        cudaSetDevice(h->device);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        DBuf<double>* bufs[] = {&h->Jv, &h->Hv, &h->y, &h->s, &h->sigma, &h->T, &h->Rval, &h->Mval, &h->sdiag,
+                                &h->Lval, &h->CB, &h->dual_r, &h->primal_r, &h->comp_r, &h->b, &h->res,
+                                &h->dx, &h->dy, &h->ds, &h->tm, &h->xw, &h->uw, &h->userval};
+        for (auto* b : bufs) b->release();
+        h->red.release();
+        if (h->d_state_raw) cudaFree(h->d_state_raw);
+        if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    }
+    h->B.reset();
+    delete h;
+    return OPB_OK;
+}
+
+const char* opb_last_error(const opb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int opb_set_stream(opb_handle* h, void* cuda_stream) {
+    if (!h) return OPB_ERR_INVALID;
+    if (h->device < 0) return h->fail(OPB_ERR_NO_DEVICE, "host-only handle");
+    if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->own_stream = false;
+    h->stream = (cudaStream_t)cuda_stream;
+    return OPB_OK;
+}
+
+int opb_set_option(opb_handle* h, const char* key, double v) {
+    if (!h || !key) return OPB_ERR_INVALID;
+    std::string k(key);
+    if (k == "nd_leaf") h->opt.nd_leaf = (int)v;
+    else if (k == "ordering") h->opt.ordering = (int)v;
+    else if (k == "relax") h->opt.relax_enable = (int)v;
+    else if (k == "relax_small") h->opt.relax_small = v;
+    else if (k == "attempts_per_sync") h->attempts_per_sync = std::max(1, (int)v);
+    else return h->fail(OPB_ERR_INVALID, "unknown option " + k);
+    return OPB_OK;
+}
+
+int opb_set_permutation(opb_handle* h, int64_t n, const int64_t* perm) {
+    if (!h) return OPB_ERR_INVALID;
+    if (!perm || n <= 0) { h->user_perm.clear(); return OPB_OK; }
+    h->user_perm.assign(perm, perm + n);
+    return OPB_OK;
+}
+
+static int upload_bundle(opb_handle* h, Bundle& B) {
+    cudaStream_t st = h->stream;
+    Symbolic& S = B.S;
+    B.device = h->device;
+    CK(B.d_sfirst.upload(S.sfirst, st)); CK(B.d_rowptr.upload(S.rowptr, st));
+    CK(B.d_rowidx.upload(S.rowidx, st)); CK(B.d_rel.upload(S.rel, st));
+    CK(B.d_Loff.upload(S.Loff, st)); CK(B.d_CBoff.upload(S.CBoff, st));
+    CK(B.d_sparent.upload(S.sparent, st)); CK(B.d_child_ptr.upload(S.child_ptr, st));
+    CK(B.d_child_list.upload(S.child_list, st)); CK(B.d_perm.upload(S.perm, st));
+    CK(B.d_sched.upload(B.sched, st));
+    {
+        // diagonal entries carry a flag so the scatter kernel adds delta to them
+        std::vector<int64_t> amap = S.amap;
+        const int64_t flag = (int64_t)1 << 62;
+        for (int j = 0; j < S.n; j++) amap[B.Mp[j]] |= flag;   // first entry of each column = diagonal
+        CK(B.d_amap.upload(amap, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    CK(B.d_dpos.upload(S.dpos, st)); CK(B.d_Mp.upload(B.Mp, st));
+    if (B.schur) {
+        SchurPattern& P = B.P;
+        CK(B.d_pair_ptr.upload(P.pair_ptr, st)); CK(B.d_pairA.upload(P.pairA, st));
+        CK(B.d_pairB.upload(P.pairB, st)); CK(B.d_hmap.upload(P.hmap, st));
+        CK(B.d_Jrow.upload(P.Jrow, st)); CK(B.d_Jp.upload(P.Jp, st));
+        CK(B.d_Rp.upload(P.Rp, st)); CK(B.d_Rcol.upload(P.Rcol, st)); CK(B.d_Rpos.upload(P.Rpos, st));
+        CK(B.d_Sp.upload(P.Sp, st)); CK(B.d_Scol.upload(P.Scol, st)); CK(B.d_Spos.upload(P.Spos, st));
+    } else {
+        CK(B.d_src.upload(B.src, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    B.dev.n = S.n; B.dev.nsuper = S.nsuper;
+    B.dev.sfirst = B.d_sfirst.p; B.dev.rowptr = B.d_rowptr.p; B.dev.rowidx = B.d_rowidx.p;
+    B.dev.rel = B.d_rel.p; B.dev.Loff = B.d_Loff.p; B.dev.CBoff = B.d_CBoff.p;
+    B.dev.sparent = B.d_sparent.p; B.dev.child_ptr = B.d_child_ptr.p; B.dev.child_list = B.d_child_list.p;
+    B.dev.perm = B.d_perm.p;
+    return OPB_OK;
+}
+
+static int alloc_numeric(opb_handle* h) {
+    Bundle& B = *h->B;
+    const Symbolic& S = B.S;
+    const int n = S.n;
+    CK(h->Mval.alloc(B.Mp[n])); CK(h->sdiag.alloc(n));
+    CK(h->Lval.alloc(S.nnzL)); CK(h->CB.alloc(S.cb_total));
+    CK(h->xw.alloc(n)); CK(h->uw.alloc(S.rowidx.size()));
+    CK(h->res.alloc(n)); CK(h->dx.alloc(n)); CK(h->b.alloc(n));
+    if (B.schur) {
+        const int m = B.P.m;
+        CK(h->Jv.alloc(B.P.nnzJ)); CK(h->Hv.alloc(B.P.nnzH)); CK(h->y.alloc(m)); CK(h->s.alloc(m));
+        CK(h->sigma.alloc(m)); CK(h->T.alloc(B.P.nnzJ)); CK(h->Rval.alloc(B.P.nnzJ));
+        CK(h->dual_r.alloc(n)); CK(h->primal_r.alloc(m)); CK(h->comp_r.alloc(m));
+        CK(h->dy.alloc(m)); CK(h->ds.alloc(m)); CK(h->tm.alloc(m));
+    }
+    return OPB_OK;
+}
+
+static std::string cache_key(int device, const SymOptions& o, bool has_perm, uint64_t h1, uint64_t h2) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "%d|%d|%d|%d|%d|%016llx|%016llx", device, o.nd_leaf, o.ordering, o.relax_enable,
+             has_perm ? 1 : 0, (unsigned long long)h1, (unsigned long long)h2);
+    return buf;
+}
+
+static std::shared_ptr<Bundle> cache_get(const std::string& key) {
+    std::lock_guard<std::mutex> g(g_cache_mu);
+    auto it = g_cache.find(key);
+    return it == g_cache.end() ? nullptr : it->second;
+}
+static void cache_put(const std::string& key, std::shared_ptr<Bundle> b) {
+    std::lock_guard<std::mutex> g(g_cache_mu);
+    if (g_cache.count(key)) return;
+    if (g_cache_order.size() >= CACHE_MAX) {
+        g_cache.erase(g_cache_order.front());
+        g_cache_order.erase(g_cache_order.begin());
+    }
+    g_cache[key] = b;
+    g_cache_order.push_back(key);
+}
+
+static int finish_structure(opb_handle* h, std::shared_ptr<Bundle> B, const std::string& key) {
+    const int64_t* up = h->user_perm.empty() ? nullptr : h->user_perm.data();
+    if (up && (int64_t)h->user_perm.size() != (int64_t)(B->Mp.size() - 1))
+        return h->fail(OPB_ERR_INVALID, "permutation length does not match n");
+    if (!analyze((int)(B->Mp.size() - 1), B->Mp, B->Mi, h->opt, up, B->S))
+        return h->fail(OPB_ERR_INTERNAL, "symbolic analysis failed: " + B->S.error);
+    build_plan(*B);
+    if (h->device >= 0) {
+        cudaSetDevice(h->device);
+        int rc = upload_bundle(h, *B);
+        if (rc) return rc;
+    }
+    cache_put(key, B);
+    h->B = B;
+    h->cached_hit = false;
+    h->ready = opb_handle::NOT_READY;
+    if (h->device >= 0) return alloc_numeric(h);
+    return OPB_OK;
+}
+
+int opb_set_structure(opb_handle* h, int64_t n, int64_t m, const int64_t* Jp, const int64_t* Ji,
+                      const int64_t* Hp, const int64_t* Hi, int base) {
+    if (!h) return OPB_ERR_INVALID;
+    if (!Jp || !Hp || (base != 0 && base != 1) || n <= 0 || m < 0) return h->fail(OPB_ERR_INVALID, "bad arguments");
+    if (h->device >= 0) cudaSetDevice(h->device);
+    const int64_t nnzJ = Jp[n] - base, nnzH = Hp[n] - base;
+    if (nnzJ < 0 || nnzH < 0) return h->fail(OPB_ERR_INVALID, "bad colptr");
+    uint64_t h1 = pattern_hash(n, Jp, Ji, nnzJ) ^ (uint64_t)m * 0x9e3779b97f4a7c15ull;
+    uint64_t h2 = pattern_hash(n, Hp, Hi, nnzH) + (uint64_t)base;
+    if (!h->user_perm.empty()) h2 ^= pattern_hash(0, h->user_perm.data(), h->user_perm.data(), (int64_t)h->user_perm.size());
+    std::string key = "S|" + cache_key(h->device, h->opt, !h->user_perm.empty(), h1, h2);
+    if (auto B = cache_get(key)) {
+        if (B->S.n == n && B->P.m == m && B->P.nnzJ == nnzJ && B->P.nnzH == nnzH) {
+            h->B = B; h->cached_hit = true; h->ready = opb_handle::NOT_READY;
+            if (h->device >= 0) return alloc_numeric(h);
+            return OPB_OK;
+        }
+    }
+    auto B = std::make_shared<Bundle>();
+    B->schur = true;
+    std::string err;
+    if (!build_schur_pattern(n, m, Jp, Ji, Hp, Hi, base, B->P, err)) return h->fail(OPB_ERR_INVALID, err);
+    B->Mp = B->P.Mp; B->Mi = B->P.Mi;
+    return finish_structure(h, B, key);
+}
+
+// ---- staged (asynchronous) building blocks ---------------------------------
+static int need_device(opb_handle* h) {
+    if (!h) return OPB_ERR_INVALID;
+    if (h->device < 0) return h->fail(OPB_ERR_NO_DEVICE, "numeric call on a host-only handle (no CPU fallback)");
+    cudaSetDevice(h->device);
+    return OPB_OK;
+}
+
+static int stage_form(opb_handle* h) {
+    Bundle& B = *h->B;
+    cudaStream_t st = h->stream;
+    launch_sigma_T(h->Jv.p, B.d_Jrow.p, h->y.p, h->s.p, h->sigma.p, h->T.p, B.P.nnzJ, B.P.m, st);
+    launch_assemble_M(B.d_pair_ptr.p, B.d_pairA.p, B.d_pairB.p, B.d_hmap.p, h->T.p, h->Jv.p, h->Hv.p,
+                      h->Mval.p, B.Mp[B.S.n], st);
+    launch_diag_extract(B.d_Mp.p, h->Mval.p, h->sdiag.p, h->d_state, B.S.n, st);
+    launch_csr_gather(h->Jv.p, B.d_Rpos.p, h->Rval.p, B.P.nnzJ, st);
+    CK(cudaGetLastError());
+    h->ready = opb_handle::SYSTEM_FORMED;
+    return OPB_OK;
+}
+
+static void enqueue_attempt(opb_handle* h) {
+    Bundle& B = *h->B;
+    cudaStream_t st = h->stream;
+    launch_ctl_begin(h->d_state, st);
+    launch_scatter_fronts(h->Mval.p, B.d_amap.p, B.d_dpos.p, h->sdiag.p, h->Lval.p, B.S.nnzL,
+                          B.Mp[B.S.n], B.S.n, h->d_state, 1, st);
+    launch_factor_levels(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->d_state, st);
+    launch_ctl_end(h->d_state, st);
+}
+
+static int read_state(opb_handle* h) {
+    CK(cudaMemcpyAsync(&h->h_state, h->d_state, sizeof(DeltaState), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return OPB_OK;
+}
+
+// enqueue attempts until the device controller reports done
+static int run_delta_loop(opb_handle* h, bool first_chunk_only) {
+    for (;;) {
+        for (int a = 0; a < h->attempts_per_sync; a++) enqueue_attempt(h);
+        CK(cudaGetLastError());
+        if (first_chunk_only) return OPB_OK;
+        int rc = read_state(h);
+        if (rc) return rc;
+        if (h->h_state.done) return OPB_OK;
+    }
+}
+
+int opb_upload_values(opb_handle* h, const double* Jx, const double* Hx, const double* y, const double* s) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || !h->B->schur) return h->fail(OPB_ERR_STATE, "opb_set_structure has not been called");
+    Bundle& B = *h->B;
+    cudaStream_t st = h->stream;
+    if (B.P.nnzJ) CK(cudaMemcpyAsync(h->Jv.p, Jx, B.P.nnzJ * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (B.P.nnzH) CK(cudaMemcpyAsync(h->Hv.p, Hx, B.P.nnzH * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (B.P.m) {
+        CK(cudaMemcpyAsync(h->y.p, y, B.P.m * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->s.p, s, B.P.m * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    return OPB_OK;
+}
+
+int opb_form_resident(opb_handle* h) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || !h->B->schur) return h->fail(OPB_ERR_STATE, "opb_set_structure has not been called");
+    return stage_form(h);
+}
+
+int opb_form(opb_handle* h, const double* Jx, const double* Hx, const double* y, const double* s,
+             double* schur_diag_out, double* diag_min_out) {
+    int rc = opb_upload_values(h, Jx, Hx, y, s); if (rc) return rc;
+    rc = stage_form(h); if (rc) return rc;
+    if (schur_diag_out)
+        CK(cudaMemcpyAsync(schur_diag_out, h->sdiag.p, h->B->S.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    rc = read_state(h); if (rc) return rc;
+    if (diag_min_out) *diag_min_out = h->h_state.diag_min;
+    return OPB_OK;
+}
+
+int opb_get_M_pattern(opb_handle* h, int64_t* cp, int64_t* ri) {
+    if (!h || !h->B) return OPB_ERR_STATE;
+    const Bundle& B = *h->B;
+    if (cp) memcpy(cp, B.Mp.data(), B.Mp.size() * sizeof(int64_t));
+    if (ri) for (size_t k = 0; k < B.Mi.size(); k++) ri[k] = B.Mi[k];
+    return OPB_OK;
+}
+
+int opb_get_M_values(opb_handle* h, double* out) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || h->ready == opb_handle::NOT_READY) return h->fail(OPB_ERR_STATE, "system not formed");
+    CK(cudaMemcpyAsync(out, h->Mval.p, h->B->Mp[h->B->S.n] * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return OPB_OK;
+}
+
+int opb_delta_loop_resident(opb_handle* h, double delta_prev, double delta_zero, double delta_min,
+                            double delta_max, double delta_start, double inc, double dec, int max_it) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || h->ready == opb_handle::NOT_READY) return h->fail(OPB_ERR_STATE, "kkt solver not ready to factor (form_system first)");
+    h->mode = OPB_MODE_CHOLESKY;
+    launch_ctl_init(h->d_state, delta_prev, delta_zero, delta_min, delta_max, delta_start, inc, dec,
+                    max_it, OPB_MODE_CHOLESKY, h->stream);
+    rc = run_delta_loop(h, false);
+    if (rc) return rc;
+    h->ready = opb_handle::FACTORED;
+    return OPB_OK;
+}
+
+int opb_factor_delta_loop(opb_handle* h, double delta_prev, double delta_zero, double delta_min,
+                          double delta_max, double delta_start, double inc, double dec, int max_it,
+                          double* delta_out, int* num_fac_out, int* status_out) {
+    int rc = opb_delta_loop_resident(h, delta_prev, delta_zero, delta_min, delta_max, delta_start, inc, dec, max_it);
+    if (rc) return rc;
+    if (delta_out) *delta_out = h->h_state.delta;
+    if (num_fac_out) *num_fac_out = h->h_state.num_fac;
+    if (status_out) *status_out = h->h_state.status;
+    return OPB_OK;
+}
+
+static int single_factor(opb_handle* h, double delta, int mode, int* ok) {
+    h->mode = mode;
+    launch_ctl_single(h->d_state, delta, mode, h->stream);
+    enqueue_attempt(h);
+    if (mode == OPB_MODE_LDLT)
+        launch_ldlt_inertia(h->B->dev, h->Lval.p, h->B->d_dpos.p, h->B->S.n, h->d_state, h->stream);
+    CK(cudaGetLastError());
+    int rc = read_state(h); if (rc) return rc;
+    h->ready = opb_handle::FACTORED;
+    if (ok) *ok = (h->h_state.status == 1) ? 1 : 0;
+    return OPB_OK;
+}
+
+int opb_factor(opb_handle* h, double delta, int* inertia_ok) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || h->ready == opb_handle::NOT_READY) return h->fail(OPB_ERR_STATE, "kkt solver not ready to factor (form_system first)");
+    return single_factor(h, delta, OPB_MODE_CHOLESKY, inertia_ok);
+}
+
+int opb_upload_rhs(opb_handle* h, const double* dual_r, const double* primal_r, const double* comp_r) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || !h->B->schur) return h->fail(OPB_ERR_STATE, "opb_set_structure has not been called");
+    const int n = h->B->S.n, m = h->B->P.m;
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->dual_r.p, dual_r, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (m) {
+        CK(cudaMemcpyAsync(h->primal_r.p, primal_r, m * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->comp_r.p, comp_r, m * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    return OPB_OK;
+}
+
+static DirBuffers dir_buffers(opb_handle* h) {
+    Bundle& B = *h->B;
+    DirBuffers D{};
+    D.n = B.S.n; D.m = B.P.m;
+    D.Rp = B.d_Rp.p; D.Rcol = B.d_Rcol.p; D.Rval = h->Rval.p;
+    D.Jp = B.d_Jp.p; D.Jrow = B.d_Jrow.p; D.Jv = h->Jv.p;
+    D.Sp = B.d_Sp.p; D.Scol = B.d_Scol.p; D.Spos = B.d_Spos.p; D.Hv = h->Hv.p;
+    D.y = h->y.p; D.s = h->s.p; D.sigma = h->sigma.p;
+    D.dual_r = h->dual_r.p; D.primal_r = h->primal_r.p; D.comp_r = h->comp_r.p;
+    D.b = h->b.p; D.res = h->res.p; D.dx = h->dx.p; D.dy = h->dy.p; D.ds = h->ds.p;
+    D.tm = h->tm.p; D.tm2 = nullptr; D.red = h->red.p; D.st_d = h->d_state;
+    return D;
+}
+
+int opb_direction_resident(opb_handle* h, int n_refine) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || !h->B->schur) return h->fail(OPB_ERR_STATE, "opb_set_structure has not been called");
+    if (h->ready != opb_handle::FACTORED) return h->fail(OPB_ERR_STATE, "kkt solver not ready to compute direction!");
+    Bundle& B = *h->B;
+    cudaStream_t st = h->stream;
+    DirBuffers D = dir_buffers(h);
+    launch_schur_rhs(D, st);
+    for (int it = 0; it < n_refine; it++) {
+        launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, D.n, st);
+        launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->xw.p, h->uw.p, h->mode, st);
+        launch_permute_out_add(h->xw.p, B.d_perm.p, h->dx.p, D.n, 1, st);
+        // the reference also evaluates the residual after the last correction but only
+        // prints it (schur.jl:177-179); it does not influence the direction
+        if (it + 1 < n_refine) launch_residual(D, st);
+    }
+    launch_recover_and_error(D, st);
+    CK(cudaGetLastError());
+    return OPB_OK;
+}
+
+int opb_direction(opb_handle* h, const double* dual_r, const double* primal_r, const double* comp_r,
+                  int n_refine, double* dx, double* dy, double* ds, double* kkt_err) {
+    int rc = opb_upload_rhs(h, dual_r, primal_r, comp_r); if (rc) return rc;
+    rc = opb_direction_resident(h, n_refine); if (rc) return rc;
+    const int n = h->B->S.n, m = h->B->P.m;
+    cudaStream_t st = h->stream;
+    if (dx) CK(cudaMemcpyAsync(dx, h->dx.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (dy && m) CK(cudaMemcpyAsync(dy, h->dy.p, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (ds && m) CK(cudaMemcpyAsync(ds, h->ds.p, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    rc = read_state(h); if (rc) return rc;
+    if (kkt_err) memcpy(kkt_err, h->h_state.kkt_err, 6 * sizeof(double));
+    return OPB_OK;
+}
+
+int opb_solve_resident(opb_handle* h, int nsolves) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || h->ready != opb_handle::FACTORED) return h->fail(OPB_ERR_STATE, "no factor");
+    Bundle& B = *h->B;
+    for (int k = 0; k < nsolves; k++) {
+        launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, B.S.n, h->stream);
+        launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->xw.p, h->uw.p, h->mode, h->stream);
+        launch_permute_out_add(h->xw.p, B.d_perm.p, h->b.p, B.S.n, 0, h->stream);
+    }
+    CK(cudaGetLastError());
+    return OPB_OK;
+}
+
+int opb_sync_state(opb_handle* h, double* delta_out, int* num_fac_out, int* status_out, double* kkt_err_out) {
+    int rc = need_device(h); if (rc) return rc;
+    rc = read_state(h); if (rc) return rc;
+    if (delta_out) *delta_out = h->h_state.delta;
+    if (num_fac_out) *num_fac_out = h->h_state.num_fac;
+    if (status_out) *status_out = h->h_state.status;
+    if (kkt_err_out) memcpy(kkt_err_out, h->h_state.kkt_err, 6 * sizeof(double));
+    return OPB_OK;
+}
+
+}  // extern "C"
+
+// ---- L1 compatibility path: arbitrary CSC matrix -----------------------------
+namespace {
+__global__ void csc_gather_kernel(const double* __restrict__ user, const int64_t* __restrict__ src,
+                                  double* __restrict__ Mval, int64_t nnzM) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nnzM) { int64_t p = src[e]; Mval[e] = p >= 0 ? user[p] : 0.0; }
+}
+template <class T>
+int64_t copy_out(const std::vector<T>& v, int64_t* out, int64_t cap) {
+    int64_t n = (int64_t)v.size();
+    if (out) for (int64_t k = 0; k < std::min(n, cap); k++) out[k] = (int64_t)v[k];
+    return n;
+}
+}  // namespace
+
+extern "C" {
+
+int opb_ls_factor_csc(opb_handle* h, int64_t dim, const int64_t* cp, const int64_t* ri, const double* nz,
+                      int base, int mode, int64_t n_pos, int64_t m_neg, int* inertia_ok) {
+    if (!h) return OPB_ERR_INVALID;
+    if (!cp || !ri || !nz || dim <= 0 || (base != 0 && base != 1)) return h->fail(OPB_ERR_INVALID, "bad arguments");
+    if (mode != OPB_MODE_CHOLESKY && mode != OPB_MODE_LDLT) return h->fail(OPB_ERR_INVALID, "bad mode");
+    if (mode == OPB_MODE_CHOLESKY && m_neg != 0) return h->fail(OPB_ERR_INVALID, "Cholesky requires m == 0 (julia.jl:30)");
+    int rc = need_device(h); if (rc) return rc;
+    const int64_t nnz = cp[dim] - base;
+    uint64_t h1 = pattern_hash(dim, cp, ri, nnz) + (uint64_t)base;
+    std::string key = "C|" + cache_key(h->device, h->opt, !h->user_perm.empty(), h1, 0);
+    std::shared_ptr<Bundle> B = cache_get(key);
+    if (B && (B->S.n != dim || B->schur)) B.reset();
+    if (B) {
+        h->B = B; h->cached_hit = true;
+        rc = alloc_numeric(h); if (rc) return rc;
+    } else {
+        B = std::make_shared<Bundle>();
+        B->schur = false;
+        std::string err;
+        if (!build_csc_pattern(dim, cp, ri, base, B->Mp, B->Mi, B->src, err)) return h->fail(OPB_ERR_INVALID, err);
+        rc = finish_structure(h, B, key); if (rc) return rc;
+    }
+    cudaStream_t st = h->stream;
+    CK(h->userval.alloc(nnz));
+    if (nnz) CK(cudaMemcpyAsync(h->userval.p, nz, nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int64_t nnzM = h->B->Mp[dim];
+    csc_gather_kernel<<<(unsigned)((nnzM + 255) / 256), 256, 0, st>>>(h->userval.p, h->B->d_src.p, h->Mval.p, nnzM);
+    count_launch();
+    h->ready = opb_handle::SYSTEM_FORMED;
+    int ok = 0;
+    rc = single_factor(h, 0.0, mode, &ok); if (rc) return rc;
+    if (mode == OPB_MODE_LDLT && ok) {
+        const DeltaState& s = h->h_state;
+        // inertia_status (linear_system_solvers.jl:48-91) on the classified pivots
+        ok = (s.n_bad == 0 && s.n_pos == n_pos && s.n_neg == m_neg) ? 1 : 0;
+    }
+    if (inertia_ok) *inertia_ok = ok;
+    return OPB_OK;
+}
+
+int opb_ls_solve(opb_handle* h, const double* rhs, double* sol) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || h->ready != opb_handle::FACTORED) return h->fail(OPB_ERR_STATE, "ls_solve before ls_factor!");
+    Bundle& B = *h->B;
+    const int n = B.S.n;
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->res.p, rhs, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, n, st);
+    launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->xw.p, h->uw.p, h->mode, st);
+    launch_permute_out_add(h->xw.p, B.d_perm.p, h->b.p, n, 0, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(sol, h->b.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return OPB_OK;
+}
+
+// ---- introspection -----------------------------------------------------------
+int opb_get_info(opb_handle* h, const char* key, double* out) {
+    if (!h || !key || !out) return OPB_ERR_INVALID;
+    if (!h->B) return h->fail(OPB_ERR_STATE, "no structure");
+    const Bundle& B = *h->B;
+    const Symbolic& S = B.S;
+    std::string k(key);
+    if (k == "n") *out = S.n;
+    else if (k == "m") *out = B.P.m;
+    else if (k == "nnzJ") *out = (double)B.P.nnzJ;
+    else if (k == "nnzH") *out = (double)B.P.nnzH;
+    else if (k == "nnzM") *out = (double)B.Mp[S.n];
+    else if (k == "npairs") *out = B.schur ? (double)B.P.pair_ptr.back() : 0.0;
+    else if (k == "nnzL") *out = (double)S.nnzL;
+    else if (k == "nnzL_true") *out = (double)S.nnzL_true;
+    else if (k == "flops") *out = S.flops;
+    else if (k == "nsuper") *out = S.nsuper;
+    else if (k == "nlevels") *out = S.nlevels;
+    else if (k == "max_front") *out = S.max_front;
+    else if (k == "cb_total") *out = (double)S.cb_total;
+    else if (k == "n_tiny") *out = B.n_tiny;
+    else if (k == "n_small") *out = B.n_small;
+    else if (k == "n_big") *out = B.n_big;
+    else if (k == "symbolic_cached") *out = h->cached_hit ? 1 : 0;
+    else if (k == "sum_rows") *out = (double)S.rowidx.size();
+    else return h->fail(OPB_ERR_INVALID, "unknown info key " + k);
+    return OPB_OK;
+}
+
+int64_t opb_get_symbolic(opb_handle* h, const char* name, int64_t* out, int64_t cap) {
+    if (!h || !name) return OPB_ERR_INVALID;
+    if (!h->B) return h->fail(OPB_ERR_STATE, "no structure");
+    const Bundle& B = *h->B;
+    const Symbolic& S = B.S;
+    std::string k(name);
+    if (k == "perm") return copy_out(S.perm, out, cap);
+    if (k == "sfirst") return copy_out(S.sfirst, out, cap);
+    if (k == "sparent") return copy_out(S.sparent, out, cap);
+    if (k == "rowptr") return copy_out(S.rowptr, out, cap);
+    if (k == "rowidx") return copy_out(S.rowidx, out, cap);
+    if (k == "rel") return copy_out(S.rel, out, cap);
+    if (k == "Loff") return copy_out(S.Loff, out, cap);
+    if (k == "CBoff") return copy_out(S.CBoff, out, cap);
+    if (k == "level") return copy_out(S.level, out, cap);
+    if (k == "amap") return copy_out(S.amap, out, cap);
+    if (k == "dpos") return copy_out(S.dpos, out, cap);
+    if (k == "Mp") return copy_out(B.Mp, out, cap);
+    if (k == "Mi") return copy_out(B.Mi, out, cap);
+    if (k == "src") return copy_out(B.src, out, cap);
+    if (k == "pair_ptr") return copy_out(B.P.pair_ptr, out, cap);
+    if (k == "pairA") return copy_out(B.P.pairA, out, cap);
+    if (k == "pairB") return copy_out(B.P.pairB, out, cap);
+    if (k == "hmap") return copy_out(B.P.hmap, out, cap);
+    return h->fail(OPB_ERR_INVALID, "unknown symbolic array " + k);
+}
+
+int opb_get_L_values(opb_handle* h, double* out, int64_t cap) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || h->ready != opb_handle::FACTORED) return h->fail(OPB_ERR_STATE, "no factor");
+    int64_t cnt = std::min<int64_t>(cap, h->B->S.nnzL);
+    CK(cudaMemcpyAsync(out, h->Lval.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return OPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+// Internal declarations shared by the CUDA translation units of libonephase_b200.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "symbolic.h"
+
+namespace opb {
+
+// number of kernels launched by this library (bench.py reports it as gpu_launches)
+extern std::atomic<long long> g_launches;
+inline void count_launch(int k = 1) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+
+// Device-resident controller state of the delta loop (delta_strategy.jl:37-114).
+// Every factorisation kernel reads `done`/`fail` first and exits when set, so a
+// whole attempt that is no longer needed costs only empty launches.
+struct DeltaState {
+    double delta;        // shift of the attempt in flight / accepted shift
+    double tau;
+    double delta_prev, delta_zero, delta_min, delta_max, delta_start, inc, dec;
+    double diag_min;
+    int done;            // loop finished (success, failure or max_it)
+    int fail;            // current attempt hit a non-positive pivot
+    int num_fac;
+    int status;          // 1 success, 0 failure (delta > delta_max), -1 max it, 2 running
+    int it;              // index i of the reference's for-loop (0 = the delta_zero probe)
+    int max_it;
+    int mode;            // 0 Cholesky, 1 LDL'
+    int pad;
+    // LDL' inertia (julia.jl:72-80)
+    int n_pos, n_neg, n_zero, n_bad;
+    double kkt_err[6];
+};
+
+// Flat view of the symbolic structures in device memory.
+struct DevSym {
+    int n, nsuper;
+    const int* sfirst;
+    const int64_t* rowptr;
+    const int* rowidx;
+    const int* rel;
+    const int64_t* Loff;
+    const int64_t* CBoff;
+    const int* sparent;
+    const int* child_ptr;
+    const int* child_list;
+    const int* perm;   // perm[new] = old
+};
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) n = count; else p = nullptr;
+        return e;
+    }
+    cudaError_t upload(const std::vector<T>& h, cudaStream_t st) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess) return e;
+        if (h.empty()) return cudaSuccess;
+        return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// Per-level schedule built on the host from Symbolic.
+struct LevelPlan {
+    int tiny_begin = 0, tiny_count = 0;      // fronts with N <= TINY_N  (indices into d_sched)
+    int small_begin = 0, small_count = 0;    // fronts with N <= SMALL_N
+    int big_begin = 0, big_count = 0;        // the rest: blocked path in global memory
+    int small_maxN = 0, tiny_maxN = 0;
+    int big_maxN = 0, big_maxC = 0;
+    int all_begin = 0, all_count = 0;        // every supernode of the level (solves)
+    int all_maxN = 0;
+};
+
+constexpr int TINY_N = 32;
+constexpr int SMALL_N = 152;   // 152*152*8 = 184,832 B of shared memory
+constexpr int NB = 32;         // block-column width of the big-front path
+
+// ---- kernels_assembly.cu
+void launch_sigma_T(const double* Jv, const int* Jrow, const double* y, const double* s,
+                    double* sigma, double* T, int64_t nnzJ, int m, cudaStream_t st);
+void launch_assemble_M(const int64_t* pair_ptr, const int* pairA, const int* pairB, const int* hmap,
+                       const double* T, const double* Jv, const double* Hv, double* Mval,
+                       int64_t nnzM, cudaStream_t st);
+void launch_diag_extract(const int64_t* Mp, const double* Mval, double* sdiag, DeltaState* st_d,
+                         int n, cudaStream_t st);
+void launch_csr_gather(const double* src, const int* pos, double* dst, int64_t nnz, cudaStream_t st);
+void launch_scatter_fronts(const double* Mval, const int64_t* amap, const int64_t* dpos,
+                           const double* sdiag, double* Lval, int64_t nnzL, int64_t nnzM, int n,
+                           const DeltaState* st_d, int use_sdiag, cudaStream_t st);
+void launch_ctl_begin(DeltaState* st_d, cudaStream_t st);
+void launch_ctl_end(DeltaState* st_d, cudaStream_t st);
+void launch_ctl_init(DeltaState* st_d, double delta_prev, double delta_zero, double delta_min,
+                     double delta_max, double delta_start, double inc, double dec, int max_it,
+                     int mode, cudaStream_t st);
+void launch_ctl_single(DeltaState* st_d, double delta, int mode, cudaStream_t st);
+
+// ---- kernels_factor.cu
+cudaError_t factor_configure();
+void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
+                          double* Lval, double* CB, DeltaState* st_d, cudaStream_t st);
+void launch_ldlt_inertia(const DevSym& S, const double* Lval, const int64_t* dpos, int n,
+                         DeltaState* st_d, cudaStream_t st);
+
+// ---- kernels_solve.cu
+cudaError_t solve_configure();
+// x (permuted order, length n) is overwritten with the solution; u = workspace (len rowidx)
+void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
+                  const double* Lval, double* x, double* u, int mode, cudaStream_t st);
+void launch_permute_in(const double* b, const int* perm, double* x, int n, cudaStream_t st);
+void launch_permute_out_add(const double* x, const int* perm, double* dst, int n, int accumulate, cudaStream_t st);
+
+// ---- kernels_vec.cu  (direction, refinement residual, KKT error)
+struct DirBuffers {
+    int n, m;
+    // matrices
+    const int64_t* Rp; const int* Rcol; const double* Rval;      // J by rows
+    const int64_t* Jp; const int* Jrow; const double* Jv;         // J by columns
+    const int64_t* Sp; const int* Scol; const int* Spos; const double* Hv;  // H symmetric view
+    const double *y, *s, *sigma;
+    const double *dual_r, *primal_r, *comp_r;
+    double *b, *res, *dx, *dy, *ds, *tm, *tm2;
+    unsigned long long* red;   // 8 slots of max-reduction scratch
+    DeltaState* st_d;
+};
+void launch_schur_rhs(const DirBuffers& B, cudaStream_t st);
+void launch_residual(const DirBuffers& B, cudaStream_t st);          // res = b - (J'(S.(J dx)) + Hsym dx + delta dx)
+void launch_recover_and_error(const DirBuffers& B, cudaStream_t st);  // dy, ds, kkt_err[6]
+
+}  // namespace opb

@@ -1,0 +1,763 @@
+// Symbolic analysis (host, once per sparsity pattern).  See symbolic.h.
+//
+// Stages:
+//   1. build_schur_pattern : pattern of tril(J'DJ + H) + full diagonal, and the
+//      structure-fixed gather map used by the assembly kernel (replaces the two
+//      generic sparse*sparse products of eval.jl:85-87 / schur.jl:55).
+//   2. ordering            : nested dissection by BFS level structures with
+//      minimum-degree leaves (fill-reducing; CHOLMOD uses AMD/METIS here).
+//   3. etree, postorder, column counts (skeleton algorithm), supernodes with
+//      relaxed amalgamation, supernodal row structures.
+//   4. maps: M_L entry -> L panel slot, child update block -> parent front.
+#include "symbolic.h"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+namespace opb {
+
+uint64_t pattern_hash(int64_t n, const int64_t* p, const int64_t* i, int64_t nnz) {
+    uint64_t h = 1469598103934665603ull ^ (uint64_t)n;
+    auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    for (int64_t k = 0; k <= n; k++) mix((uint64_t)p[k]);
+    for (int64_t k = 0; k < nnz; k++) mix((uint64_t)i[k]);
+    return h;
+}
+
+// ---------------------------------------------------------------------------
+// 1. Schur pattern + gather map
+// ---------------------------------------------------------------------------
+bool build_schur_pattern(int64_t n64, int64_t m64, const int64_t* Jp_in, const int64_t* Ji_in,
+                         const int64_t* Hp_in, const int64_t* Hi_in, int base,
+                         SchurPattern& P, std::string& err) {
+    if (n64 <= 0 || n64 > 2000000000ll || m64 < 0 || m64 > 2000000000ll) { err = "bad dimensions"; return false; }
+    const int n = (int)n64, m = (int)m64;
+    P.n = n; P.m = m;
+    const int64_t nnzJ = Jp_in[n] - base, nnzH = Hp_in[n] - base;
+    if (nnzJ < 0 || nnzH < 0 || nnzJ > 2000000000ll || nnzH > 2000000000ll) { err = "bad colptr"; return false; }
+    P.nnzJ = nnzJ; P.nnzH = nnzH;
+    P.Jp.resize(n + 1);
+    for (int j = 0; j <= n; j++) P.Jp[j] = Jp_in[j] - base;
+    P.Jrow.resize(nnzJ);
+    for (int j = 0; j < n; j++) {
+        if (P.Jp[j + 1] < P.Jp[j]) { err = "J colptr not monotone"; return false; }
+        for (int64_t p = P.Jp[j]; p < P.Jp[j + 1]; p++) {
+            int64_t k = Ji_in[p] - base;
+            if (k < 0 || k >= m) { err = "J row index out of range"; return false; }
+            if (p > P.Jp[j] && k <= P.Jrow[p - 1]) { err = "J row indices not sorted/unique"; return false; }
+            P.Jrow[p] = (int)k;
+        }
+    }
+    // CSR view of J (columns ascending within each row)
+    P.Rp.assign(m + 1, 0);
+    for (int64_t p = 0; p < nnzJ; p++) P.Rp[P.Jrow[p] + 1]++;
+    for (int k = 0; k < m; k++) P.Rp[k + 1] += P.Rp[k];
+    P.Rcol.resize(nnzJ); P.Rpos.resize(nnzJ);
+    {
+        std::vector<int64_t> nxt(P.Rp.begin(), P.Rp.end() - 1);
+        for (int j = 0; j < n; j++)
+            for (int64_t p = P.Jp[j]; p < P.Jp[j + 1]; p++) {
+                int64_t q = nxt[P.Jrow[p]]++;
+                P.Rcol[q] = j; P.Rpos[q] = (int)p;
+            }
+    }
+    // H (lower) checks + symmetric CSR view
+    std::vector<int64_t> Hp(n + 1);
+    for (int j = 0; j <= n; j++) Hp[j] = Hp_in[j] - base;
+    std::vector<int> Hrow(nnzH);
+    P.Sp.assign(n + 1, 0);
+    for (int j = 0; j < n; j++)
+        for (int64_t p = Hp[j]; p < Hp[j + 1]; p++) {
+            int64_t i = Hi_in[p] - base;
+            if (i < j || i >= n) { err = "H must be lower triangular with in-range rows"; return false; }
+            if (p > Hp[j] && i <= Hrow[p - 1]) { err = "H row indices not sorted/unique"; return false; }
+            Hrow[p] = (int)i;
+            P.Sp[i + 1]++;
+            if (i != j) P.Sp[j + 1]++;
+        }
+    for (int i = 0; i < n; i++) P.Sp[i + 1] += P.Sp[i];
+    P.Scol.resize(P.Sp[n]); P.Spos.resize(P.Sp[n]);
+    {
+        // row i of H_sym: first the lower part (cols j <= i, ascending j), then the
+        // mirrored part (cols > i).  Two sweeps keep columns ascending in each row.
+        std::vector<int64_t> nxt(P.Sp.begin(), P.Sp.end() - 1);
+        for (int j = 0; j < n; j++)
+            for (int64_t p = Hp[j]; p < Hp[j + 1]; p++) {  // entry (i,j), i >= j: row i gets col j
+                int i = Hrow[p];
+                int64_t q = nxt[i]++;
+                P.Scol[q] = j; P.Spos[q] = (int)p;
+            }
+        for (int j = 0; j < n; j++)
+            for (int64_t p = Hp[j]; p < Hp[j + 1]; p++) {  // mirrored: row j gets col i (i > j)
+                int i = Hrow[p];
+                if (i == j) continue;
+                int64_t q = nxt[j]++;
+                P.Scol[q] = i; P.Spos[q] = (int)p;
+            }
+    }
+    // pattern of tril(J'DJ) U H U diag, column by column
+    std::vector<int> mark(n, -1), where(n, -1), list;
+    P.Mp.assign(n + 1, 0);
+    P.Mi.clear();
+    std::vector<int64_t> cnt;  // pairs per entry
+    // pass 1: pattern
+    for (int j = 0; j < n; j++) {
+        list.clear();
+        mark[j] = j; list.push_back(j);
+        for (int64_t p = P.Jp[j]; p < P.Jp[j + 1]; p++) {
+            int k = P.Jrow[p];
+            for (int64_t q = P.Rp[k + 1] - 1; q >= P.Rp[k]; q--) {
+                int i = P.Rcol[q];
+                if (i < j) break;
+                if (mark[i] != j) { mark[i] = j; list.push_back(i); }
+            }
+        }
+        for (int64_t p = Hp[j]; p < Hp[j + 1]; p++) {
+            int i = Hrow[p];
+            if (mark[i] != j) { mark[i] = j; list.push_back(i); }
+        }
+        std::sort(list.begin(), list.end());
+        P.Mi.insert(P.Mi.end(), list.begin(), list.end());
+        P.Mp[j + 1] = (int64_t)P.Mi.size();
+    }
+    const int64_t nnzM = P.Mp[n];
+    if (nnzM > 2000000000ll) { err = "Schur complement too large for int32 indexing"; return false; }
+    // pass 2: count pairs, hmap
+    P.pair_ptr.assign(nnzM + 1, 0);
+    P.hmap.assign(nnzM, -1);
+    for (int j = 0; j < n; j++) {
+        for (int64_t e = P.Mp[j]; e < P.Mp[j + 1]; e++) where[P.Mi[e]] = (int)(e - P.Mp[j]);
+        const int64_t e0 = P.Mp[j];
+        for (int64_t p = P.Jp[j]; p < P.Jp[j + 1]; p++) {
+            int k = P.Jrow[p];
+            for (int64_t q = P.Rp[k + 1] - 1; q >= P.Rp[k]; q--) {
+                int i = P.Rcol[q];
+                if (i < j) break;
+                P.pair_ptr[e0 + where[i] + 1]++;
+            }
+        }
+        for (int64_t p = Hp[j]; p < Hp[j + 1]; p++) P.hmap[e0 + where[Hrow[p]]] = (int)p;
+    }
+    for (int64_t e = 0; e < nnzM; e++) P.pair_ptr[e + 1] += P.pair_ptr[e];
+    const int64_t npairs = P.pair_ptr[nnzM];
+    if (npairs > 2000000000ll) { err = "too many J'DJ products for int32 indexing"; return false; }
+    P.pairA.resize(npairs); P.pairB.resize(npairs);
+    // pass 3: fill, k ascending inside each entry (CSC rows of J are ascending)
+    {
+        std::vector<int64_t> nxt(P.pair_ptr.begin(), P.pair_ptr.end() - 1);
+        for (int j = 0; j < n; j++) {
+            for (int64_t e = P.Mp[j]; e < P.Mp[j + 1]; e++) where[P.Mi[e]] = (int)(e - P.Mp[j]);
+            const int64_t e0 = P.Mp[j];
+            for (int64_t p = P.Jp[j]; p < P.Jp[j + 1]; p++) {
+                int k = P.Jrow[p];
+                for (int64_t q = P.Rp[k + 1] - 1; q >= P.Rp[k]; q--) {
+                    int i = P.Rcol[q];
+                    if (i < j) break;
+                    int64_t t = nxt[e0 + where[i]]++;
+                    P.pairA[t] = P.Rpos[q];   // J[k,i]  (scaled by sigma first)
+                    P.pairB[t] = (int)p;      // J[k,j]
+                }
+            }
+        }
+    }
+    return true;
+}
+
+bool build_csc_pattern(int64_t n64, const int64_t* Ap, const int64_t* Ai, int base,
+                       std::vector<int64_t>& Mp, std::vector<int>& Mi, std::vector<int64_t>& src,
+                       std::string& err) {
+    if (n64 <= 0 || n64 > 2000000000ll) { err = "bad dimension"; return false; }
+    const int n = (int)n64;
+    Mp.assign(n + 1, 0); Mi.clear(); src.clear();
+    std::vector<std::pair<int, int64_t>> col;
+    for (int j = 0; j < n; j++) {
+        col.clear();
+        bool have_diag = false;
+        for (int64_t p = Ap[j] - base; p < Ap[j + 1] - base; p++) {
+            int64_t i = Ai[p] - base;
+            if (i < 0 || i >= n) { err = "row index out of range"; return false; }
+            if (i < j) continue;  // upper triangle is never read (test/linear_system_solvers.jl:74-84)
+            if (i == j) have_diag = true;
+            col.emplace_back((int)i, p);
+        }
+        if (!have_diag) col.emplace_back(j, (int64_t)-1);
+        std::sort(col.begin(), col.end());
+        for (size_t t = 0; t < col.size(); t++) {
+            if (t && col[t].first == col[t - 1].first) { err = "duplicate entry"; return false; }
+            Mi.push_back(col[t].first); src.push_back(col[t].second);
+        }
+        Mp[j + 1] = (int64_t)Mi.size();
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// 2. Ordering
+// ---------------------------------------------------------------------------
+namespace {
+
+struct Graph {
+    int n;
+    std::vector<int64_t> xadj;
+    std::vector<int> adj;
+};
+
+void build_graph(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi, Graph& G) {
+    G.n = n;
+    G.xadj.assign(n + 1, 0);
+    for (int j = 0; j < n; j++)
+        for (int64_t p = Mp[j]; p < Mp[j + 1]; p++) {
+            int i = Mi[p];
+            if (i == j) continue;
+            G.xadj[i + 1]++; G.xadj[j + 1]++;
+        }
+    for (int i = 0; i < n; i++) G.xadj[i + 1] += G.xadj[i];
+    G.adj.resize(G.xadj[n]);
+    std::vector<int64_t> nxt(G.xadj.begin(), G.xadj.end() - 1);
+    for (int j = 0; j < n; j++)
+        for (int64_t p = Mp[j]; p < Mp[j + 1]; p++) {
+            int i = Mi[p];
+            if (i == j) continue;
+            G.adj[nxt[i]++] = j; G.adj[nxt[j]++] = i;
+        }
+}
+
+// Exact minimum degree on a small vertex set using bitset adjacency (elimination
+// graph model).  verts: global ids; reg[v]==rid marks membership.
+void md_small(const Graph& G, const std::vector<int>& verts, const std::vector<int>& reg, int rid,
+              std::vector<int>& local, int* out) {
+    const int k = (int)verts.size();
+    if (k <= 2) { for (int t = 0; t < k; t++) out[t] = verts[t]; return; }
+    const int W = (k + 63) / 64;
+    for (int t = 0; t < k; t++) local[verts[t]] = t;
+    std::vector<uint64_t> A((size_t)k * W, 0), alive(W, 0);
+    for (int t = 0; t < k; t++) {
+        alive[t >> 6] |= 1ull << (t & 63);
+        int v = verts[t];
+        for (int64_t p = G.xadj[v]; p < G.xadj[v + 1]; p++) {
+            int u = G.adj[p];
+            if (reg[u] != rid) continue;
+            int lu = local[u];
+            A[(size_t)t * W + (lu >> 6)] |= 1ull << (lu & 63);
+        }
+    }
+    std::vector<int> deg(k);
+    for (int t = 0; t < k; t++) {
+        int d = 0;
+        for (int w = 0; w < W; w++) d += __builtin_popcountll(A[(size_t)t * W + w]);
+        deg[t] = d;
+    }
+    std::vector<char> dead(k, 0);
+    for (int step = 0; step < k; step++) {
+        int best = -1, bd = 1 << 30;
+        for (int t = 0; t < k; t++)
+            if (!dead[t] && deg[t] < bd) { bd = deg[t]; best = t; }
+        out[step] = verts[best];
+        dead[best] = 1;
+        alive[best >> 6] &= ~(1ull << (best & 63));
+        uint64_t* Ab = &A[(size_t)best * W];
+        for (int w = 0; w < W; w++) Ab[w] &= alive[w];
+        for (int w = 0; w < W; w++) {
+            uint64_t bits = Ab[w];
+            while (bits) {
+                int u = (w << 6) + __builtin_ctzll(bits);
+                bits &= bits - 1;
+                uint64_t* Au = &A[(size_t)u * W];
+                int d = 0;
+                for (int x = 0; x < W; x++) { Au[x] = (Au[x] | Ab[x]) & alive[x]; }
+                Au[u >> 6] &= ~(1ull << (u & 63));
+                for (int x = 0; x < W; x++) d += __builtin_popcountll(Au[x]);
+                deg[u] = d;
+            }
+        }
+    }
+}
+
+struct NDWork {
+    const Graph* G;
+    std::vector<int> reg;      // region id of each vertex
+    std::vector<int> lvl;      // BFS level scratch
+    std::vector<int> queue;
+    std::vector<int> local;
+    int next_rid = 1;
+    int leaf;
+    int* perm;                 // output, new -> old
+};
+
+// BFS inside region rid from root; fills W.queue (order) and W.lvl; returns #levels.
+int bfs(NDWork& W, int root, int rid, std::vector<int>& lptr) {
+    const Graph& G = *W.G;
+    W.queue.clear(); lptr.clear();
+    W.queue.push_back(root); W.lvl[root] = 0;
+    lptr.push_back(0);
+    size_t head = 0;
+    int cur = 0;
+    // lvl is reset by the caller via stamp trick: we use lvl = -1 for unvisited in region
+    while (head < W.queue.size()) {
+        int v = W.queue[head];
+        if (W.lvl[v] != cur) { cur = W.lvl[v]; lptr.push_back((int)head); }
+        head++;
+        for (int64_t p = G.xadj[v]; p < G.xadj[v + 1]; p++) {
+            int u = G.adj[p];
+            if (W.reg[u] != rid || W.lvl[u] >= 0) continue;
+            W.lvl[u] = cur + 1;
+            W.queue.push_back(u);
+        }
+    }
+    lptr.push_back((int)W.queue.size());
+    return (int)lptr.size() - 1;
+}
+
+void order_fallback(NDWork& W, std::vector<int>& verts, int rid, int offset) {
+    if ((int)verts.size() <= 2048) {
+        md_small(*W.G, verts, W.reg, rid, W.local, W.perm + offset);
+    } else {
+        std::sort(verts.begin(), verts.end());
+        for (size_t t = 0; t < verts.size(); t++) W.perm[offset + t] = verts[t];
+    }
+}
+
+void nd_rec(NDWork& W, std::vector<int>& verts, int offset, int depth) {
+    const Graph& G = *W.G;
+    const int k = (int)verts.size();
+    if (k == 0) return;
+    const int rid = W.next_rid++;
+    for (int v : verts) { W.reg[v] = rid; W.lvl[v] = -1; }
+    if (k <= W.leaf || depth > 200) { order_fallback(W, verts, rid, offset); return; }
+    // connected components
+    std::vector<int> lptr;
+    bfs(W, verts[0], rid, lptr);
+    if ((int)W.queue.size() < k) {
+        // split into components, recurse on each
+        std::vector<std::vector<int>> comps;
+        comps.emplace_back(W.queue.begin(), W.queue.end());
+        for (int v : verts) {
+            if (W.lvl[v] >= 0) continue;
+            bfs(W, v, rid, lptr);
+            comps.emplace_back(W.queue.begin(), W.queue.end());
+        }
+        std::vector<int>().swap(verts);
+        // group tiny components together to avoid deep recursion on dust
+        std::vector<int> dust;
+        int off = offset;
+        for (auto& c : comps) {
+            if ((int)c.size() <= W.leaf / 4 + 1) { dust.insert(dust.end(), c.begin(), c.end()); continue; }
+            int sz = (int)c.size();
+            nd_rec(W, c, off, depth + 1);
+            off += sz;
+        }
+        if (!dust.empty()) {
+            // dust: components are independent; order each by md in chunks
+            size_t pos = 0;
+            while (pos < dust.size()) {
+                size_t end = std::min(dust.size(), pos + (size_t)std::max(W.leaf, 64));
+                std::vector<int> chunk(dust.begin() + pos, dust.begin() + end);
+                const int r2 = W.next_rid++;
+                for (int v : chunk) W.reg[v] = r2;
+                md_small(G, chunk, W.reg, r2, W.local, W.perm + off);
+                off += (int)chunk.size();
+                pos = end;
+            }
+        }
+        return;
+    }
+    // pseudo-peripheral root: repeat BFS from a min-degree vertex of the last level
+    int root = verts[0];
+    int nlev = (int)lptr.size() - 1;
+    for (int it = 0; it < 3; it++) {
+        int last0 = lptr[nlev - 1], last1 = lptr[nlev];
+        int cand = W.queue[last0];
+        int64_t cd = G.xadj[cand + 1] - G.xadj[cand];
+        for (int t = last0; t < last1; t++) {
+            int v = W.queue[t];
+            int64_t d = G.xadj[v + 1] - G.xadj[v];
+            if (d < cd) { cd = d; cand = v; }
+        }
+        for (int v : verts) W.lvl[v] = -1;
+        std::vector<int> lptr2;
+        int root_prev = root;
+        root = cand;
+        int nlev2 = bfs(W, root, rid, lptr2);
+        bool better = nlev2 > nlev;
+        lptr.swap(lptr2); nlev = nlev2;
+        (void)root_prev;
+        if (!better) break;
+    }
+    if (nlev < 3) { order_fallback(W, verts, rid, offset); return; }
+    // choose separator level: smallest level whose split is balanced
+    int best = -1; int64_t bestsz = INT64_MAX;
+    for (int l = 1; l + 1 < nlev; l++) {
+        int left = lptr[l], sz = lptr[l + 1] - lptr[l], right = k - lptr[l + 1];
+        if (left < 0.3 * k || right < 0.3 * k) continue;
+        if (sz < bestsz) { bestsz = sz; best = l; }
+    }
+    if (best < 0) {
+        // median level
+        for (int l = 1; l + 1 < nlev; l++) if (lptr[l + 1] >= k / 2) { best = l; break; }
+        if (best < 0) best = nlev / 2;
+        if (best < 1) best = 1;
+        if (best > nlev - 2) best = nlev - 2;
+    }
+    int sz = lptr[best + 1] - lptr[best];
+    if (sz > 0.6 * k) { order_fallback(W, verts, rid, offset); return; }
+    std::vector<int> left(W.queue.begin(), W.queue.begin() + lptr[best]);
+    std::vector<int> right(W.queue.begin() + lptr[best + 1], W.queue.end());
+    std::vector<int> sep;
+    // thin the separator: level-`best` vertices with no neighbour in level best+1 go left
+    for (int t = lptr[best]; t < lptr[best + 1]; t++) {
+        int v = W.queue[t];
+        bool touches = false;
+        for (int64_t p = G.xadj[v]; p < G.xadj[v + 1] && !touches; p++) {
+            int u = G.adj[p];
+            if (W.reg[u] == rid && W.lvl[u] == best + 1) touches = true;
+        }
+        if (touches) sep.push_back(v); else left.push_back(v);
+    }
+    std::vector<int>().swap(verts);
+    const int nl = (int)left.size(), nr = (int)right.size();
+    // separator last
+    std::sort(sep.begin(), sep.end());
+    for (size_t t = 0; t < sep.size(); t++) { W.perm[offset + nl + nr + t] = sep[t]; W.reg[sep[t]] = 0; }
+    nd_rec(W, left, offset, depth + 1);
+    nd_rec(W, right, offset + nl, depth + 1);
+}
+
+void nd_order(const Graph& G, int leaf, std::vector<int>& perm) {
+    NDWork W;
+    W.G = &G;
+    W.reg.assign(G.n, 0);
+    W.lvl.assign(G.n, -1);
+    W.local.assign(G.n, 0);
+    W.leaf = std::max(leaf, 4);
+    perm.resize(G.n);
+    W.perm = perm.data();
+    std::vector<int> all(G.n);
+    std::iota(all.begin(), all.end(), 0);
+    nd_rec(W, all, 0, 0);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// 3+4. etree, postorder, column counts, supernodes, structures, maps
+// ---------------------------------------------------------------------------
+namespace {
+
+// lower CSC of the permuted matrix (rows unsorted), strictly-lower entries only
+void permuted_lower(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
+                    const std::vector<int>& iperm, std::vector<int64_t>& Bp, std::vector<int>& Bi) {
+    Bp.assign(n + 1, 0);
+    for (int j = 0; j < n; j++)
+        for (int64_t p = Mp[j]; p < Mp[j + 1]; p++) {
+            int i = Mi[p];
+            if (i == j) continue;
+            int a = iperm[i], b = iperm[j];
+            Bp[std::min(a, b) + 1]++;
+        }
+    for (int j = 0; j < n; j++) Bp[j + 1] += Bp[j];
+    Bi.resize(Bp[n]);
+    std::vector<int64_t> nxt(Bp.begin(), Bp.end() - 1);
+    for (int j = 0; j < n; j++)
+        for (int64_t p = Mp[j]; p < Mp[j + 1]; p++) {
+            int i = Mi[p];
+            if (i == j) continue;
+            int a = iperm[i], b = iperm[j];
+            Bi[nxt[std::min(a, b)]++] = std::max(a, b);
+        }
+}
+
+// transpose of strictly-lower CSC = for each k the list of i < k with B[k,i] != 0
+void transpose_lower(int n, const std::vector<int64_t>& Bp, const std::vector<int>& Bi,
+                     std::vector<int64_t>& Up, std::vector<int>& Ui) {
+    Up.assign(n + 1, 0);
+    for (int64_t p = 0; p < Bp[n]; p++) Up[Bi[p] + 1]++;
+    for (int j = 0; j < n; j++) Up[j + 1] += Up[j];
+    Ui.resize(Up[n]);
+    std::vector<int64_t> nxt(Up.begin(), Up.end() - 1);
+    for (int j = 0; j < n; j++)
+        for (int64_t p = Bp[j]; p < Bp[j + 1]; p++) Ui[nxt[Bi[p]]++] = j;
+}
+
+void etree(int n, const std::vector<int64_t>& Up, const std::vector<int>& Ui, std::vector<int>& parent) {
+    parent.assign(n, -1);
+    std::vector<int> anc(n, -1);
+    for (int k = 0; k < n; k++)
+        for (int64_t p = Up[k]; p < Up[k + 1]; p++) {
+            int i = Ui[p];
+            while (i != -1 && i < k) {
+                int nx = anc[i];
+                anc[i] = k;
+                if (nx == -1) parent[i] = k;
+                i = nx;
+            }
+        }
+}
+
+// postorder with children sorted so that the heaviest subtree comes last
+void postorder(int n, const std::vector<int>& parent, std::vector<int>& post) {
+    std::vector<int> size(n, 1);
+    for (int j = 0; j < n; j++) if (parent[j] >= 0) size[parent[j]] += size[j];  // parent[j] > j
+    std::vector<int> cptr(n + 2, 0), clist(n);
+    for (int j = 0; j < n; j++) cptr[(parent[j] < 0 ? n : parent[j]) + 1]++;
+    for (int j = 0; j <= n; j++) cptr[j + 1] += cptr[j];
+    {
+        std::vector<int> nxt(cptr.begin(), cptr.end() - 1);
+        for (int j = 0; j < n; j++) clist[nxt[parent[j] < 0 ? n : parent[j]]++] = j;
+    }
+    for (int v = 0; v <= n; v++)
+        std::stable_sort(clist.begin() + cptr[v], clist.begin() + cptr[v + 1],
+                         [&](int a, int b) { return size[a] < size[b]; });
+    post.clear(); post.reserve(n);
+    // iterative DFS; virtual root = n
+    std::vector<int> stack, it(n + 1);
+    for (int v = 0; v <= n; v++) it[v] = cptr[v];
+    stack.push_back(n);
+    while (!stack.empty()) {
+        int v = stack.back();
+        if (it[v] < cptr[v + 1]) { stack.push_back(clist[it[v]++]); }
+        else { stack.pop_back(); if (v != n) post.push_back(v); }
+    }
+}
+
+// column counts (incl. diagonal) for a postordered matrix; Bp/Bi strictly lower CSC
+void colcounts(int n, const std::vector<int64_t>& Bp, const std::vector<int>& Bi,
+               const std::vector<int>& parent, std::vector<int64_t>& cc) {
+    std::vector<int> first(n, -1), maxfirst(n, -1), prevleaf(n, -1), anc(n);
+    std::vector<int64_t> delta(n, 0);
+    for (int j = 0; j < n; j++) {
+        if (first[j] == -1) { first[j] = j; delta[j] = 1; }  // leaf of the etree
+        else delta[j] = 0;
+        int p = parent[j];
+        if (p >= 0 && first[p] == -1) first[p] = first[j];
+    }
+    for (int j = 0; j < n; j++) anc[j] = j;
+    auto find = [&](int v) {
+        int r = v;
+        while (anc[r] != r) r = anc[r];
+        while (anc[v] != r) { int nx = anc[v]; anc[v] = r; v = nx; }
+        return r;
+    };
+    for (int j = 0; j < n; j++) {
+        if (parent[j] >= 0) delta[parent[j]]--;
+        for (int64_t p = Bp[j]; p < Bp[j + 1]; p++) {
+            int i = Bi[p];  // i > j, entry (i,j): j belongs to row subtree of i
+            if (first[j] > maxfirst[i]) {
+                // j is a leaf of the row subtree of i
+                maxfirst[i] = first[j];
+                int pl = prevleaf[i];
+                prevleaf[i] = j;
+                delta[j]++;
+                if (pl != -1) { int q = find(pl); delta[q]--; }
+            }
+        }
+        if (parent[j] >= 0) anc[j] = parent[j];
+    }
+    cc.assign(n, 0);
+    for (int j = 0; j < n; j++) {
+        cc[j] += delta[j];
+        if (parent[j] >= 0) cc[parent[j]] += cc[j];
+    }
+}
+
+}  // namespace
+
+bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
+             const SymOptions& opt, const int64_t* user_perm, Symbolic& S) {
+    S = Symbolic();
+    S.n = n;
+    // ---- ordering
+    std::vector<int> perm0(n);
+    if (user_perm) {
+        std::vector<char> seen(n, 0);
+        for (int k = 0; k < n; k++) {
+            int64_t v = user_perm[k];
+            if (v < 0 || v >= n || seen[v]) { S.error = "user permutation invalid"; return false; }
+            seen[v] = 1; perm0[k] = (int)v;
+        }
+    } else if (opt.ordering == 1) {
+        std::iota(perm0.begin(), perm0.end(), 0);
+    } else {
+        Graph G;
+        build_graph(n, Mp, Mi, G);
+        nd_order(G, opt.nd_leaf, perm0);
+    }
+    std::vector<int> iperm0(n);
+    for (int k = 0; k < n; k++) iperm0[perm0[k]] = k;
+    // ---- etree + postorder on the first permutation
+    std::vector<int64_t> Bp, Up;
+    std::vector<int> Bi, Ui, parent0, post;
+    permuted_lower(n, Mp, Mi, iperm0, Bp, Bi);
+    transpose_lower(n, Bp, Bi, Up, Ui);
+    etree(n, Up, Ui, parent0);
+    postorder(n, parent0, post);
+    S.perm.resize(n); S.iperm.resize(n);
+    for (int k = 0; k < n; k++) S.perm[k] = perm0[post[k]];
+    for (int k = 0; k < n; k++) S.iperm[S.perm[k]] = k;
+    // ---- final permuted pattern, etree, counts
+    permuted_lower(n, Mp, Mi, S.iperm, Bp, Bi);
+    transpose_lower(n, Bp, Bi, Up, Ui);
+    std::vector<int> parent;
+    etree(n, Up, Ui, parent);
+    std::vector<int64_t> cc;
+    colcounts(n, Bp, Bi, parent, cc);
+    S.flops = 0; S.nnzL_true = 0;
+    for (int j = 0; j < n; j++) { S.flops += (double)cc[j] * (double)cc[j]; S.nnzL_true += cc[j]; }
+    // ---- fundamental (maximal) supernodes
+    std::vector<int> sfirst;  // first column of each supernode
+    for (int j = 0; j < n; j++) {
+        bool join = j > 0 && parent[j - 1] == j && cc[j - 1] == cc[j] + 1;
+        if (!join) sfirst.push_back(j);
+    }
+    int ns = (int)sfirst.size();
+    sfirst.push_back(n);
+    std::vector<int> col2s(n);
+    for (int s = 0; s < ns; s++) for (int j = sfirst[s]; j < sfirst[s + 1]; j++) col2s[j] = s;
+    // ---- relaxed amalgamation (merge a supernode into its parent when it is the
+    //      parent's last child and few explicit zeros are introduced)
+    std::vector<int64_t> nc(ns), rr(ns), zz(ns, 0);
+    std::vector<int> sp(ns), first_of(ns);
+    std::vector<char> dead(ns, 0);
+    for (int s = 0; s < ns; s++) {
+        nc[s] = sfirst[s + 1] - sfirst[s];
+        rr[s] = cc[sfirst[s]] - nc[s];
+        int last = sfirst[s + 1] - 1;
+        sp[s] = parent[last] < 0 ? -1 : col2s[parent[last]];
+        first_of[s] = sfirst[s];
+    }
+    if (opt.relax_enable) {
+        for (int s = 0; s < ns; s++) {
+            int p = sp[s];
+            if (p < 0) continue;
+            if (first_of[s] + nc[s] != first_of[p]) continue;  // not the last (contiguous) child
+            int64_t ncm = nc[s] + nc[p];
+            int64_t newz = nc[s] * (nc[p] + rr[p] - rr[s]);
+            int64_t z = zz[s] + zz[p] + newz;
+            double total = (double)ncm * (ncm + 1) / 2.0 + (double)ncm * rr[p];
+            double frac = total > 0 ? (double)z / total : 0.0;
+            bool merge;
+            if (ncm <= opt.relax_small || newz == 0) merge = true;
+            else if (ncm <= 16) merge = frac < opt.relax_z16;
+            else if (ncm <= 32) merge = frac < opt.relax_z32;
+            else if (ncm <= 64) merge = frac < opt.relax_z64;
+            else merge = frac < opt.relax_zinf;
+            if (merge) {
+                dead[s] = 1;
+                first_of[p] = first_of[s];
+                nc[p] = ncm; zz[p] = z;
+            }
+        }
+    }
+    S.sfirst.clear();
+    for (int s = 0; s < ns; s++) if (!dead[s]) S.sfirst.push_back(first_of[s]);
+    S.nsuper = (int)S.sfirst.size();
+    S.sfirst.push_back(n);
+    S.col2super.resize(n);
+    for (int s = 0; s < S.nsuper; s++) for (int j = S.sfirst[s]; j < S.sfirst[s + 1]; j++) S.col2super[j] = s;
+    S.sparent.assign(S.nsuper, -1);
+    // ---- supernodal row structures (bottom-up union of children + own columns)
+    const int NS = S.nsuper;
+    S.child_ptr.assign(NS + 1, 0);
+    S.rowptr.assign(NS + 1, 0);
+    S.rowidx.clear();
+    {
+        std::vector<int> mark(n, -1), tmp;
+        // children are discovered as structures are built: parent(s) = super(rows(s)[0])
+        std::vector<std::vector<int>> kids(NS);
+        for (int s = 0; s < NS; s++) {
+            const int f = S.sfirst[s], l = S.sfirst[s + 1] - 1;
+            tmp.clear();
+            for (int j = f; j <= l; j++)
+                for (int64_t p = Bp[j]; p < Bp[j + 1]; p++) {
+                    int i = Bi[p];
+                    if (i > l && mark[i] != s) { mark[i] = s; tmp.push_back(i); }
+                }
+            for (int c : kids[s])
+                for (int64_t p = S.rowptr[c]; p < S.rowptr[c + 1]; p++) {
+                    int i = S.rowidx[p];
+                    if (i > l && mark[i] != s) { mark[i] = s; tmp.push_back(i); }
+                }
+            std::sort(tmp.begin(), tmp.end());
+            S.rowidx.insert(S.rowidx.end(), tmp.begin(), tmp.end());
+            S.rowptr[s + 1] = (int64_t)S.rowidx.size();
+            if (!tmp.empty()) {
+                int p = S.col2super[tmp[0]];
+                S.sparent[s] = p;
+                kids[p].push_back(s);
+            }
+            std::vector<int>().swap(kids[s]);
+        }
+    }
+    for (int s = 0; s < NS; s++) if (S.sparent[s] >= 0) S.child_ptr[S.sparent[s] + 1]++;
+    for (int s = 0; s < NS; s++) S.child_ptr[s + 1] += S.child_ptr[s];
+    S.child_list.resize(S.child_ptr[NS]);
+    {
+        std::vector<int> nxt(S.child_ptr.begin(), S.child_ptr.end() - 1);
+        for (int s = 0; s < NS; s++) if (S.sparent[s] >= 0) S.child_list[nxt[S.sparent[s]]++] = s;
+    }
+    // ---- storage offsets, levels
+    S.Loff.assign(NS + 1, 0); S.CBoff.assign(NS + 1, 0);
+    S.level.assign(NS, 0);
+    S.max_front = 0;
+    for (int s = 0; s < NS; s++) {
+        int64_t c = S.sfirst[s + 1] - S.sfirst[s], r = S.rowptr[s + 1] - S.rowptr[s];
+        S.Loff[s + 1] = S.Loff[s] + (c + r) * c;
+        S.CBoff[s + 1] = S.CBoff[s] + r * r;
+        S.max_front = std::max<int64_t>(S.max_front, c + r);
+        if (S.sparent[s] >= 0) S.level[S.sparent[s]] = std::max(S.level[S.sparent[s]], S.level[s] + 1);
+    }
+    S.nnzL = S.Loff[NS]; S.cb_total = S.CBoff[NS];
+    S.nlevels = 0;
+    for (int s = 0; s < NS; s++) S.nlevels = std::max(S.nlevels, S.level[s] + 1);
+    S.level_ptr.assign(S.nlevels + 1, 0);
+    for (int s = 0; s < NS; s++) S.level_ptr[S.level[s] + 1]++;
+    for (int l = 0; l < S.nlevels; l++) S.level_ptr[l + 1] += S.level_ptr[l];
+    S.level_list.resize(NS);
+    {
+        std::vector<int> nxt(S.level_ptr.begin(), S.level_ptr.end() - 1);
+        for (int s = 0; s < NS; s++) S.level_list[nxt[S.level[s]]++] = s;
+    }
+    // ---- relative indices of each update block inside the parent's front
+    S.rel.assign(S.rowidx.size(), -1);
+    for (int s = 0; s < NS; s++) {
+        int p = S.sparent[s];
+        if (p < 0) continue;
+        const int pf = S.sfirst[p], pl = S.sfirst[p + 1] - 1, pc = pl - pf + 1;
+        int64_t q = S.rowptr[p];
+        const int64_t qe = S.rowptr[p + 1];
+        for (int64_t t = S.rowptr[s]; t < S.rowptr[s + 1]; t++) {
+            int x = S.rowidx[t];
+            if (x <= pl) { S.rel[t] = x - pf; continue; }
+            while (q < qe && S.rowidx[q] < x) q++;
+            if (q >= qe || S.rowidx[q] != x) { S.error = "internal: child row missing from parent front"; return false; }
+            S.rel[t] = pc + (int)(q - S.rowptr[p]);
+        }
+    }
+    // ---- map M_L entries into the L panels
+    S.amap.assign(Mp[n], -1);
+    S.dpos.assign(n, -1);
+    for (int j = 0; j < n; j++)
+        for (int64_t e = Mp[j]; e < Mp[j + 1]; e++) {
+            int i = Mi[e];
+            int a = S.iperm[i], b = S.iperm[j];
+            int row = std::max(a, b), col = std::min(a, b);
+            int s = S.col2super[col];
+            const int f = S.sfirst[s], l = S.sfirst[s + 1] - 1;
+            const int64_t c = l - f + 1, r = S.rowptr[s + 1] - S.rowptr[s], ld = c + r;
+            int64_t lrow;
+            if (row <= l) lrow = row - f;
+            else {
+                const int* b0 = S.rowidx.data() + S.rowptr[s];
+                const int* b1 = S.rowidx.data() + S.rowptr[s + 1];
+                const int* it = std::lower_bound(b0, b1, row);
+                if (it == b1 || *it != row) { S.error = "internal: entry missing from supernode structure"; return false; }
+                lrow = c + (it - b0);
+            }
+            int64_t off = S.Loff[s] + lrow + (int64_t)(col - f) * ld;
+            S.amap[e] = off;
+            if (i == j) S.dpos[i] = off;
+        }
+    return true;
+}
+
+}  // namespace opb

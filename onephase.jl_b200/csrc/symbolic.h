@@ -1,0 +1,83 @@
+// Host-side symbolic analysis for the B200 KKT path: runs once per sparsity
+// pattern and is reused across IPM iterations (the reference redoes CHOLMOD's
+// analyze on every ls_factor! call, linear_system_solvers/julia.jl:34, because
+// linear_solver_recycle=false, parameters.jl:38).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace opb {
+
+struct SymOptions {
+    int nd_leaf = 96;          // nested dissection stops at parts of this size
+    int ordering = 0;          // 0 = nested dissection + min-degree leaves, 1 = natural, 2 = user perm
+    double relax_small = 8;    // always merge a last child when merged width <= this
+    double relax_z16 = 0.8, relax_z32 = 0.3, relax_z64 = 0.1, relax_zinf = 0.05;
+    int relax_enable = 1;
+};
+
+// Pattern of M_L = tril(J' D J + H) with full diagonal, and the gather map
+// that assembles it (schur.jl:55: Q = J_T * Diagonal(y./s) * J + H).
+struct SchurPattern {
+    int n = 0, m = 0;
+    int64_t nnzJ = 0, nnzH = 0;
+    std::vector<int64_t> Mp;     // n+1
+    std::vector<int> Mi;         // nnzM, sorted in each column, first entry = diagonal
+    std::vector<int64_t> pair_ptr;   // nnzM+1
+    std::vector<int> pairA, pairB;   // positions in J.nzval: A -> J[k,row], B -> J[k,col]
+    std::vector<int> hmap;       // nnzM: position in H.nzval or -1
+    std::vector<int> Jrow;       // nnzJ: 0-based row of every J entry (CSC order)
+    std::vector<int64_t> Jp;     // n+1, 0-based
+    // CSR view of J for J*x products
+    std::vector<int64_t> Rp;     // m+1
+    std::vector<int> Rcol, Rpos; // nnzJ
+    // symmetric (both triangles) CSR view of H for H_sym*v
+    std::vector<int64_t> Sp;     // n+1
+    std::vector<int> Scol, Spos; // 2*nnzH - ndiag
+};
+
+struct Symbolic {
+    int n = 0;
+    std::vector<int> perm, iperm;        // perm[new] = old
+    int nsuper = 0;
+    std::vector<int> sfirst;             // nsuper+1, permuted column ranges
+    std::vector<int> sparent;            // supernodal elimination tree (-1 = root)
+    std::vector<int64_t> rowptr;         // nsuper+1
+    std::vector<int> rowidx;             // below-diagonal rows of each supernode (permuted, sorted)
+    std::vector<int> rel;                // same shape as rowidx: position in the parent's front
+    std::vector<int64_t> Loff;           // nsuper+1: panel (c+r) x c, column-major, ld = c+r
+    std::vector<int64_t> CBoff;          // nsuper+1: update block r x r, column-major, ld = r
+    std::vector<int> level;              // height above the leaves
+    int nlevels = 0;
+    std::vector<int> level_ptr, level_list;  // supernodes grouped by level
+    std::vector<int> child_ptr, child_list;  // children of each supernode (ascending)
+    std::vector<int64_t> amap;           // per M_L entry: destination offset in L storage
+    std::vector<int64_t> dpos;           // per original variable: offset of its diagonal in L
+    std::vector<int> col2super;          // permuted column -> supernode
+    int64_t nnzL = 0;                    // sum (c+r)*c
+    int64_t nnzL_true = 0;               // entries of the trapezoids (lower part only)
+    int64_t cb_total = 0;
+    double flops = 0;                    // sum_j colcount_j^2
+    int max_front = 0;
+    std::string error;
+};
+
+// index_base: 0 or 1.  Returns false and sets err on invalid input.
+bool build_schur_pattern(int64_t n, int64_t m, const int64_t* Jp, const int64_t* Ji,
+                         const int64_t* Hp, const int64_t* Hi, int index_base,
+                         SchurPattern& out, std::string& err);
+
+// Pattern from a user CSC matrix (L1-compat path, julia.jl:21-97): only entries
+// with row >= col are read; the full diagonal is always present.  src[e] is the
+// position in the caller's nzval or -1 for an inserted diagonal.
+bool build_csc_pattern(int64_t n, const int64_t* Ap, const int64_t* Ai, int index_base,
+                       std::vector<int64_t>& Mp, std::vector<int>& Mi, std::vector<int64_t>& src,
+                       std::string& err);
+
+bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
+             const SymOptions& opt, const int64_t* user_perm, Symbolic& S);
+
+uint64_t pattern_hash(int64_t n, const int64_t* p, const int64_t* i, int64_t nnz);
+
+}  // namespace opb

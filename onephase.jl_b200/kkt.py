@@ -1,0 +1,339 @@
+"""Host-side mirror of the reference's two plugin interfaces for the KKT path,
+bound to libonephase_b200.so.  Julia is not available in this image, so this
+Python mirror is what the parity tests drive; the Julia shim with the same
+structure is in julia/ (INTEGRATION.md).  Names, argument meaning and error
+behaviour follow the reference (Julia's `!` suffix is dropped):
+
+  linear_solver_B200      <: abstract_linear_system_solver
+      initialize / finalize / ls_factor / ls_solve_inplace (ls_solve!) / ls_solve
+      (src/linear_system_solvers/linear_system_solvers.jl:11,40-46; julia.jl:1-113)
+  Schur_B200_KKT_solver   <: abstract_schur_solver
+      form_system / update_delta_vecs / factor_implementation /
+      compute_direction_implementation / kkt_associate_rhs, plus the generic
+      factor / compute_direction / update_delta / diag_min
+      (src/kkt_system_solver/kkt_system_solver.jl:10-25,98-113,178-204,291-294;
+       schur.jl:3-182)
+  ipopt_strategy          (src/IPM/delta_strategy.jl:37-114), specialised on the
+      B200 solver so the whole delta loop runs on the device
+  pick_KKT_solver         (kkt_system_solver.jl:232-287) with the new symbols
+      kkt_solver_type = :schur_b200, linear_solver_type = :b200
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+
+
+# ---------------------------------------------------------------------------
+# parameter mirror (src/parameters.jl:17-45,147-158)
+# ---------------------------------------------------------------------------
+@dataclass
+class Class_delta_pars:
+    max: float = 1e50
+    start: float = 1e-6
+    zero: float = 0.0
+    min: float = 1e-12
+    inc: float = 8.0
+    dec: float = 1.0 / np.pi
+
+
+@dataclass
+class Class_kkt_pars:
+    ItRefine_Num: int = 3
+    ItRefine_BigFloat: bool = False
+    kkt_solver_type: str = "schur_b200"
+    linear_solver_type: str = "b200"
+    linear_solver_safe_mode: bool = False
+    linear_solver_recycle: bool = False
+
+
+@dataclass
+class Class_parameters:
+    output_level: int = 0
+    kkt: Class_kkt_pars = field(default_factory=Class_kkt_pars)
+    delta: Class_delta_pars = field(default_factory=Class_delta_pars)
+    device: int = 0
+
+
+@dataclass
+class Class_point:
+    """utils/Class_point.jl:2-13 (only the fields the path touches)."""
+    x: np.ndarray
+    y: np.ndarray
+    s: np.ndarray
+    mu: float = 0.0
+    primal_scale: float = 1.0
+
+
+@dataclass
+class Class_iterate:
+    """The slice of Class_iterate (utils/Class_iterate.jl:4-84) the path reads:
+    cached J (m x n CSC), H (lower CSC), point.y, point.s and local_info.delta."""
+    J: sp.csc_matrix
+    H: sp.csc_matrix
+    y: np.ndarray
+    s: np.ndarray
+    delta: float = 0.0     # get_delta(iter)
+    mu: float = 0.0
+    primal_scale: float = 1.0
+
+
+@dataclass
+class System_rhs:
+    """system_rhs.jl:39-74."""
+    dual_r: np.ndarray
+    primal_r: np.ndarray
+    comp_r: np.ndarray
+
+
+@dataclass
+class Class_kkt_error:
+    """kkt_system_solver.jl:49-65."""
+    error_D: float = 0.0
+    error_P: float = 0.0
+    error_mu: float = 0.0
+    overall: float = 0.0
+    rhs_norm: float = 0.0
+    ratio: float = 0.0
+
+
+def dim(it):
+    return it.J.shape[1]
+
+
+def ncon(it):
+    return it.J.shape[0]
+
+
+def get_delta(it):
+    return it.delta
+
+
+def set_delta(it, d):
+    it.delta = d
+
+
+def _csc(A):
+    A = sp.csc_matrix(A)
+    if not A.has_sorted_indices:
+        A = A.copy(); A.sort_indices()
+    return A
+
+
+# ---------------------------------------------------------------------------
+# L1: linear system solver
+# ---------------------------------------------------------------------------
+class linear_solver_B200:
+    """Drop-in for linear_solver_JULIA (julia.jl:1-19)."""
+
+    def __init__(self, sym, safe_mode=False, recycle=False, device=0):
+        if sym not in ("definite", "symmetric"):
+            # julia.jl:92: error("this.options.sym = ... not supported"); :unsymmetric is dead upstream
+            raise ValueError("this.options.sym = %s not supported" % sym)
+        self.sym = sym
+        self.safe_mode = safe_mode
+        self.recycle = recycle   # symbolic analysis is always reused (pattern-hash cache)
+        self.device = device
+        self._h = None
+        self._factor_defined = False
+
+    def initialize(self):
+        if self._h is None:
+            self._h = _lib.Handle(self.device)
+
+    def finalize(self):
+        if self._h is not None:
+            self._h.close(); self._h = None
+        self._factor_defined = False
+
+    def ls_factor(self, SparseMatrix, n, m, timer=None):
+        """julia.jl:21-97.  Returns 1 when the inertia is (n, m), else 0."""
+        self.initialize()
+        Q = _csc(SparseMatrix)
+        if self.sym == "definite":
+            assert m == 0
+            mode = _lib.MODE_CHOLESKY
+        else:
+            mode = _lib.MODE_LDLT
+        ok = self._h.ls_factor_csc(Q.shape[0], Q.indptr, Q.indices, Q.data, 0, mode, n, m)
+        self._factor_defined = True
+        return ok
+
+    def ls_solve_inplace(self, my_rhs, my_sol, timer=None):
+        """ls_solve!  (julia.jl:99-103)."""
+        self._h.ls_solve(np.asarray(my_rhs, dtype=np.float64), out=my_sol)
+
+    def ls_solve(self, my_rhs, timer=None):
+        """julia.jl:105-113; a sparse rhs is densified like Vector(my_rhs)."""
+        if sp.issparse(my_rhs):
+            my_rhs = np.asarray(my_rhs.todense()).ravel()
+        return self._h.ls_solve(np.asarray(my_rhs, dtype=np.float64))
+
+
+# ---------------------------------------------------------------------------
+# L2: KKT system solver
+# ---------------------------------------------------------------------------
+class Schur_B200_KKT_solver:
+    """Drop-in for Schur_KKT_solver (schur.jl:3-31).  The matrix Q, its factor and
+    the cached (J, H, y, s) of factor_it live in HBM behind one opb handle."""
+
+    def __init__(self, device=0):
+        self.ls_solver = None
+        self.factor_it = None
+        self.delta_x_vec = None
+        self.delta_s_vec = None
+        self.rhs = None
+        self.dir = None
+        self.kkt_err_norm = Class_kkt_error()
+        self.rhs_norm = 0.0
+        self.pars = None
+        self.schur_diag = None
+        self.ready = "not_ready"
+        self.Q = None            # host copy of tril(Q), materialised on demand (is_diag_dom)
+        self.current_it = None
+        self.reduct_factors = None
+        self.device = device
+        self._h = None
+        self._delta = 0.0
+        self._diag_min = np.nan
+        self._pattern_key = None
+
+    # -- initialize!(kkt_solver, it)  kkt_system_solver.jl:21-25
+    def initialize(self, initial_it):
+        if self._h is None:
+            self._h = _lib.Handle(self.device)
+        self.dir = Class_point(np.zeros(dim(initial_it)), np.zeros(ncon(initial_it)), np.zeros(ncon(initial_it)))
+
+    def finalize(self):
+        if self._h is not None:
+            self._h.close(); self._h = None
+
+    def set_permutation(self, perm):
+        self._h.set_permutation(perm)
+        self._pattern_key = None
+
+    # -- form_system!  schur.jl:47-62
+    def form_system(self, it, timer=None):
+        J = _csc(it.J); H = _csc(it.H)
+        key = (J.shape, J.indptr.tobytes() if J.nnz < 1 << 16 else hash(J.indptr.tobytes()),
+               hash(J.indices.tobytes()), hash(H.indptr.tobytes()), hash(H.indices.tobytes()))
+        if key != self._pattern_key:
+            # pattern changed (Class_cutest.jl:490-502 can drop numerical zeros): new symbolic analysis
+            self._h.set_structure(J.shape[1], J.shape[0], J.indptr, J.indices, H.indptr, H.indices, 0)
+            self._pattern_key = key
+        self.schur_diag, self._diag_min = self._h.form(J.data, H.data, it.y, it.s)
+        self.factor_it = it
+        self.Q = None
+        self.ready = "system_formed"
+
+    def get_Q(self):
+        """Lower triangle of Q with the current shift, as scipy CSC (for is_diag_dom)."""
+        cp, ri = self._h.M_pattern()
+        v = self._h.M_values()
+        Q = sp.csc_matrix((v, ri, cp), shape=(self._h.n, self._h.n))
+        Q.setdiag(self.schur_diag + (self._delta if self.delta_x_vec is not None else 0.0))
+        return Q
+
+    # -- update_delta!/update_delta_vecs!  kkt_system_solver.jl:109-113, schur.jl:64-83
+    def update_delta(self, delta_x, delta_s, timer=None):
+        n = dim(self.factor_it)
+        self.update_delta_vecs(delta_x * np.ones(n), delta_s * self.factor_it.s ** (-2.0), timer)
+
+    def update_delta_vecs(self, delta_x_vec, delta_s_vec, timer=None):
+        self.delta_x_vec = delta_x_vec
+        self.delta_s_vec = delta_s_vec
+        if np.sum(np.abs(delta_s_vec)) > 0.0:
+            raise RuntimeError("Not implemented")          # schur.jl:71
+        if delta_x_vec.size and np.any(delta_x_vec != delta_x_vec[0]):
+            raise RuntimeError("Not implemented: non-uniform delta_x_vec")
+        self._delta = float(delta_x_vec[0]) if delta_x_vec.size else 0.0
+        self.ready = "delta_updated"
+
+    # -- factor!  kkt_system_solver.jl:98-107,190-204
+    def factor(self, delta_x, timer=None, delta_s=0.0):
+        self.update_delta(delta_x, delta_s, timer)
+        return self._factor(timer)
+
+    def _factor(self, timer=None):
+        if self.ready != "delta_updated":
+            raise RuntimeError("kkt solver not ready to factor kkt_solver.ready = %s != :delta_updated" % self.ready)
+        self.ready = "factored"
+        return self.factor_implementation(timer)
+
+    def factor_implementation(self, timer=None):
+        return self._h.factor(self._delta)
+
+    # -- kkt_associate_rhs!  schur.jl:34-45
+    def kkt_associate_rhs(self, it, rhs, reduct_factors=None, timer=None):
+        """The reference builds System_rhs(iter, reduct_factors) from the NLP
+        (system_rhs.jl:57-73); the NLP lives outside the path, so the caller
+        passes the three vectors."""
+        self.rhs = rhs
+        if reduct_factors is not None:
+            self.dir.mu = -(1.0 - reduct_factors[2]) * it.mu
+            self.dir.primal_scale = -(1.0 - reduct_factors[0]) * it.primal_scale
+        self.reduct_factors = reduct_factors
+        self.current_it = it
+
+    # -- compute_direction!  kkt_system_solver.jl:178-188
+    def compute_direction(self, timer=None):
+        if self.ready != "factored":
+            raise RuntimeError("kkt solver not ready to compute direction!")
+        self.compute_direction_implementation(timer)
+        for v in (self.dir.x, self.dir.y, self.dir.s):      # check_for_nan, IPM_tools.jl:32-49
+            if np.isnan(v).any():
+                raise FloatingPointError("NaN in direction")
+
+    def compute_direction_implementation(self, timer=None):
+        n_ref = self.pars.kkt.ItRefine_Num if self.pars is not None else 3
+        dx, dy, ds, err = self._h.direction(self.rhs.dual_r, self.rhs.primal_r, self.rhs.comp_r, n_ref)
+        self.dir.x, self.dir.y, self.dir.s = dx, dy, ds
+        self.kkt_err_norm = Class_kkt_error(*[float(v) for v in err])
+        self.rhs_norm = float(err[4])
+
+    def diag_min(self):
+        return self._diag_min
+
+
+def diag_min(kkt_solver):
+    """kkt_system_solver.jl:291-294."""
+    return kkt_solver.diag_min()
+
+
+def ipopt_strategy(it, kkt_solver, pars, timer=None):
+    """delta_strategy.jl:37-114 for the B200 solver: one library call runs the
+    probe at delta.zero, the first shift and the x8 retries on the device.
+    Returns (status, num_fac, delta) with status 'success' or 'failure'."""
+    if kkt_solver.ready not in ("system_formed", "delta_updated", "factored"):
+        raise RuntimeError("kkt solver not ready to factor")
+    d = pars.delta
+    st, num_fac, delta = kkt_solver._h.factor_delta_loop(get_delta(it), d.zero, d.min, d.max, d.start,
+                                                         d.inc, d.dec, 500)
+    n = dim(it)
+    kkt_solver.delta_x_vec = delta * np.ones(n)
+    kkt_solver.delta_s_vec = np.zeros(ncon(it))
+    kkt_solver._delta = delta
+    kkt_solver.ready = "factored"
+    if st == 1:
+        return "success", num_fac, delta
+    if st == 0:
+        return "failure", num_fac, delta
+    raise RuntimeError("max it")                         # delta_strategy.jl:113
+
+
+def pick_KKT_solver(pars):
+    """kkt_system_solver.jl:232-287 extended with the B200 symbols."""
+    t, ls = pars.kkt.kkt_solver_type, pars.kkt.linear_solver_type
+    if t == "schur_b200":
+        if ls != "b200":
+            raise ValueError("pick a valid solver!")
+        k = Schur_B200_KKT_solver(pars.device)
+        k.ls_solver = linear_solver_B200("definite", pars.kkt.linear_solver_safe_mode,
+                                         pars.kkt.linear_solver_recycle, pars.device)
+    else:
+        raise ValueError("pick a solver!")
+    k.kkt_err_norm = Class_kkt_error()
+    k.pars = pars
+    return k

@@ -1,0 +1,141 @@
+"""numpy emulation of the device algorithms driven by the symbolic structures the
+library exports (test infrastructure: lets the CPU-only suite validate the gather
+map, ordering, supernode structures, extend-add maps and panel offsets that the
+CUDA kernels consume, before any GPU time is spent)."""
+import numpy as np
+
+
+class Sym:
+    def __init__(self, h):
+        g = h.symbolic
+        self.n = int(h.info("n"))
+        self.perm = g("perm"); self.sfirst = g("sfirst"); self.sparent = g("sparent")
+        self.rowptr = g("rowptr"); self.rowidx = g("rowidx"); self.rel = g("rel")
+        self.Loff = g("Loff"); self.CBoff = g("CBoff"); self.level = g("level")
+        self.amap = g("amap"); self.dpos = g("dpos"); self.Mp = g("Mp"); self.Mi = g("Mi")
+        self.nsuper = len(self.sfirst) - 1
+        self.nnzL = int(h.info("nnzL"))
+
+
+def assemble_M(h, Jx, Hx, y, s):
+    """tril(J'DJ + H) through the gather map, in the kernel's operation order."""
+    pp = h.symbolic("pair_ptr"); A = h.symbolic("pairA"); B = h.symbolic("pairB"); hm = h.symbolic("hmap")
+    sig = y / s
+    n = int(h.info("n"))
+    # row of every J entry
+    T = None
+    nnzM = len(hm)
+    M = np.zeros(nnzM)
+    return pp, A, B, hm, sig
+
+
+def assemble_M_values(h, Jp, Ji, Jx, Hx, y, s):
+    pp = h.symbolic("pair_ptr"); A = h.symbolic("pairA"); B = h.symbolic("pairB"); hm = h.symbolic("hmap")
+    sig = y / s
+    T = Jx * sig[Ji]
+    nnzM = len(hm)
+    M = np.zeros(nnzM)
+    prod = T[A] * Jx[B]
+    for e in range(nnzM):
+        t0, t1 = pp[e], pp[e + 1]
+        have = False
+        acc = 0.0
+        if t1 > t0:
+            acc = prod[t0]
+            for t in range(t0 + 1, t1):
+                acc = acc + prod[t]
+            have = True
+        if hm[e] >= 0:
+            acc = acc + Hx[hm[e]] if have else Hx[hm[e]]
+        M[e] = acc
+    return M
+
+
+def factor(S, Mval, delta, mode="chol"):
+    """Multifrontal factorisation with the exported maps.  Returns (ok, Lval)."""
+    L = np.zeros(S.nnzL)
+    L[S.amap] = Mval
+    L[S.dpos] += delta
+    CB = {}
+    children = [[] for _ in range(S.nsuper)]
+    for s in range(S.nsuper):
+        if S.sparent[s] >= 0:
+            children[S.sparent[s]].append(s)
+    order = np.argsort(S.level, kind="stable")
+    for s in order:
+        f = S.sfirst[s]; c = S.sfirst[s + 1] - f
+        r = S.rowptr[s + 1] - S.rowptr[s]; N = c + r
+        F = np.zeros((N, N))
+        F[:, :c] = L[S.Loff[s]:S.Loff[s] + N * c].reshape(c, N).T
+        for ch in children[s]:
+            rel = S.rel[S.rowptr[ch]:S.rowptr[ch + 1]]
+            cb = CB.pop(ch)
+            idx = np.ix_(rel, rel)
+            F[idx] += np.tril(cb)
+        for j in range(c):
+            d = F[j, j]
+            if mode == "chol":
+                if not (d > 0):
+                    return False, L
+                ljj = np.sqrt(d)
+                F[j + 1:, j] /= ljj
+                F[j, j] = ljj
+                col = F[j + 1:, j]
+                F[j + 1:, j + 1:] -= np.tril(np.outer(col, col))
+            else:
+                if d == 0 or d != d:
+                    return False, L
+                w = F[j + 1:, j].copy()
+                F[j + 1:, j] = w / d
+                F[j + 1:, j + 1:] -= np.tril(np.outer(F[j + 1:, j], w))
+        L[S.Loff[s]:S.Loff[s] + N * c] = F[:, :c].T.reshape(-1)
+        CB[s] = F[c:, c:].copy()
+    return True, L
+
+
+def solve(S, L, b, mode="chol"):
+    n = S.n
+    x = b[S.perm].astype(float).copy()
+    u = {}
+    children = [[] for _ in range(S.nsuper)]
+    for s in range(S.nsuper):
+        if S.sparent[s] >= 0:
+            children[S.sparent[s]].append(s)
+    order = np.argsort(S.level, kind="stable")
+    panels = {}
+    for s in order:
+        f = S.sfirst[s]; c = S.sfirst[s + 1] - f
+        r = S.rowptr[s + 1] - S.rowptr[s]; N = c + r
+        P = L[S.Loff[s]:S.Loff[s] + N * c].reshape(c, N).T
+        panels[s] = P
+        us = np.zeros(r)
+        for ch in children[s]:
+            rel = S.rel[S.rowptr[ch]:S.rowptr[ch + 1]]
+            uc = u.pop(ch)
+            for t, dst in enumerate(rel):
+                if dst < c:
+                    x[f + dst] += uc[t]
+                else:
+                    us[dst - c] += uc[t]
+        L11 = np.tril(P[:c, :c])
+        if mode != "chol":
+            L11 = np.tril(L11, -1) + np.eye(c)
+        yv = np.linalg.solve(L11, x[f:f + c]) if c else x[f:f + c]
+        x[f:f + c] = yv
+        us -= P[c:, :c] @ yv
+        u[s] = us
+    for s in order[::-1]:
+        f = S.sfirst[s]; c = S.sfirst[s + 1] - f
+        r = S.rowptr[s + 1] - S.rowptr[s]
+        P = panels[s]
+        rows = S.rowidx[S.rowptr[s]:S.rowptr[s + 1]]
+        L11 = np.tril(P[:c, :c])
+        rhs = x[f:f + c].copy()
+        if mode != "chol":
+            rhs = rhs / np.diag(P[:c, :c])
+            L11 = np.tril(L11, -1) + np.eye(c)
+        rhs -= P[c:, :c].T @ x[rows]
+        x[f:f + c] = np.linalg.solve(L11.T, rhs)
+    out = np.empty(n)
+    out[S.perm] = x
+    return out

