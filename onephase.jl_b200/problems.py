@@ -114,10 +114,11 @@ TOY_NAMES = ["readme"] + ["toy_lp%d" % i for i in range(9)]
 # ---------------------------------------------------------------------------
 # C2: banded collocation stand-in for COPS chain / camshape
 # ---------------------------------------------------------------------------
-def chain(nh=2500, seed=0, neq=3, indefinite=False):
+def chain(nh=2500, seed=0, neq=3, neg_curv=0.0, offdiag_curv=0.0):
     """nh intervals, 4 variables per node, `neq` equalities per interval each
     touching the 8 variables of two adjacent nodes (duplicated with sign), plus
-    lower and upper bound rows on every variable.  n = 4(nh+1)."""
+    lower and upper bound rows on every variable.  n = 4(nh+1).  H is block
+    diagonal (4x4 lower blocks), shifted by -neg_curv*I."""
     rng = np.random.default_rng(seed)
     n = 4 * (nh + 1)
     k = np.arange(nh)
@@ -134,9 +135,11 @@ def chain(nh=2500, seed=0, neq=3, indefinite=False):
     bi, bj = np.tril_indices(4)
     nb = nh + 1
     B = rng.standard_normal((nb, 4, 4))
-    B = B @ B.transpose(0, 2, 1) * 0.25 + (0.0 if indefinite else 0.5) * np.eye(4)
-    if indefinite:
-        B -= 0.6 * np.eye(4)
+    # neg_curv > 0 makes the Hessian blocks indefinite so the delta loop has work to do
+    B = B @ B.transpose(0, 2, 1) * 0.25 + (0.5 - neg_curv) * np.eye(4)
+    # offdiag_curv = g adds g*(ones - I): eigenvalues 3g and -g (x3) with a zero diagonal, i.e.
+    # negative curvature that the diagonal test of the delta rule cannot see (probe fails, x8 retries)
+    B = B + offdiag_curv * (np.ones((4, 4)) - np.eye(4))
     hr = (4 * np.arange(nb)[:, None] + bi[None, :]).ravel()
     hc = (4 * np.arange(nb)[:, None] + bj[None, :]).ravel()
     H = _csc(sp.csc_matrix((B[:, bi, bj].ravel(), (hr, hc)), shape=(n, n)))
@@ -275,29 +278,27 @@ def grid_nd_perm(N, leaf=4):
 # ---------------------------------------------------------------------------
 # IPM-like sequence: same pattern, drifting (y, s), occasionally indefinite H
 # ---------------------------------------------------------------------------
-def ipm_sequence(prob: KKTProblem, steps=6, seed=0, indefinite_every=3, shift=0.75):
+def ipm_sequence(prob: KKTProblem, steps=6, seed=0, indefinite_every=3, shift=5.0):
     """Yield KKTProblems sharing prob's sparsity pattern, mimicking outer
-    iterations: s*y is driven towards a shrinking mu and every
-    `indefinite_every`-th iterate gets H - shift*I on its stored diagonal so the
-    delta loop (delta_strategy.jl:37-114) has work to do."""
+    iterations: s*y is driven towards a shrinking mu, J's values drift, and every
+    `indefinite_every`-th iterate gets `shift` subtracted from H's stored diagonal
+    so the delta loop (delta_strategy.jl:37-114) has work to do.  delta_prev is
+    left at 0; the caller threads the accepted delta through like one_phase.jl:205-206."""
     rng = np.random.default_rng(seed)
     y = prob.y.copy(); s = prob.s.copy()
-    mu = float(np.mean(y * s))
+    mu = float(np.exp(np.mean(np.log(y * s))))
+    H0 = prob.H
+    # positions of the stored diagonal entries of H (lower CSC: first entry of a column if row == col)
+    cols = np.repeat(np.arange(prob.n), np.diff(H0.indptr))
+    dpos = np.nonzero(H0.indices == cols)[0]
     for t in range(steps):
         mu *= 0.3
         s = np.sqrt(s * (mu / y)) * np.exp(0.3 * rng.standard_normal(s.shape[0]))
         y = mu / s * np.exp(0.1 * rng.standard_normal(s.shape[0]))
-        H = prob.H.copy()
+        H = H0.copy()
         if indefinite_every and (t % indefinite_every) == indefinite_every - 1:
-            H = H.copy()
-            d = H.diagonal()
-            H = _csc(H - sp.diags(np.where(d != 0, shift, 0.0)))
-            # keep the pattern identical (explicit zeros may have been dropped)
-            if H.nnz != prob.H.nnz:
-                H = _csc(prob.H + 0 * H)
-                H.data = prob.H.data.copy()
-                dd = H.diagonal()
-                Hl = H.tolil(); Hl.setdiag(dd - shift); H = _csc(Hl)
+            H.data = H.data.copy()
+            H.data[dpos] -= shift
         J = prob.J.copy()
         J.data = prob.J.data * (1.0 + 0.01 * rng.standard_normal(J.nnz))
         yield KKTProblem("%s_it%d" % (prob.name, t), J, H, y.copy(), s.copy(),

@@ -1,0 +1,86 @@
+"""The C-ABI library loads without a GPU, exports every symbol the header declares,
+and refuses numeric work on a host-only handle (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_match_header(pkg):
+    hdr = open(os.path.join(ROOT, "include", "onephase_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(opb_[a-zA-Z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    L = ctypes.CDLL(pkg._lib.LIB_PATH)
+    for sym in declared:
+        assert hasattr(L, sym), "library does not export %s" % sym
+    assert sorted(pkg._lib.EXPORTS) == declared
+
+
+def test_version_and_launch_counter(pkg):
+    L = pkg._lib.load()
+    assert b"sm_100a" in L.opb_version()
+    assert pkg.launch_count() >= 0
+
+
+def test_library_is_sm100a_only(pkg):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", pkg._lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_numeric_calls_fail_loudly_without_device(pkg):
+    prob = pkg.problems.chain(5, seed=0)
+    h = pkg.Handle(-1)
+    h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
+    with pytest.raises(pkg.OPBError) as e:
+        h.form(prob.J.data, prob.H.data, prob.y, prob.s)
+    assert e.value.code == pkg._lib.OPB_ERR_NO_DEVICE
+    for call in (lambda: h.factor(0.0), lambda: h.factor_delta_loop(0.0),
+                 lambda: h.direction(*prob.rhs[0]), lambda: h.ls_solve(np.zeros(prob.n)),
+                 lambda: h.ls_factor_csc(2, [0, 1, 2], [0, 1], [1.0, 1.0], 0, 0, 2, 0)):
+        with pytest.raises(pkg.OPBError) as e:
+            call()
+        assert e.value.code == pkg._lib.OPB_ERR_NO_DEVICE
+
+
+def test_no_gpu_means_create_fails(pkg, have_gpu):
+    if have_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.OPBError) as e:
+        pkg.Handle(0)
+    assert e.value.code == pkg._lib.OPB_ERR_CUDA
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package or include/ refers to it."""
+    bad = []
+    for base in ("onephase.jl_b200", "include", "julia"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cpp", ".h", ".jl")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"(import\s+oracle|from\s+oracle|kkt_oracle|libkkt_oracle)", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def test_host_mirror_state_machine(pkg):
+    """ready-state errors of kkt_system_solver.jl:181-183,195-199 without touching the device."""
+    k = pkg.Schur_B200_KKT_solver()
+    with pytest.raises(RuntimeError, match="not ready to compute direction"):
+        k.compute_direction()
+    with pytest.raises(RuntimeError, match="not ready to factor"):
+        k._factor()
+    with pytest.raises(ValueError):
+        pkg.linear_solver_B200("unsymmetric")
+    pars = pkg.Class_parameters()
+    pars.kkt.linear_solver_type = "julia"
+    with pytest.raises(ValueError, match="pick a valid solver"):
+        pkg.pick_KKT_solver(pars)

@@ -85,7 +85,7 @@ def test_chain(pkg, orc, nh):
 
 
 def test_chain_indefinite_delta_sequence(pkg, orc):
-    p = pkg.problems.chain(nh=300, seed=1, indefinite=True)
+    p = pkg.problems.chain(nh=300, seed=1, offdiag_curv=25.0)
     nf, delta = _compare(pkg, orc, p, delta_prev=0.0)
     assert nf >= 2
     nf2, delta2 = _compare(pkg, orc, p, delta_prev=delta)   # warm start from the previous delta

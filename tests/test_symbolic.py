@@ -1,0 +1,158 @@
+"""CPU tests of the host-side symbolic analysis (csrc/symbolic.cpp) through a
+host-only handle (device_id = -1): the gather map, ordering, supernodes,
+extend-add maps and panel offsets that the CUDA kernels consume are validated by
+emulating the device algorithms in numpy (tests/emulate.py) and comparing with the
+oracle.  No numeric library call is made (there is no CPU fallback to call)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import emulate
+
+
+def _handle(pkg, prob, **opts):
+    h = pkg.Handle(-1)
+    for k, v in opts.items():
+        h.set_option(k, v)
+    h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
+    return h
+
+
+def _problems(pkg):
+    P = pkg.problems
+    return [P.toy(nm) for nm in P.TOY_NAMES] + [
+        P.chain(50, seed=1), P.sparse_qp(600, 300, win=5, seed=2), P.elec(20, seed=3), P.pde_control(6, seed=4)]
+
+
+@pytest.mark.parametrize("opts", [{}, {"relax": 0}, {"nd_leaf": 8}, {"ordering": 1}])
+def test_maps_reproduce_oracle(pkg, orc, opts):
+    for prob in _problems(pkg):
+        h = _handle(pkg, prob, **opts)
+        S = emulate.Sym(h)
+        assert sorted(S.perm.tolist()) == list(range(prob.n))
+        # gather map -> tril(Q) bit for bit
+        Mv = emulate.assemble_M_values(h, prob.J.indptr, prob.J.indices, prob.J.data, prob.H.data, prob.y, prob.s)
+        Q, sd = orc.form_system(prob.J, prob.H, prob.y, prob.s)
+        QL = sp.tril(Q, format="csc"); QL.sort_indices()
+        assert np.array_equal(S.Mp, QL.indptr) or prob.H.nnz == 0   # LP: diagonal may be inserted
+        M = sp.csc_matrix((Mv, S.Mi, S.Mp), shape=(prob.n, prob.n))
+        assert abs(M - QL).max() == 0.0 if (M - QL).nnz else True
+        assert np.all(S.Mi[S.Mp[:-1]] == np.arange(prob.n)), "diagonal must lead every column"
+        # multifrontal emulation with the exported maps == oracle factor/solve
+        delta = 0.5 + abs(min(sd.min(), 0.0)) * 2 + (300.0 if prob.name.startswith("elec") else 0.0)
+        F = orc.Factor(QL, S.perm)
+        ok_o = F.factorize(QL.data, sd + delta)
+        ok, L = emulate.factor(S, Mv, delta)
+        assert ok == bool(ok_o)
+        if ok:
+            b = prob.rhs[0][0]
+            x = emulate.solve(S, L, b)
+            xo = F.solve(b)
+            assert np.linalg.norm(x - xo) <= 1e-10 * np.linalg.norm(xo)
+            # same pivots as the simplicial oracle under the same permutation
+            assert np.allclose(np.sort(L[S.dpos]), np.sort(F.diag()), rtol=1e-9)
+            assert int(h.info("nnzL_true")) == F.lnz     # skeleton column counts are exact
+        h.close()
+
+
+def test_ldlt_emulation_inertia(pkg, orc):
+    prob = pkg.problems.chain(20, seed=5, neg_curv=3.0)
+    h = _handle(pkg, prob)
+    S = emulate.Sym(h)
+    Mv = emulate.assemble_M_values(h, prob.J.indptr, prob.J.indices, prob.J.data, prob.H.data, prob.y, prob.s)
+    ok, L = emulate.factor(S, Mv, 0.0, mode="ldlt")
+    Q, sd = orc.form_system(prob.J, prob.H, prob.y, prob.s)
+    QL = sp.tril(Q, format="csc")
+    F = orc.Factor(QL, S.perm)
+    assert F.factorize(QL.data, mode="ldlt") == int(ok)
+    if ok:
+        d = L[S.dpos]
+        do = F.diag()
+        assert (d > 0).sum() == (do > 0).sum() and (d < 0).sum() == (do < 0).sum()
+        b = prob.rhs[0][0]
+        assert np.linalg.norm(emulate.solve(S, L, b, mode="ldlt") - F.solve(b)) <= 1e-9 * np.linalg.norm(F.solve(b))
+
+
+def test_structure_invariants(pkg):
+    prob = pkg.problems.sparse_qp(3000, 1500, seed=7)
+    h = _handle(pkg, prob)
+    S = emulate.Sym(h)
+    ns = S.nsuper
+    assert S.sfirst[0] == 0 and S.sfirst[-1] == prob.n and np.all(np.diff(S.sfirst) > 0)
+    for s in range(ns):
+        rows = S.rowidx[S.rowptr[s]:S.rowptr[s + 1]]
+        assert np.all(np.diff(rows) > 0)
+        if len(rows):
+            assert rows[0] >= S.sfirst[s + 1]
+            p = S.sparent[s]
+            assert p > s and S.sfirst[p] <= rows[0] < S.sfirst[p + 1]
+            assert S.level[p] > S.level[s]
+            rel = S.rel[S.rowptr[s]:S.rowptr[s + 1]]
+            assert np.all(np.diff(rel) > 0)
+            # rel really points at the same global row in the parent's front
+            pc = S.sfirst[p + 1] - S.sfirst[p]
+            prow = np.concatenate([np.arange(S.sfirst[p], S.sfirst[p + 1]), S.rowidx[S.rowptr[p]:S.rowptr[p + 1]]])
+            assert np.array_equal(prow[rel], rows)
+            assert rel.max() < pc + (S.rowptr[p + 1] - S.rowptr[p])
+        else:
+            assert S.sparent[s] == -1
+    # panels tile the L storage exactly, maps are injective
+    c = np.diff(S.sfirst); r = np.diff(S.rowptr)
+    assert np.array_equal(np.diff(S.Loff), (c + r) * c) and np.array_equal(np.diff(S.CBoff), r * r)
+    assert len(np.unique(S.amap)) == len(S.amap) and S.amap.min() >= 0 and S.amap.max() < S.Loff[-1]
+    h.close()
+
+
+def test_missing_structural_diagonal_is_inserted(pkg):
+    # LP with an empty Hessian and a variable that appears in no constraint (gotcha 9.7-2)
+    J = sp.csc_matrix(np.array([[1.0, 0.0, 2.0], [0.0, 0.0, 1.0]]))
+    H = sp.csc_matrix((3, 3))
+    h = pkg.Handle(-1)
+    h.set_structure(3, 2, J.indptr, J.indices, H.indptr, H.indices, 0)
+    Mp, Mi = h.symbolic("Mp"), h.symbolic("Mi")
+    assert np.all(Mi[Mp[:-1]] == np.arange(3))
+    pp = h.symbolic("pair_ptr")
+    assert pp[Mp[1] + 1] - pp[Mp[1]] == 0      # column 1: diagonal present with no products
+
+
+def test_one_based_indices_and_cache(pkg):
+    prob = pkg.problems.chain(30, seed=9)
+    h0 = _handle(pkg, prob)
+    h1 = pkg.Handle(-1)
+    h1.set_structure(prob.n, prob.m, prob.J.indptr + 1, prob.J.indices + 1, prob.H.indptr + 1, prob.H.indices + 1, 1)
+    for nm in ("perm", "sfirst", "rowidx", "amap", "pairA", "pairB", "hmap"):
+        assert np.array_equal(h0.symbolic(nm), h1.symbolic(nm)), nm
+    # a second handle on the same pattern reuses the analysis (two solver objects per solve)
+    h2 = _handle(pkg, prob)
+    assert h2.info("symbolic_cached") == 1.0
+
+
+def test_bad_patterns_are_rejected(pkg):
+    h = pkg.Handle(-1)
+    J = sp.csc_matrix(np.array([[1.0, 2.0], [3.0, 4.0]]))
+    Hup = sp.csc_matrix(np.array([[1.0, 1.0], [0.0, 1.0]]))   # upper entry: not lower triangular
+    with pytest.raises(pkg.OPBError) as e:
+        h.set_structure(2, 2, J.indptr, J.indices, Hup.indptr, Hup.indices, 0)
+    assert e.value.code == -1
+    bad = J.indices.copy(); bad[0] = 5
+    Hl = sp.csc_matrix(np.tril(np.ones((2, 2))))
+    with pytest.raises(pkg.OPBError):
+        h.set_structure(2, 2, J.indptr, bad, Hl.indptr, Hl.indices, 0)
+
+
+def test_user_permutation(pkg, orc):
+    N = 5
+    prob = pkg.problems.pde_control(N, seed=1)
+    perm = pkg.problems.grid_nd_perm(N, leaf=2)
+    h = pkg.Handle(-1)
+    h.set_permutation(perm)
+    h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
+    S = emulate.Sym(h)
+    assert sorted(S.perm.tolist()) == list(range(prob.n))
+    Mv = emulate.assemble_M_values(h, prob.J.indptr, prob.J.indices, prob.J.data, prob.H.data, prob.y, prob.s)
+    ok, L = emulate.factor(S, Mv, 1e-3)
+    assert ok
+    with pytest.raises(pkg.OPBError):
+        hb = pkg.Handle(-1)
+        hb.set_permutation(np.zeros(prob.n, np.int64))
+        hb.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
