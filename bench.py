@@ -188,8 +188,11 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--phase-repeat", type=int, default=3)
+    ap.add_argument("--ncu", action="store_true",
+                    help="profiling run: resident steps only (no e2e, phase or CPU legs); never a bench value")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "b200" and not args.ncu:
+        args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":
         run_reference(args)
@@ -239,14 +242,16 @@ def main():
             k.compute_direction()
         return nf, delta
 
-    for _ in range(args.warmup):
-        nf, delta = e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        nf, delta = e2e_step()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_ms = float("nan")
+    if not args.ncu:
+        for _ in range(args.warmup):
+            nf, delta = e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            nf, delta = e2e_step()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     n, m = prob.n, prob.m
     h2d = 8 * (prob.J.nnz + prob.H.nnz + 2 * m) + N_DIRECTIONS * 8 * (n + 2 * m)
     d2h = 8 * n + 8 + N_DIRECTIONS * (8 * (n + 2 * m) + 48) + 3 * 8
@@ -283,6 +288,12 @@ def main():
 
     # ---------------- per-phase timing (rank 0) for the rooflines ----------------
     phases = {}
+    if args.ncu:
+        if rank == 0:
+            print(json.dumps({"ncu_run": True, "workload": args.workload, "ms_per_step_under_profiler": ms_step,
+                              "launches": int(launches), "num_fac": nf_res}))
+        k.finalize()
+        return
     if rank == 0:
         def timed(fn, reps):
             fn(); torch.cuda.synchronize()

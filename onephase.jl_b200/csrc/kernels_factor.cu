@@ -26,7 +26,7 @@ __device__ __forceinline__ bool stop_requested(const DeltaState* st) {
 }
 
 struct FrontDims {
-    int s, first, c, r, N;
+    int s, first, c, r, N, ld;
     int64_t loff, cboff;
 };
 
@@ -37,6 +37,7 @@ __device__ __forceinline__ FrontDims front_dims(const DevSym& S, int s) {
     d.c = S.sfirst[s + 1] - d.first;
     d.r = (int)(S.rowptr[s + 1] - S.rowptr[s]);
     d.N = d.c + d.r;
+    d.ld = ld_of(d.N);
     d.loff = S.Loff[s];
     d.cboff = S.CBoff[s];
     return d;
@@ -92,7 +93,8 @@ front_small_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ 
     const int N = d.N, c = d.c, r = d.r;
     double* panel = Lval + d.loff;
     double* colv = F + (size_t)N * N;
-    for (int idx = tid; idx < N * c; idx += THREADS) F[idx] = panel[idx];
+    const int ld = d.ld;
+    for (int idx = tid; idx < N * c; idx += THREADS) { const int i = idx % N, j = idx / N; F[idx] = panel[i + (size_t)j * ld]; }
     for (int idx = tid; idx < N * r; idx += THREADS) F[N * c + idx] = 0.0;
     __syncthreads();
     // extend-add the children's update blocks (ascending child order)
@@ -114,7 +116,7 @@ front_small_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ 
         if (tid == 0) st->fail = 1;
         return;
     }
-    for (int idx = tid; idx < N * c; idx += THREADS) panel[idx] = F[idx];
+    for (int idx = tid; idx < N * c; idx += THREADS) { const int i = idx % N, j = idx / N; panel[i + (size_t)j * ld] = F[idx]; }
     double* cbo = CB + d.cboff;
     for (int j = 0; j < r; j++)
         for (int i = j + tid; i < r; i += THREADS)
@@ -125,7 +127,7 @@ front_small_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ 
 // Big fronts: blocked right-looking factorisation in global memory.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double* front_elem(const FrontDims& d, double* Lval, double* CB, int i, int j) {
-    return (j < d.c) ? (Lval + d.loff + i + (size_t)j * d.N)
+    return (j < d.c) ? (Lval + d.loff + i + (size_t)j * d.ld)
                      : (CB + d.cboff + (i - d.c) + (size_t)(j - d.c) * d.r);
 }
 
@@ -180,10 +182,10 @@ big_potrf_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
     const int j0 = t * NB;
     if (j0 >= d.c) return;
     const int b = min(NB, d.c - j0);
-    double* base = Lval + d.loff + j0 + (size_t)j0 * d.N;
+    double* base = Lval + d.loff + j0 + (size_t)j0 * d.ld;
     for (int idx = threadIdx.x; idx < b * b; idx += 256) {
         int i = idx % b, j = idx / b;
-        D[idx] = base[i + (size_t)j * d.N];
+        D[idx] = base[i + (size_t)j * d.ld];
     }
     __syncthreads();
     if (!factor_in_smem<256>(D, D + NB * NB, b, b, st->mode)) {
@@ -192,7 +194,7 @@ big_potrf_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
     }
     for (int idx = threadIdx.x; idx < b * b; idx += 256) {
         int i = idx % b, j = idx / b;
-        if (i >= j) base[i + (size_t)j * d.N] = D[idx];
+        if (i >= j) base[i + (size_t)j * d.ld] = D[idx];
     }
 }
 
@@ -207,19 +209,19 @@ big_trsm_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lva
     const int b = min(NB, d.c - j0);
     const int i0 = j0 + b + blockIdx.x * 128;
     if (i0 >= d.N) return;
-    const double* base = Lval + d.loff + j0 + (size_t)j0 * d.N;
+    const double* base = Lval + d.loff + j0 + (size_t)j0 * d.ld;
     for (int idx = threadIdx.x; idx < b * b; idx += 128) {
         int i = idx % b, j = idx / b;
-        D[i + j * NB] = base[i + (size_t)j * d.N];
+        D[i + j * NB] = base[i + (size_t)j * d.ld];
     }
     __syncthreads();
     const int i = i0 + threadIdx.x;
     if (i >= d.N) return;
     const int mode = st->mode;
-    double* row = Lval + d.loff + i + (size_t)j0 * d.N;
+    double* row = Lval + d.loff + i + (size_t)j0 * d.ld;
     double x[NB];
 #pragma unroll
-    for (int q = 0; q < NB; q++) x[q] = (q < b) ? row[(size_t)q * d.N] : 0.0;
+    for (int q = 0; q < NB; q++) x[q] = (q < b) ? row[(size_t)q * d.ld] : 0.0;
     if (mode == 0) {
 #pragma unroll
         for (int q = 0; q < NB; q++) {
@@ -245,7 +247,7 @@ big_trsm_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lva
         for (int q = 0; q < NB; q++) if (q < b) x[q] = x[q] / D[q + q * NB];
     }
 #pragma unroll
-    for (int q = 0; q < NB; q++) if (q < b) row[(size_t)q * d.N] = x[q];
+    for (int q = 0; q < NB; q++) if (q < b) row[(size_t)q * d.ld] = x[q];
 }
 
 constexpr int UT = 64;   // tile edge of the trailing update
@@ -276,15 +278,15 @@ big_update_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ L
     const int J = (int)(tp - (long long)I * (I + 1) / 2);
     const int ri = j1 + I * UT, rj = j1 + J * UT;
     const int mode = st->mode;
-    const double* pan = Lval + d.loff + (size_t)j0 * d.N;
+    const double* pan = Lval + d.loff + (size_t)j0 * d.ld;
     for (int idx = threadIdx.x; idx < NB * UT; idx += 256) {
         const int i = idx % UT, p = idx / UT;
         double a = 0.0, bb = 0.0;
         if (p < b) {
-            if (ri + i < d.N) a = pan[(ri + i) + (size_t)p * d.N];
+            if (ri + i < d.N) a = pan[(ri + i) + (size_t)p * d.ld];
             if (rj + i < d.N) {
-                bb = pan[(rj + i) + (size_t)p * d.N];
-                if (mode == 1) bb *= pan[(j0 + p) + (size_t)p * d.N];
+                bb = pan[(rj + i) + (size_t)p * d.ld];
+                if (mode == 1) bb *= pan[(j0 + p) + (size_t)p * d.ld];
             }
         }
         As[idx] = a; Bs[idx] = bb;
@@ -357,36 +359,49 @@ cudaError_t factor_configure() {
                                 (int)small_smem(TINY_N));
 }
 
+void launch_big_extend_add(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
+                           double* CB, DeltaState* st_d, cudaStream_t st) {
+    if (!L.big_count) return;
+    dim3 gea((L.big_maxN + EA_RB - 1) / EA_RB, L.big_count);
+    big_extend_add_kernel<<<gea, 256, 0, st>>>(S, d_sched + L.big_begin, Lval, CB, st_d);
+    count_launch();
+}
+
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
-                          double* Lval, double* CB, DeltaState* st_d, cudaStream_t st) {
+                          double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode, cudaStream_t st) {
     for (const LevelPlan& L : plan) {
-        if (L.tiny_count)
+        if (L.tiny_count) {
             front_small_kernel<64><<<L.tiny_count, 64, small_smem(L.tiny_maxN), st>>>(
                 S, d_sched + L.tiny_begin, Lval, CB, st_d);
-                count_launch();
-        if (L.small_count)
+            count_launch();
+        }
+        if (L.small_count) {
             front_small_kernel<256><<<L.small_count, 256, small_smem(L.small_maxN), st>>>(
                 S, d_sched + L.small_begin, Lval, CB, st_d);
-                count_launch();
-        if (L.big_count) {
-            const int* list = d_sched + L.big_begin;
-            dim3 gea((L.big_maxN + EA_RB - 1) / EA_RB, L.big_count);
-            big_extend_add_kernel<<<gea, 256, 0, st>>>(S, list, Lval, CB, st_d);
             count_launch();
-            const int nsteps = (L.big_maxC + NB - 1) / NB;
-            for (int t = 0; t < nsteps; t++) {
-                big_potrf_kernel<<<L.big_count, 256, 0, st>>>(S, list, Lval, t, st_d);
-                count_launch();
-                const int rem = L.big_maxN - t * NB;   // upper bound on rows below
-                if (rem <= 0) continue;
-                dim3 gt((rem + 127) / 128, L.big_count);
-                big_trsm_kernel<<<gt, 128, 0, st>>>(S, list, Lval, t, st_d);
-                count_launch();
-                const long long nt = (rem + UT - 1) / UT;
-                dim3 gu((unsigned)(nt * (nt + 1) / 2), L.big_count);
-                big_update_kernel<<<gu, 256, 0, st>>>(S, list, Lval, CB, t, st_d);
-                count_launch();
-            }
+        }
+        if (!L.big_count) continue;
+        if (mode == 0) {
+            // Cholesky: blocked right-looking on the FP64 tensor pipe (kernels_dense.cu)
+            launch_big_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, st);
+            continue;
+        }
+        // LDL' fallback: scalar blocked path
+        const int* list = d_sched + L.big_begin;
+        launch_big_extend_add(S, L, d_sched, Lval, CB, st_d, st);
+        const int nsteps = (L.big_maxC + NB - 1) / NB;
+        for (int t = 0; t < nsteps; t++) {
+            big_potrf_kernel<<<L.big_count, 256, 0, st>>>(S, list, Lval, t, st_d);
+            count_launch();
+            const int rem = L.big_maxN - t * NB;   // upper bound on rows below
+            if (rem <= 0) continue;
+            dim3 gt((rem + 127) / 128, L.big_count);
+            big_trsm_kernel<<<gt, 128, 0, st>>>(S, list, Lval, t, st_d);
+            count_launch();
+            const long long nt = (rem + UT - 1) / UT;
+            dim3 gu((unsigned)(nt * (nt + 1) / 2), L.big_count);
+            big_update_kernel<<<gu, 256, 0, st>>>(S, list, Lval, CB, t, st_d);
+            count_launch();
         }
     }
 }

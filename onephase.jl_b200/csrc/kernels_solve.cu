@@ -24,7 +24,7 @@ fwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
     const int c = S.sfirst[s + 1] - first;
     const int64_t rp = S.rowptr[s];
     const int r = (int)(S.rowptr[s + 1] - rp);
-    const int N = c + r;
+    const int N = c + r, ld = ld_of(N);
     const double* __restrict__ panel = Lval + S.Loff[s];
     double* xs = x + first;
     double* us = u + rp;
@@ -50,7 +50,7 @@ fwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
             const int lane = tid;
             double xv = (lane < b) ? xs[j0 + lane] : 0.0;
             for (int q = 0; q < b; q++) {
-                double lpq = (lane >= q && lane < b) ? panel[(j0 + lane) + (size_t)(j0 + q) * N] : 0.0;
+                double lpq = (lane >= q && lane < b) ? panel[(j0 + lane) + (size_t)(j0 + q) * ld] : 0.0;
                 double dq = __shfl_sync(0xffffffffu, lpq, q);
                 double xq = __shfl_sync(0xffffffffu, xv, q);
                 double val = (mode == 0) ? xq / dq : xq;
@@ -62,8 +62,8 @@ fwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
         __syncthreads();
         for (int i = j0 + b + tid; i < N; i += ST) {
             double acc = 0.0;
-            const double* pr = panel + i + (size_t)j0 * N;
-            for (int q = 0; q < b; q++) acc += pr[(size_t)q * N] * yb[q];
+            const double* pr = panel + i + (size_t)j0 * ld;
+            for (int q = 0; q < b; q++) acc += pr[(size_t)q * ld] * yb[q];
             if (i < c) xs[i] -= acc; else us[i - c] -= acc;
         }
         __syncthreads();
@@ -79,7 +79,7 @@ bwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
     const int c = S.sfirst[s + 1] - first;
     const int64_t rp = S.rowptr[s];
     const int r = (int)(S.rowptr[s + 1] - rp);
-    const int N = c + r;
+    const int N = c + r, ld = ld_of(N);
     const double* __restrict__ panel = Lval + S.Loff[s];
     double* xs = x + first;
     double* us = u + rp;
@@ -87,14 +87,14 @@ bwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int t = tid; t < r; t += ST) us[t] = x[rows[t]];
     if (mode == 1)
-        for (int j = tid; j < c; j += ST) xs[j] = xs[j] / panel[j + (size_t)j * N];
+        for (int j = tid; j < c; j += ST) xs[j] = xs[j] / panel[j + (size_t)j * ld];
     __syncthreads();
     const int nblk = (c + SB - 1) / SB;
     for (int blk = nblk - 1; blk >= 0; blk--) {
         const int j0 = blk * SB;
         const int b = min(SB, c - j0);
         for (int q = warp; q < b; q += ST / 32) {
-            const double* col = panel + (size_t)(j0 + q) * N;
+            const double* col = panel + (size_t)(j0 + q) * ld;
             double acc = 0.0;
             for (int i = j0 + b + lane; i < N; i += 32) {
                 const double f = (i < c) ? xs[i] : us[i - c];
@@ -108,7 +108,7 @@ bwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
             double xv = (lane < b) ? yb[lane] : 0.0;
             for (int q = b - 1; q >= 0; q--) {
                 // L[j0+q, j0+lane], lane <= q
-                double lql = (lane <= q) ? panel[(j0 + q) + (size_t)(j0 + lane) * N] : 0.0;
+                double lql = (lane <= q) ? panel[(j0 + q) + (size_t)(j0 + lane) * ld] : 0.0;
                 double dq = __shfl_sync(0xffffffffu, lql, q);
                 double xq = __shfl_sync(0xffffffffu, xv, q);
                 double val = (mode == 0) ? xq / dq : xq;
@@ -141,16 +141,22 @@ __global__ void permute_out_kernel(const double* __restrict__ x, const int* __re
 cudaError_t solve_configure() { return cudaSuccess; }
 
 void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
-                  const double* Lval, double* x, double* u, int mode, cudaStream_t st) {
+                  const double* Lval, const double* Xinv, double* x, double* xnew, double* u, int mode,
+                  cudaStream_t st) {
+    // Cholesky: big supernodes take the multi-CTA path through inv(L11) (kernels_dense.cu);
+    // LDL': every supernode is solved by one CTA.
+    const bool wide = (mode == 0);
     for (size_t l = 0; l < plan.size(); l++) {
         const LevelPlan& L = plan[l];
-        if (L.all_count) fwd_kernel<<<L.all_count, ST, 0, st>>>(S, d_sched + L.all_begin, Lval, x, u, mode);
-        count_launch();
+        const int solo = wide ? L.tiny_count + L.small_count : L.all_count;
+        if (solo) { fwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.all_begin, Lval, x, u, mode); count_launch(); }
+        if (wide) launch_solve_wide_fwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
     }
     for (size_t l = plan.size(); l-- > 0;) {
         const LevelPlan& L = plan[l];
-        if (L.all_count) bwd_kernel<<<L.all_count, ST, 0, st>>>(S, d_sched + L.all_begin, Lval, x, u, mode);
-        count_launch();
+        const int solo = wide ? L.tiny_count + L.small_count : L.all_count;
+        if (solo) { bwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.all_begin, Lval, x, u, mode); count_launch(); }
+        if (wide) launch_solve_wide_bwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
     }
 }
 

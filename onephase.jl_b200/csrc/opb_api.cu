@@ -3,6 +3,7 @@
 // done on the host; without a CUDA device the numeric entry points fail.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -25,12 +26,15 @@ struct Bundle {
     Symbolic S;
     std::vector<LevelPlan> plan;
     std::vector<int> sched;
+    std::vector<int64_t> Xoff;   // per supernode: offset of inv(L11) in Xinv (big supernodes) or -1
+    int64_t x_total = 0;
+    TrtriPlan trtri;
     int n_tiny = 0, n_small = 0, n_big = 0;
     int device = -1;
     size_t device_bytes = 0;
     // device copies
     DBuf<int> d_sfirst, d_rowidx, d_rel, d_sparent, d_child_ptr, d_child_list, d_perm, d_sched;
-    DBuf<int64_t> d_rowptr, d_Loff, d_CBoff, d_amap, d_dpos, d_Mp, d_src;
+    DBuf<int64_t> d_rowptr, d_Loff, d_CBoff, d_amap, d_dpos, d_Mp, d_src, d_Xoff;
     DBuf<int64_t> d_pair_ptr, d_Jp, d_Rp, d_Sp;
     DBuf<int> d_pairA, d_pairB, d_hmap, d_Jrow, d_Rcol, d_Rpos, d_Scol, d_Spos;
     DevSym dev{};
@@ -39,7 +43,7 @@ struct Bundle {
         d_sfirst.release(); d_rowidx.release(); d_rel.release(); d_sparent.release();
         d_child_ptr.release(); d_child_list.release(); d_perm.release(); d_sched.release();
         d_rowptr.release(); d_Loff.release(); d_CBoff.release(); d_amap.release(); d_dpos.release();
-        d_Mp.release(); d_src.release(); d_pair_ptr.release(); d_Jp.release(); d_Rp.release(); d_Sp.release();
+        d_Mp.release(); d_src.release(); d_Xoff.release(); d_pair_ptr.release(); d_Jp.release(); d_Rp.release(); d_Sp.release();
         d_pairA.release(); d_pairB.release(); d_hmap.release(); d_Jrow.release(); d_Rcol.release();
         d_Rpos.release(); d_Scol.release(); d_Spos.release();
     }
@@ -55,17 +59,32 @@ static void build_plan(Bundle& B) {
     B.plan.assign(S.nlevels, LevelPlan());
     B.sched.clear();
     B.n_tiny = B.n_small = B.n_big = 0;
+    B.Xoff.assign(S.nsuper, -1);
+    B.x_total = 0;
+    auto cols = [&](int s) { return S.sfirst[s + 1] - S.sfirst[s]; };
+    auto rows = [&](int s) { return cols(s) + (int)(S.rowptr[s + 1] - S.rowptr[s]); };
+    std::vector<int> all_big;
     for (int l = 0; l < S.nlevels; l++) {
         LevelPlan& L = B.plan[l];
         std::vector<int> tiny, small, big;
         for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
             int s = S.level_list[t];
-            int c = S.sfirst[s + 1] - S.sfirst[s];
-            int N = c + (int)(S.rowptr[s + 1] - S.rowptr[s]);
+            int c = cols(s), N = rows(s);
             L.all_maxN = std::max(L.all_maxN, N);
             if (N <= TINY_N) { tiny.push_back(s); L.tiny_maxN = std::max(L.tiny_maxN, N); }
             else if (N <= SMALL_N) { small.push_back(s); L.small_maxN = std::max(L.small_maxN, N); }
             else { big.push_back(s); L.big_maxN = std::max(L.big_maxN, N); L.big_maxC = std::max(L.big_maxC, c); }
+        }
+        // big fronts by pivot-column count, descending: outer step t touches a prefix
+        std::stable_sort(big.begin(), big.end(), [&](int a, int b) { return cols(a) > cols(b); });
+        const int nsteps = (L.big_maxC + WB - 1) / WB;
+        L.step_count.assign(nsteps, 0); L.step_maxN.assign(nsteps, 0);
+        for (int s : big) {
+            const int c = cols(s), N = rows(s);
+            for (int t = 0; t * WB < c; t++) { L.step_count[t]++; L.step_maxN[t] = std::max(L.step_maxN[t], N); }
+            B.Xoff[s] = B.x_total;
+            B.x_total += (int64_t)ld_of(c) * c;
+            all_big.push_back(s);
         }
         L.all_begin = L.tiny_begin = (int)B.sched.size();
         L.tiny_count = (int)tiny.size();
@@ -78,6 +97,26 @@ static void build_plan(Bundle& B) {
         B.sched.insert(B.sched.end(), big.begin(), big.end());
         L.all_count = L.tiny_count + L.small_count + L.big_count;
         B.n_tiny += L.tiny_count; B.n_small += L.small_count; B.n_big += L.big_count;
+    }
+    // pivot-block inverses: every big supernode with more than one WB block takes part in the
+    // recursive merge; they are batched over the whole tree (independent of the levels)
+    TrtriPlan& T = B.trtri;
+    T = TrtriPlan();
+    std::vector<int> multi;
+    for (int s : all_big) if (cols(s) > WB) multi.push_back(s);
+    std::stable_sort(multi.begin(), multi.end(), [&](int a, int b) { return cols(a) > cols(b); });
+    T.count = (int)multi.size();
+    T.list_begin = (int)B.sched.size();
+    B.sched.insert(B.sched.end(), multi.begin(), multi.end());
+    if (!multi.empty()) {
+        const int maxc = cols(multi[0]);
+        for (int l = 0; (WB << l) < maxc; l++) {
+            const int Sz = WB << l;
+            int cnt = 0;
+            for (int s : multi) if (cols(s) > Sz) cnt++;
+            T.level_count.push_back(cnt);
+            T.level_pairs.push_back((maxc - Sz - 1) / (2 * Sz) + 1);
+        }
     }
 }
 
@@ -99,7 +138,7 @@ struct opb_handle {
     enum Ready { NOT_READY, SYSTEM_FORMED, FACTORED } ready = NOT_READY;
     int mode = OPB_MODE_CHOLESKY;
     DBuf<double> Jv, Hv, y, s, sigma, T, Rval, Mval, sdiag, Lval, CB;
-    DBuf<double> dual_r, primal_r, comp_r, b, res, dx, dy, ds, tm, xw, uw, userval;
+    DBuf<double> dual_r, primal_r, comp_r, b, res, dx, dy, ds, tm, xw, xw2, uw, userval, Xinv, Twork;
     DBuf<unsigned long long> red;
     char* d_state_raw = nullptr;
     DeltaState* d_state = nullptr;
@@ -147,6 +186,8 @@ int opb_create(opb_handle** out, int device_id, unsigned flags) {
         if (e != cudaSuccess) return h->cuda_fail(e, "cudaMemset(state)");
         e = factor_configure();
         if (e != cudaSuccess) return h->cuda_fail(e, "factor_configure (is this an sm_100a device?)");
+        e = dense_configure();
+        if (e != cudaSuccess) return h->cuda_fail(e, "dense_configure (is this an sm_100a device?)");
         e = h->red.alloc(8);
         if (e != cudaSuccess) return h->cuda_fail(e, "cudaMalloc(red)");
     }
@@ -160,7 +201,7 @@ int opb_destroy(opb_handle* h) {
         if (h->stream) cudaStreamSynchronize(h->stream);
         DBuf<double>* bufs[] = {&h->Jv, &h->Hv, &h->y, &h->s, &h->sigma, &h->T, &h->Rval, &h->Mval, &h->sdiag,
                                 &h->Lval, &h->CB, &h->dual_r, &h->primal_r, &h->comp_r, &h->b, &h->res,
-                                &h->dx, &h->dy, &h->ds, &h->tm, &h->xw, &h->uw, &h->userval};
+                                &h->dx, &h->dy, &h->ds, &h->tm, &h->xw, &h->xw2, &h->uw, &h->userval, &h->Xinv, &h->Twork};
         for (auto* b : bufs) b->release();
         h->red.release();
         if (h->d_state_raw) cudaFree(h->d_state_raw);
@@ -211,6 +252,7 @@ static int upload_bundle(opb_handle* h, Bundle& B) {
     CK(B.d_sparent.upload(S.sparent, st)); CK(B.d_child_ptr.upload(S.child_ptr, st));
     CK(B.d_child_list.upload(S.child_list, st)); CK(B.d_perm.upload(S.perm, st));
     CK(B.d_sched.upload(B.sched, st));
+    CK(B.d_Xoff.upload(B.Xoff, st));
     {
         // diagonal entries carry a flag so the scatter kernel adds delta to them
         std::vector<int64_t> amap = S.amap;
@@ -235,7 +277,7 @@ static int upload_bundle(opb_handle* h, Bundle& B) {
     B.dev.sfirst = B.d_sfirst.p; B.dev.rowptr = B.d_rowptr.p; B.dev.rowidx = B.d_rowidx.p;
     B.dev.rel = B.d_rel.p; B.dev.Loff = B.d_Loff.p; B.dev.CBoff = B.d_CBoff.p;
     B.dev.sparent = B.d_sparent.p; B.dev.child_ptr = B.d_child_ptr.p; B.dev.child_list = B.d_child_list.p;
-    B.dev.perm = B.d_perm.p;
+    B.dev.perm = B.d_perm.p; B.dev.Xoff = B.d_Xoff.p;
     return OPB_OK;
 }
 
@@ -245,7 +287,14 @@ static int alloc_numeric(opb_handle* h) {
     const int n = S.n;
     CK(h->Mval.alloc(B.Mp[n])); CK(h->sdiag.alloc(n));
     CK(h->Lval.alloc(S.nnzL)); CK(h->CB.alloc(S.cb_total));
-    CK(h->xw.alloc(n)); CK(h->uw.alloc(S.rowidx.size()));
+    CK(h->xw.alloc(n)); CK(h->xw2.alloc(n)); CK(h->uw.alloc(S.rowidx.size()));
+    {
+        // inverses of the big supernodes' pivot blocks; the strictly upper parts must stay zero
+        const size_t had = h->Xinv.n;
+        CK(h->Xinv.alloc((size_t)B.x_total)); CK(h->Twork.alloc((size_t)B.x_total));
+        if (B.x_total && (h->Xinv.n != had || true))
+            CK(cudaMemsetAsync(h->Xinv.p, 0, (size_t)B.x_total * sizeof(double), h->stream));
+    }
     CK(h->res.alloc(n)); CK(h->dx.alloc(n)); CK(h->b.alloc(n));
     if (B.schur) {
         const int m = B.P.m;
@@ -353,7 +402,9 @@ static void enqueue_attempt(opb_handle* h) {
     launch_ctl_begin(h->d_state, st);
     launch_scatter_fronts(h->Mval.p, B.d_amap.p, B.d_dpos.p, h->sdiag.p, h->Lval.p, B.S.nnzL,
                           B.Mp[B.S.n], B.S.n, h->d_state, 1, st);
-    launch_factor_levels(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->d_state, st);
+    launch_factor_levels(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->Xinv.p, h->d_state, h->mode, st);
+    if (h->mode == OPB_MODE_CHOLESKY && B.trtri.count)
+        launch_trtri(B.dev, B.trtri, B.d_sched.p, h->Lval.p, h->Xinv.p, h->Twork.p, h->d_state, st);
     launch_ctl_end(h->d_state, st);
 }
 
@@ -502,7 +553,7 @@ int opb_direction_resident(opb_handle* h, int n_refine) {
     launch_schur_rhs(D, st);
     for (int it = 0; it < n_refine; it++) {
         launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, D.n, st);
-        launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->xw.p, h->uw.p, h->mode, st);
+        launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode, st);
         launch_permute_out_add(h->xw.p, B.d_perm.p, h->dx.p, D.n, 1, st);
         // the reference also evaluates the residual after the last correction but only
         // prints it (schur.jl:177-179); it does not influence the direction
@@ -533,7 +584,7 @@ int opb_solve_resident(opb_handle* h, int nsolves) {
     Bundle& B = *h->B;
     for (int k = 0; k < nsolves; k++) {
         launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, B.S.n, h->stream);
-        launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->xw.p, h->uw.p, h->mode, h->stream);
+        launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode, h->stream);
         launch_permute_out_add(h->xw.p, B.d_perm.p, h->b.p, B.S.n, 0, h->stream);
     }
     CK(cudaGetLastError());
@@ -617,7 +668,7 @@ int opb_ls_solve(opb_handle* h, const double* rhs, double* sol) {
     cudaStream_t st = h->stream;
     CK(cudaMemcpyAsync(h->res.p, rhs, n * sizeof(double), cudaMemcpyHostToDevice, st));
     launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, n, st);
-    launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->xw.p, h->uw.p, h->mode, st);
+    launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode, st);
     launch_permute_out_add(h->xw.p, B.d_perm.p, h->b.p, n, 0, st);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(sol, h->b.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -650,6 +701,8 @@ int opb_get_info(opb_handle* h, const char* key, double* out) {
     else if (k == "n_big") *out = B.n_big;
     else if (k == "symbolic_cached") *out = h->cached_hit ? 1 : 0;
     else if (k == "sum_rows") *out = (double)S.rowidx.size();
+    else if (k == "x_total") *out = (double)B.x_total;
+    else if (k == "n_trtri") *out = B.trtri.count;
     else return h->fail(OPB_ERR_INVALID, "unknown info key " + k);
     return OPB_OK;
 }

@@ -36,6 +36,9 @@ struct DeltaState {
     double kkt_err[6];
 };
 
+// leading dimension of a panel / inverse block with N rows (even: 16-byte aligned columns)
+__host__ __device__ inline int ld_of(int N) { return (N + 1) & ~1; }
+
 // Flat view of the symbolic structures in device memory.
 struct DevSym {
     int n, nsuper;
@@ -49,6 +52,7 @@ struct DevSym {
     const int* child_ptr;
     const int* child_list;
     const int* perm;   // perm[new] = old
+    const int64_t* Xoff;  // per supernode: offset of inv(L11) (c x c, ld = ld_of(c)) in Xinv, or -1
 };
 
 template <class T>
@@ -80,11 +84,15 @@ struct LevelPlan {
     int big_maxN = 0, big_maxC = 0;
     int all_begin = 0, all_count = 0;        // every supernode of the level (solves)
     int all_maxN = 0;
+    // big fronts are sorted by pivot-column count (descending); outer step t of the blocked
+    // factorisation touches the first step_count[t] of them
+    std::vector<int> step_count, step_maxN;
 };
 
 constexpr int TINY_N = 32;
 constexpr int SMALL_N = 152;   // 152*152*8 = 184,832 B of shared memory
-constexpr int NB = 32;         // block-column width of the big-front path
+constexpr int NB = 32;         // block-column width of the LDL' big-front path
+constexpr int WB = 128;        // outer block width of the Cholesky big-front path (DMMA)
 
 // ---- kernels_assembly.cu
 void launch_sigma_T(const double* Jv, const int* Jrow, const double* y, const double* s,
@@ -108,7 +116,27 @@ void launch_ctl_single(DeltaState* st_d, double delta, int mode, cudaStream_t st
 // ---- kernels_factor.cu
 cudaError_t factor_configure();
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
-                          double* Lval, double* CB, DeltaState* st_d, cudaStream_t st);
+                          double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode, cudaStream_t st);
+void launch_big_extend_add(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
+                           double* CB, DeltaState* st_d, cudaStream_t st);
+
+// ---- kernels_dense.cu  (Cholesky of big fronts on the FP64 tensor pipe, pivot-block inverses,
+//                         multi-CTA triangular solves for big supernodes)
+struct TrtriPlan {
+    int count = 0;                    // big supernodes with more than one WB block (sorted by c descending)
+    int list_begin = 0;               // position in d_sched
+    std::vector<int> level_count;     // merge level l: number of participating supernodes
+    std::vector<int> level_pairs;     // merge level l: max number of block pairs per supernode
+};
+cudaError_t dense_configure();
+void launch_big_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
+                           double* CB, double* Xinv, DeltaState* st_d, cudaStream_t st);
+void launch_trtri(const DevSym& S, const TrtriPlan& T, const int* d_sched, const double* Lval,
+                  double* Xinv, double* Twork, const DeltaState* st_d, cudaStream_t st);
+void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
+                           const double* Xinv, double* x, double* xnew, double* u, cudaStream_t st);
+void launch_solve_wide_bwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
+                           const double* Xinv, double* x, double* xnew, double* u, cudaStream_t st);
 void launch_ldlt_inertia(const DevSym& S, const double* Lval, const int64_t* dpos, int n,
                          DeltaState* st_d, cudaStream_t st);
 
@@ -116,7 +144,8 @@ void launch_ldlt_inertia(const DevSym& S, const double* Lval, const int64_t* dpo
 cudaError_t solve_configure();
 // x (permuted order, length n) is overwritten with the solution; u = workspace (len rowidx)
 void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
-                  const double* Lval, double* x, double* u, int mode, cudaStream_t st);
+                  const double* Lval, const double* Xinv, double* x, double* xnew, double* u, int mode,
+                  cudaStream_t st);
 void launch_permute_in(const double* b, const int* perm, double* x, int n, cudaStream_t st);
 void launch_permute_out_add(const double* x, const int* perm, double* dst, int n, int accumulate, cudaStream_t st);
 

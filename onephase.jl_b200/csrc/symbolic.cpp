@@ -701,7 +701,7 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
     S.max_front = 0;
     for (int s = 0; s < NS; s++) {
         int64_t c = S.sfirst[s + 1] - S.sfirst[s], r = S.rowptr[s + 1] - S.rowptr[s];
-        S.Loff[s + 1] = S.Loff[s] + (c + r) * c;
+        S.Loff[s + 1] = S.Loff[s] + panel_ld(c + r) * c;
         S.CBoff[s + 1] = S.CBoff[s] + r * r;
         S.max_front = std::max<int64_t>(S.max_front, c + r);
         if (S.sparent[s] >= 0) S.level[S.sparent[s]] = std::max(S.level[S.sparent[s]], S.level[s] + 1);
@@ -743,7 +743,7 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
             int row = std::max(a, b), col = std::min(a, b);
             int s = S.col2super[col];
             const int f = S.sfirst[s], l = S.sfirst[s + 1] - 1;
-            const int64_t c = l - f + 1, r = S.rowptr[s + 1] - S.rowptr[s], ld = c + r;
+            const int64_t c = l - f + 1, r = S.rowptr[s + 1] - S.rowptr[s], ld = panel_ld(c + r);
             int64_t lrow;
             if (row <= l) lrow = row - f;
             else {

@@ -9,6 +9,10 @@
 
 namespace opb {
 
+// Leading dimension of a supernode panel with N = c + r rows: padded to an even
+// count so that every panel column starts on a 16-byte boundary (TMA bulk copies).
+inline int64_t panel_ld(int64_t N) { return (N + 1) & ~(int64_t)1; }
+
 struct SymOptions {
     int nd_leaf = 96;          // nested dissection stops at parts of this size
     int ordering = 0;          // 0 = nested dissection + min-degree leaves, 1 = natural, 2 = user perm
@@ -46,7 +50,7 @@ struct Symbolic {
     std::vector<int64_t> rowptr;         // nsuper+1
     std::vector<int> rowidx;             // below-diagonal rows of each supernode (permuted, sorted)
     std::vector<int> rel;                // same shape as rowidx: position in the parent's front
-    std::vector<int64_t> Loff;           // nsuper+1: panel (c+r) x c, column-major, ld = c+r
+    std::vector<int64_t> Loff;           // nsuper+1: panel (c+r) x c, column-major, ld = panel_ld(c+r)
     std::vector<int64_t> CBoff;          // nsuper+1: update block r x r, column-major, ld = r
     std::vector<int> level;              // height above the leaves
     int nlevels = 0;
@@ -55,7 +59,7 @@ struct Symbolic {
     std::vector<int64_t> amap;           // per M_L entry: destination offset in L storage
     std::vector<int64_t> dpos;           // per original variable: offset of its diagonal in L
     std::vector<int> col2super;          // permuted column -> supernode
-    int64_t nnzL = 0;                    // sum (c+r)*c
+    int64_t nnzL = 0;                    // sum panel_ld(c+r)*c
     int64_t nnzL_true = 0;               // entries of the trapezoids (lower part only)
     int64_t cb_total = 0;
     double flops = 0;                    // sum_j colcount_j^2

@@ -66,7 +66,8 @@ def factor(S, Mval, delta, mode="chol"):
         f = S.sfirst[s]; c = S.sfirst[s + 1] - f
         r = S.rowptr[s + 1] - S.rowptr[s]; N = c + r
         F = np.zeros((N, N))
-        F[:, :c] = L[S.Loff[s]:S.Loff[s] + N * c].reshape(c, N).T
+        ld = (N + 1) & ~1     # panel leading dimension (symbolic.h: panel_ld)
+        F[:, :c] = L[S.Loff[s]:S.Loff[s] + ld * c].reshape(c, ld).T[:N]
         for ch in children[s]:
             rel = S.rel[S.rowptr[ch]:S.rowptr[ch + 1]]
             cb = CB.pop(ch)
@@ -88,7 +89,8 @@ def factor(S, Mval, delta, mode="chol"):
                 w = F[j + 1:, j].copy()
                 F[j + 1:, j] = w / d
                 F[j + 1:, j + 1:] -= np.tril(np.outer(F[j + 1:, j], w))
-        L[S.Loff[s]:S.Loff[s] + N * c] = F[:, :c].T.reshape(-1)
+        P = np.zeros((ld, c)); P[:N] = F[:, :c]
+        L[S.Loff[s]:S.Loff[s] + ld * c] = P.T.reshape(-1)
         CB[s] = F[c:, c:].copy()
     return True, L
 
@@ -106,7 +108,8 @@ def solve(S, L, b, mode="chol"):
     for s in order:
         f = S.sfirst[s]; c = S.sfirst[s + 1] - f
         r = S.rowptr[s + 1] - S.rowptr[s]; N = c + r
-        P = L[S.Loff[s]:S.Loff[s] + N * c].reshape(c, N).T
+        ld = (N + 1) & ~1
+        P = L[S.Loff[s]:S.Loff[s] + ld * c].reshape(c, ld).T[:N]
         panels[s] = P
         us = np.zeros(r)
         for ch in children[s]:

@@ -98,7 +98,7 @@ def test_structure_invariants(pkg):
             assert S.sparent[s] == -1
     # panels tile the L storage exactly, maps are injective
     c = np.diff(S.sfirst); r = np.diff(S.rowptr)
-    assert np.array_equal(np.diff(S.Loff), (c + r) * c) and np.array_equal(np.diff(S.CBoff), r * r)
+    assert np.array_equal(np.diff(S.Loff), ((c + r + 1) & ~1) * c) and np.array_equal(np.diff(S.CBoff), r * r)
     assert len(np.unique(S.amap)) == len(S.amap) and S.amap.min() >= 0 and S.amap.max() < S.Loff[-1]
     h.close()
 
