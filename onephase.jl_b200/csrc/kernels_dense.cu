@@ -196,87 +196,273 @@ __device__ __forceinline__ double* front_elem(const Front& d, double* Lval, doub
 }
 
 // ---------------------------------------------------------------------------
-// Diagonal block: Cholesky of the b x b block of outer step t in shared memory,
-// then its inverse (one warp per column, forward substitution in registers).
+// Cholesky of a shared-memory panel (n rows, c <= 128 pivot columns) in 32-column
+// sub-blocks: the diagonal 32 x 32 block is factorised and inverted by one warp in
+// registers (shuffles, no block barrier), the rows below are multiplied by that
+// inverse, the remaining panel columns get the rank-32 update.  The inverse of the
+// whole c x c pivot block is left in global memory X (ldx) for the TRSM-as-GEMM of
+// the big fronts and for the multi-CTA triangular solves.
 // ---------------------------------------------------------------------------
-constexpr int PT = 1024;             // threads of the diagonal-block kernel
-constexpr int LDD = WB + 1;          // odd leading dimension: conflict-free row and column sweeps
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int INVLD = 33;
+constexpr int INVBUF = 32 * INVLD;           // doubles
+constexpr int TBUF = 3 * INVBUF;             // doubles: up to 3 block pairs in flight
 
+__device__ __forceinline__ bool warp_potrf32(double* P, int ld, int j0, int w, double* invbuf,
+                                             double* X, int ldx) {
+    const int lane = threadIdx.x & 31;
+    double a[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        double v = (j == lane) ? 1.0 : 0.0;                 // padding rows: identity
+        if (lane < w && j <= lane) v = P[(j0 + lane) + (size_t)(j0 + j) * ld];
+        a[j] = v;
+    }
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const double d = __shfl_sync(FULL, a[j], j);
+        if (!(d > 0.0)) ok = false;          // pivot <= 0 or NaN (julia.jl:39-41); uniform across the warp
+        const double rs = rsqrt(d);
+        const double lj = a[j] * rs;         // lane j: d * rsqrt(d) = sqrt(d)
+        a[j] = lj;
+#pragma unroll
+        for (int k = j + 1; k < 32; k++) {
+            const double lk = __shfl_sync(FULL, lj, k);
+            if (lane >= k) a[k] -= lj * lk;
+        }
+    }
+    if (!ok) return false;
+#pragma unroll
+    for (int j = 0; j < 32; j++)
+        if (lane < w && j <= lane) P[(j0 + lane) + (size_t)(j0 + j) * ld] = a[j];
+    // inverse: lane j owns column j of X = L^-1 (forward substitution, rows broadcast by shuffles)
+    double dg = 1.0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) if (lane == j) dg = a[j];
+    const double rd = 1.0 / dg;
+    double x[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        double acc = (k == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int m = 0; m < k; m++) acc -= __shfl_sync(FULL, a[m], k) * x[m];
+        x[k] = acc * __shfl_sync(FULL, rd, k);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        invbuf[k + lane * INVLD] = x[k];
+        if (k >= lane && k < w) X[(j0 + k) + (size_t)(j0 + lane) * ldx] = x[k];
+    }
+    return true;
+}
+
+// P: shared-memory panel, column-major (ld), n rows, c pivot columns (top c x c = pivot block).
+// invbuf: INVBUF doubles, tbuf: TBUF doubles, s_flag: shared int preset to 0.
+__device__ bool panel_chol_smem(double* P, int ld, int n, int c, double* invbuf, double* tbuf,
+                                double* X, int ldx, int* s_flag) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    for (int j0 = 0; j0 < c; j0 += 32) {
+        const int w = min(32, c - j0);
+        if (warp == 0) {
+            if (!warp_potrf32(P, ld, j0, w, invbuf, X, ldx) && lane == 0) *s_flag = 1;
+        }
+        __syncthreads();
+        if (*s_flag) return false;
+        const int i1 = j0 + w;
+        // rows below the diagonal block: L = A * inv(Ld)^T, one thread per row
+        for (int i = i1 + tid; i < n; i += nthr) {
+            double arow[32];
+#pragma unroll
+            for (int k = 0; k < 32; k++) arow[k] = (k < w) ? P[i + (size_t)(j0 + k) * ld] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                if (j < w) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k <= j; k++) acc += arow[k] * invbuf[j + k * INVLD];
+                    P[i + (size_t)(j0 + j) * ld] = acc;
+                }
+            }
+        }
+        __syncthreads();
+        // rank-w update of the remaining panel columns (lower part): item = 4 columns x 32 rows
+        if (i1 < c) {
+            const int nrc = (n - i1 + 31) / 32;
+            const int ncg = (c - i1 + 3) / 4;
+            for (int it = warp; it < ncg * nrc; it += nwarp) {
+                const int g = it / nrc, rc = it % nrc;
+                const int jb = i1 + 4 * g;
+                if (i1 + 32 * rc + 31 < jb) continue;
+                const int i = i1 + 32 * rc + lane;
+                const bool iv = i < n;
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int k = 0; k < w; k++) {
+                    const double* col = P + (size_t)(j0 + k) * ld;
+                    const double pik = iv ? col[i] : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int j = jb + q;
+                        acc[q] += pik * ((j < c) ? col[j] : 0.0);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int j = jb + q;
+                    if (j < c && iv && i >= j) P[i + (size_t)j * ld] -= acc[q];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // off-diagonal blocks of X = inv(L11) by block forward substitution:
+    //   X_IJ = - X_II * sum_{K=J}^{I-1} L_IK X_KJ
+    const int nb = (c + 31) >> 5;
+    for (int dist = 1; dist < nb; dist++) {
+        const int npair = nb - dist;            // (J, J + dist), J = 0 .. npair-1; at most 3
+        for (int e = tid; e < npair * 1024; e += nthr) {
+            const int pr = e >> 10, ii = e & 31, jj = (e >> 5) & 31;
+            const int I = pr + dist, J = pr;
+            const int gi = 32 * I + ii, gj = 32 * J + jj;
+            double acc = 0.0;
+            if (gi < c) {
+                const double* xc = X + (size_t)gj * ldx;
+                for (int k = gj; k < 32 * I; k++) acc += P[gi + (size_t)k * ld] * xc[k];
+            }
+            tbuf[pr * INVBUF + ii + jj * INVLD] = acc;
+        }
+        __syncthreads();
+        for (int e = tid; e < npair * 1024; e += nthr) {
+            const int pr = e >> 10, ii = e & 31, jj = (e >> 5) & 31;
+            const int I = pr + dist, J = pr;
+            const int gi = 32 * I + ii, gj = 32 * J + jj;
+            if (gi < c) {
+                double acc = 0.0;
+                const double* t = tbuf + pr * INVBUF + jj * INVLD;
+                for (int m = 0; m <= ii; m++) acc += X[gi + (size_t)(32 * I + m) * ldx] * t[m];
+                X[gi + (size_t)gj * ldx] = -acc;
+            }
+        }
+        __syncthreads();
+    }
+    return true;
+}
+
+constexpr int PT = 512;              // threads of the panel kernels
+constexpr int LDD = WB + 1;
+
+// diagonal block of outer step t of a big front: Cholesky + inverse
 __global__ void __launch_bounds__(PT)
 chol_diag_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval, double* __restrict__ Xinv,
                  int t, DeltaState* st) {
-    extern __shared__ double D[];          // LDD * WB + 2 * WB
-    __shared__ int s_fail;
+    extern __shared__ double D[];          // LDD * WB + INVBUF + TBUF
+    __shared__ int s_flag;
     if (stop_requested(st)) return;
     const Front d = get_front(S, list[blockIdx.x]);
     const int j0 = t * WB;
     if (j0 >= d.c) return;
     const int b = min(WB, d.c - j0);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* colv = D + LDD * WB;
-    double* rinv = colv + WB;
+    const int tid = threadIdx.x;
+    double* invbuf = D + LDD * WB;
+    double* tbuf = invbuf + INVBUF;
     double* base = Lval + d.loff + j0 + (size_t)j0 * d.ld;
     for (int idx = tid; idx < b * b; idx += PT) {
         const int i = idx % b, j = idx / b;
         D[i + j * LDD] = (i >= j) ? base[i + (size_t)j * d.ld] : 0.0;
     }
-    if (tid == 0) s_fail = 0;
+    if (tid == 0) s_flag = 0;
     __syncthreads();
-    // right-looking Cholesky, one column per step
-    for (int j = 0; j < b; j++) {
-        const double dj = D[j + j * LDD];
-        if (!(dj > 0.0)) {       // pivot <= 0 or NaN: not positive definite (julia.jl:39-41)
-            if (tid == 0) st->fail = 1;
-            return;
-        }
-        const double ljj = sqrt(dj);
-        __syncthreads();
-        double* cj = D + j * LDD;
-        for (int i = j + 1 + tid; i < b; i += PT) cj[i] = cj[i] / ljj;
-        if (tid == 0) cj[j] = ljj;
-        __syncthreads();
-        for (int k = j + 1 + warp; k < b; k += PT / 32) {
-            const double lkj = cj[k];
-            double* ck = D + k * LDD;
-            for (int i = k + lane; i < b; i += 32) ck[i] -= cj[i] * lkj;
-        }
-        __syncthreads();
+    double* X = Xinv + d.xoff + j0 + (size_t)j0 * d.ldx;
+    if (!panel_chol_smem(D, LDD, b, b, invbuf, tbuf, X, d.ldx, &s_flag)) {
+        if (tid == 0) st->fail = 1;
+        return;
     }
     for (int idx = tid; idx < b * b; idx += PT) {
         const int i = idx % b, j = idx / b;
         if (i >= j) base[i + (size_t)j * d.ld] = D[i + j * LDD];
     }
-    for (int k = tid; k < b; k += PT) rinv[k] = 1.0 / D[k + k * LDD];
-    __syncthreads();
-    // inverse: column j of X = L^-1 solves L x = e_j; lane owns rows lane + 32*qq
-    double* X = Xinv + d.xoff + j0 + (size_t)j0 * d.ldx;
-    for (int j = warp; j < b; j += PT / 32) {
-        double x[WB / 32];
-#pragma unroll
-        for (int qq = 0; qq < WB / 32; qq++) x[qq] = (lane + 32 * qq == j) ? 1.0 : 0.0;
-#pragma unroll
-        for (int qk = 0; qk < WB / 32; qk++) {
-            if (qk * 32 + 31 < j || qk * 32 >= b) continue;
-            for (int kk = 0; kk < 32; kk++) {
-                const int k = qk * 32 + kk;
-                if (k < j || k >= b) continue;
-                const double xk = __shfl_sync(0xffffffffu, x[qk], kk) * rinv[k];
-                if (lane == kk) x[qk] = xk;
-                const double* Lk = D + k * LDD;
-#pragma unroll
-                for (int qq = 0; qq < WB / 32; qq++) {
-                    const int i = lane + 32 * qq;
-                    if (i > k && i < b) x[qq] -= Lk[i] * xk;
-                }
-            }
-        }
-#pragma unroll
-        for (int qq = 0; qq < WB / 32; qq++) {
-            const int i = lane + 32 * qq;
-            if (i >= j && i < b) X[i + (size_t)j * d.ldx] = x[qq];
-        }
+}
+
+// medium fronts: the whole N x c panel lives in shared memory.  Children's update blocks are
+// added into the panel columns (ascending child order), the panel is factorised, its pivot-block
+// inverse goes to Xinv; the update block of the front is produced later by front_cb_kernel.
+__global__ void __launch_bounds__(PT)
+mid_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval,
+                 const double* __restrict__ CB, double* __restrict__ Xinv, DeltaState* st) {
+    extern __shared__ double P[];          // N * c + INVBUF + TBUF
+    __shared__ int s_flag;
+    if (stop_requested(st)) return;
+    const Front d = get_front(S, list[blockIdx.x]);
+    const int N = d.N, c = d.c, tid = threadIdx.x;
+    double* invbuf = P + (size_t)N * c;
+    double* tbuf = invbuf + INVBUF;
+    double* panel = Lval + d.loff;
+    for (int idx = tid; idx < N * c; idx += PT) {
+        const int i = idx % N, j = idx / N;
+        P[idx] = panel[i + (size_t)j * d.ld];
     }
-    (void)s_fail;
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+    for (int k = S.child_ptr[d.s]; k < S.child_ptr[d.s + 1]; k++) {
+        const int ch = S.child_list[k];
+        const int64_t rp = S.rowptr[ch];
+        const int rc = (int)(S.rowptr[ch + 1] - rp);
+        const int* __restrict__ relc = S.rel + rp;
+        const double* __restrict__ cb = CB + S.CBoff[ch];
+        int lo = 0, hi = rc;               // uc = number of child rows that land on pivot columns
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < c) lo = mid + 1; else hi = mid; }
+        const int uc = lo;
+        for (int idx = tid; idx < uc * rc; idx += PT) {
+            const int tt = idx % rc, u = idx / rc;
+            if (tt >= u) P[relc[tt] + (size_t)relc[u] * N] += cb[tt + (size_t)u * rc];
+        }
+        __syncthreads();
+    }
+    if (!panel_chol_smem(P, N, N, c, invbuf, tbuf, Xinv + d.xoff, d.ldx, &s_flag)) {
+        if (tid == 0) st->fail = 1;
+        return;
+    }
+    for (int idx = tid; idx < N * c; idx += PT) {
+        const int i = idx % N, j = idx / N;
+        panel[i + (size_t)j * d.ld] = P[idx];
+    }
+}
+
+// big fronts: add the children's update blocks into the panel columns only
+constexpr int EAP_RB = 32;
+__global__ void __launch_bounds__(256)
+big_extend_add_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval,
+                            const double* __restrict__ CB, DeltaState* st) {
+    if (stop_requested(st)) return;
+    const Front d = get_front(S, list[blockIdx.y]);
+    const int row0 = blockIdx.x * EAP_RB;
+    if (row0 >= d.N) return;
+    const int row1 = min(d.N, row0 + EAP_RB);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = S.child_ptr[d.s]; k < S.child_ptr[d.s + 1]; k++) {
+        const int ch = S.child_list[k];
+        const int64_t rp = S.rowptr[ch];
+        const int rc = (int)(S.rowptr[ch + 1] - rp);
+        const int* __restrict__ relc = S.rel + rp;
+        const double* __restrict__ cb = CB + S.CBoff[ch];
+        int lo = 0, hi = rc;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < row0) lo = mid + 1; else hi = mid; }
+        const int t0 = lo;
+        hi = rc;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < row1) lo = mid + 1; else hi = mid; }
+        const int t1 = lo;
+        if (t0 == t1) continue;
+        lo = 0; hi = rc;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < d.c) lo = mid + 1; else hi = mid; }
+        const int uc = lo;
+        for (int tt = t0 + tx; tt < t1; tt += 32) {
+            const int pi = relc[tt];
+            const int ue = min(uc, tt + 1);
+            for (int u = ty; u < ue; u += 8)
+                Lval[d.loff + pi + (size_t)relc[u] * d.ld] += cb[tt + (size_t)u * rc];
+        }
+        __syncthreads();     // the next child may hit the same panel entries from other threads
+    }
 }
 
 // rows below the diagonal block:  L21 = A21 * inv(L_kk)^T  as a tensor-core GEMM
@@ -312,10 +498,11 @@ chol_trsm_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
     }
 }
 
-// trailing update  C -= L[:,blk] * L[:,blk]^T  over the lower 128 x 128 tiles of [j1, N)^2
+// right-looking update of the remaining PANEL columns [j1, c):  L[i,k] -= sum L[i,blk] L[k,blk]
+// (the update block of the front is formed once, at the end, by front_cb_kernel)
 __global__ void __launch_bounds__(GEMM_THREADS)
-chol_syrk_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval, double* __restrict__ CB,
-                 int t, DeltaState* st) {
+chol_panel_update_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval,
+                         int t, DeltaState* st) {
     extern __shared__ __align__(16) unsigned char smraw[];
     GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smraw);
     if (stop_requested(st)) return;
@@ -324,17 +511,17 @@ chol_syrk_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
     if (j0 >= d.c) return;
     const int b = min(WB, d.c - j0);
     const int j1 = j0 + b;
+    if (j1 >= d.c) return;                 // no panel columns left
     const int j1e = j1 & ~1;
-    const int rem = d.N - j1e;
-    if (d.N - j1 <= 0) return;
-    const int nt_ = (rem + BM - 1) / BM;
-    const long long tp = blockIdx.x;
-    if (tp >= (long long)nt_ * (nt_ + 1) / 2) return;
-    int I = (int)((sqrt(8.0 * (double)tp + 1.0) - 1.0) * 0.5);
-    while ((long long)I * (I + 1) / 2 > tp) I--;
-    while ((long long)(I + 1) * (I + 2) / 2 <= tp) I++;
-    const int J = (int)(tp - (long long)I * (I + 1) / 2);
-    const int ri = j1e + I * BM, rj = j1e + J * BM;
+    const int nrow = (d.N - j1e + BM - 1) / BM;
+    const int ncol = (d.c - j1e + BN - 1) / BN;
+    int tp = blockIdx.x, I = -1, J = 0;
+    for (; J < ncol; J++) {
+        if (tp < nrow - J) { I = J + tp; break; }
+        tp -= nrow - J;
+    }
+    if (I < 0) return;
+    const int ri = j1e + I * BM, rj = j1e + J * BN;
     const double* Ag = Lval + d.loff + ri + (size_t)j0 * d.ld;
     const double* Bg = Lval + d.loff + rj + (size_t)j0 * d.ld;
     double acc[8][4][2];
@@ -344,14 +531,84 @@ chol_syrk_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             const int k = rj + acc_col(nt, e);
-            if (k < j1 || k >= d.N) continue;
+            if (k < j1 || k >= d.c) continue;
+            double* colp = Lval + d.loff + (size_t)k * d.ld;
 #pragma unroll
             for (int mt = 0; mt < 8; mt++) {
                 const int i = ri + acc_row(mt);
                 if (i >= d.N || i < k) continue;
-                *front_elem(d, Lval, CB, i, k) -= acc[mt][nt][e];
+                colp[i] -= acc[mt][nt][e];
             }
         }
+}
+
+// update block of a medium / big front, written once:
+//   CB[I,J] = sum_children (extend-add) - L21[I,:] * L21[J,:]^T      (K = all c pivot columns)
+constexpr int TLD = BM + 1;
+__global__ void __launch_bounds__(GEMM_THREADS)
+front_cb_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lval,
+                double* __restrict__ CB, DeltaState* st) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smraw);
+    if (stop_requested(st)) return;
+    const Front d = get_front(S, list[blockIdx.y]);
+    if (d.r <= 0) return;
+    const int ce = d.c & ~1;
+    const int nt_ = (d.N - ce + BM - 1) / BM;
+    const long long tp = blockIdx.x;
+    if (tp >= (long long)nt_ * (nt_ + 1) / 2) return;
+    int I = (int)((sqrt(8.0 * (double)tp + 1.0) - 1.0) * 0.5);
+    while ((long long)I * (I + 1) / 2 > tp) I--;
+    while ((long long)(I + 1) * (I + 2) / 2 <= tp) I++;
+    const int J = (int)(tp - (long long)I * (I + 1) / 2);
+    const int ri = ce + I * BM, rj = ce + J * BN;
+    const double* Ag = Lval + d.loff + ri;
+    const double* Bg = Lval + d.loff + rj;
+    double acc[8][4][2];
+    gemm_mainloop<false>(sm, Ag, d.ld, min(BM, d.N - ri), Bg, d.ld, min(BN, d.N - rj), d.c, acc);
+    // the stage buffers are free now: reuse them as the 128 x 128 tile (ld 129)
+    double* T = reinterpret_cast<double*>(smraw);
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) T[acc_row(mt) + acc_col(nt, e) * TLD] = -acc[mt][nt][e];
+    __syncthreads();
+    const int tid = threadIdx.x;
+    for (int k = S.child_ptr[d.s]; k < S.child_ptr[d.s + 1]; k++) {
+        const int ch = S.child_list[k];
+        const int64_t rp = S.rowptr[ch];
+        const int rc = (int)(S.rowptr[ch + 1] - rp);
+        const int* __restrict__ relc = S.rel + rp;
+        // child rows landing in [ri, ri+BM) and child columns landing in [rj, rj+BN)
+        int lo = 0, hi = rc;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < ri) lo = mid + 1; else hi = mid; }
+        const int t0 = lo;
+        hi = rc;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < ri + BM) lo = mid + 1; else hi = mid; }
+        const int t1 = lo;
+        lo = 0; hi = rc;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < rj) lo = mid + 1; else hi = mid; }
+        const int u0 = lo;
+        hi = rc;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < rj + BN) lo = mid + 1; else hi = mid; }
+        const int u1 = lo;
+        const int nt2 = t1 - t0, nu = u1 - u0;
+        if (nt2 <= 0 || nu <= 0) continue;          // uniform across the CTA
+        const double* __restrict__ cb = CB + S.CBoff[ch];
+        for (int idx = tid; idx < nt2 * nu; idx += GEMM_THREADS) {
+            const int tt = t0 + idx % nt2, u = u0 + idx / nt2;
+            if (tt >= u) T[(relc[tt] - ri) + (relc[u] - rj) * TLD] += cb[tt + (size_t)u * rc];
+        }
+        __syncthreads();
+    }
+    double* out = CB + d.cboff;
+    for (int idx = tid; idx < BM * BN; idx += GEMM_THREADS) {
+        const int i = ri + idx % BM, kk = rj + idx / BM;
+        if (i < d.N && kk >= d.c && kk < d.N && i >= kk)
+            out[(i - d.c) + (size_t)(kk - d.c) * d.r] = T[(i - ri) + (kk - rj) * TLD];
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -574,7 +831,8 @@ wide_bwd_tri_kernel(DevSym S, const int* __restrict__ list, const double* __rest
     if (lane == 0) x[d.first + k] = acc;
 }
 
-inline size_t diag_smem() { return (size_t)(LDD * WB + 2 * WB) * sizeof(double); }
+inline size_t diag_smem() { return (size_t)(LDD * WB + INVBUF + TBUF) * sizeof(double); }
+inline size_t mid_smem(int panel) { return (size_t)(panel + INVBUF + TBUF) * sizeof(double); }
 
 }  // namespace
 
@@ -582,32 +840,61 @@ cudaError_t dense_configure() {
     cudaError_t e;
     e = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem());
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mid_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem(MIDL_PANEL));
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(chol_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem));
+    e = cudaFuncSetAttribute(chol_panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(front_cb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(trtri_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem));
 }
 
-void launch_big_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
-                           double* CB, double* Xinv, DeltaState* st_d, cudaStream_t st) {
-    if (!L.big_count) return;
-    const int* list = d_sched + L.big_begin;
-    launch_big_extend_add(S, L, d_sched, Lval, CB, st_d, st);
-    for (size_t t = 0; t < L.step_count.size(); t++) {
-        const int cnt = L.step_count[t];
-        if (cnt <= 0) break;
-        const int maxN = L.step_maxN[t];
-        chol_diag_kernel<<<cnt, PT, diag_smem(), st>>>(S, list, Lval, Xinv, (int)t, st_d);
+void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
+                            double* CB, double* Xinv, DeltaState* st_d, cudaStream_t st) {
+    if (!L.wide_count) return;
+    // medium fronts: panel in shared memory
+    for (int fc = FC_MID; fc <= FC_MIDL; fc++) {
+        if (!L.count[fc]) continue;
+        mid_panel_kernel<<<L.count[fc], PT, mid_smem(L.maxPanel[fc]), st>>>(S, d_sched + L.begin[fc], Lval, CB, Xinv, st_d);
         count_launch();
-        const int rem = maxN - (int)t * WB;     // rows from the start of the block (upper bound)
-        if (rem <= 0) continue;
-        dim3 gt((rem + BM - 1) / BM + 1, cnt);
-        chol_trsm_kernel<<<gt, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, list, Lval, Xinv, (int)t, st_d);
+    }
+    // big fronts: blocked right-looking factorisation of the panel columns
+    if (L.count[FC_BIG]) {
+        const int* list = d_sched + L.begin[FC_BIG];
+        dim3 gea((L.maxN[FC_BIG] + EAP_RB - 1) / EAP_RB, L.count[FC_BIG]);
+        big_extend_add_panel_kernel<<<gea, 256, 0, st>>>(S, list, Lval, CB, st_d);
         count_launch();
-        const long long nt = (rem + BM - 1) / BM + 1;
-        dim3 gu((unsigned)(nt * (nt + 1) / 2), cnt);
-        chol_syrk_kernel<<<gu, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, list, Lval, CB, (int)t, st_d);
+        for (size_t t = 0; t < L.step_count.size(); t++) {
+            const int cnt = L.step_count[t];
+            if (cnt <= 0) break;
+            const int maxN = L.step_maxN[t];
+            chol_diag_kernel<<<cnt, PT, diag_smem(), st>>>(S, list, Lval, Xinv, (int)t, st_d);
+            count_launch();
+            const int rem = maxN - (int)t * WB;     // rows from the start of the block (upper bound)
+            if (rem <= 0) continue;
+            const int nrow = (rem + BM - 1) / BM + 1;
+            dim3 gt(nrow, cnt);
+            chol_trsm_kernel<<<gt, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, list, Lval, Xinv, (int)t, st_d);
+            count_launch();
+            if (t + 1 < L.step_count.size() && L.step_count[t + 1] > 0) {
+                // only fronts with pivot columns beyond this block have panel columns to update
+                const int cnt2 = L.step_count[t + 1];
+                const int ncol = (L.maxC[FC_BIG] - (int)(t + 1) * WB + BN - 1) / BN + 1;
+                long long tiles = 0;
+                for (int J = 0; J < ncol && J < nrow; J++) tiles += nrow - J;
+                dim3 gu((unsigned)tiles, cnt2);
+                chol_panel_update_kernel<<<gu, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, list, Lval, (int)t, st_d);
+                count_launch();
+            }
+        }
+    }
+    // update blocks of all medium and big fronts, written once
+    {
+        const long long nt = (L.wide_maxR + 1 + BM - 1) / BM + 1;
+        dim3 g((unsigned)(nt * (nt + 1) / 2), L.wide_count);
+        front_cb_kernel<<<g, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, d_sched + L.wide_begin, Lval, CB, st_d);
         count_launch();
     }
 }
@@ -629,24 +916,23 @@ void launch_trtri(const DevSym& S, const TrtriPlan& T, const int* d_sched, const
 
 void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
                            const double* Xinv, double* x, double* xnew, double* u, cudaStream_t st) {
-    if (!L.big_count) return;
-    const int* list = d_sched + L.big_begin;
-    wide_fwd_gather_kernel<<<L.big_count, WT, 0, st>>>(S, list, x, u);
-    dim3 g1((L.big_maxC + SLAB - 1) / SLAB, L.big_count);
+    if (!L.wide_count) return;
+    const int* list = d_sched + L.wide_begin;
+    wide_fwd_gather_kernel<<<L.wide_count, WT, 0, st>>>(S, list, x, u);
+    dim3 g1((L.wide_maxC + SLAB - 1) / SLAB, L.wide_count);
     wide_fwd_tri_kernel<<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew);
-    dim3 g2((L.big_maxN + SLAB - 1) / SLAB, L.big_count);
+    dim3 g2((L.wide_maxN + SLAB - 1) / SLAB, L.wide_count);
     wide_fwd_upd_kernel<<<g2, WT, 0, st>>>(S, list, Lval, x, xnew, u);
     count_launch(3);
 }
 
 void launch_solve_wide_bwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
                            const double* Xinv, double* x, double* xnew, double* u, cudaStream_t st) {
-    if (!L.big_count) return;
-    const int* list = d_sched + L.big_begin;
-    const int maxR = L.big_maxN;   // upper bound on r
-    dim3 g0((maxR + WT - 1) / WT, L.big_count);
+    if (!L.wide_count) return;
+    const int* list = d_sched + L.wide_begin;
+    dim3 g0((L.wide_maxR + WT) / WT, L.wide_count);
     wide_bwd_gather_kernel<<<g0, WT, 0, st>>>(S, list, x, u);
-    dim3 g1((L.big_maxC + KG - 1) / KG, L.big_count);
+    dim3 g1((L.wide_maxC + KG - 1) / KG, L.wide_count);
     wide_bwd_upd_kernel<<<g1, WT, 0, st>>>(S, list, Lval, x, xnew, u);
     wide_bwd_tri_kernel<<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew);
     count_launch(3);

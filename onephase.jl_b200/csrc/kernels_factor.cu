@@ -356,50 +356,45 @@ cudaError_t factor_configure() {
                                          (int)small_smem(SMALL_N));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(front_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)small_smem(TINY_N));
-}
-
-void launch_big_extend_add(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
-                           double* CB, DeltaState* st_d, cudaStream_t st) {
-    if (!L.big_count) return;
-    dim3 gea((L.big_maxN + EA_RB - 1) / EA_RB, L.big_count);
-    big_extend_add_kernel<<<gea, 256, 0, st>>>(S, d_sched + L.big_begin, Lval, CB, st_d);
-    count_launch();
+                                (int)small_smem(FC_MAXN[FC_T32]));
 }
 
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode, cudaStream_t st) {
     for (const LevelPlan& L : plan) {
-        if (L.tiny_count) {
-            front_small_kernel<64><<<L.tiny_count, 64, small_smem(L.tiny_maxN), st>>>(
-                S, d_sched + L.tiny_begin, Lval, CB, st_d);
+        if (L.count[FC_T32]) {
+            front_small_kernel<64><<<L.count[FC_T32], 64, small_smem(L.maxN[FC_T32]), st>>>(
+                S, d_sched + L.begin[FC_T32], Lval, CB, st_d);
             count_launch();
         }
-        if (L.small_count) {
-            front_small_kernel<256><<<L.small_count, 256, small_smem(L.small_maxN), st>>>(
-                S, d_sched + L.small_begin, Lval, CB, st_d);
+        for (int fc = FC_S64; fc <= FC_S152; fc++) {
+            if (!L.count[fc]) continue;
+            front_small_kernel<256><<<L.count[fc], 256, small_smem(L.maxN[fc]), st>>>(
+                S, d_sched + L.begin[fc], Lval, CB, st_d);
             count_launch();
         }
-        if (!L.big_count) continue;
+        if (!L.wide_count) continue;
         if (mode == 0) {
-            // Cholesky: blocked right-looking on the FP64 tensor pipe (kernels_dense.cu)
-            launch_big_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, st);
+            // Cholesky: panels in shared memory / blocked on the FP64 tensor pipe (kernels_dense.cu)
+            launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, st);
             continue;
         }
-        // LDL' fallback: scalar blocked path
-        const int* list = d_sched + L.big_begin;
-        launch_big_extend_add(S, L, d_sched, Lval, CB, st_d, st);
-        const int nsteps = (L.big_maxC + NB - 1) / NB;
+        // LDL' fallback: scalar blocked path over every front that does not fit in shared memory
+        const int* list = d_sched + L.wide_begin;
+        dim3 gea((L.wide_maxN + EA_RB - 1) / EA_RB, L.wide_count);
+        big_extend_add_kernel<<<gea, 256, 0, st>>>(S, list, Lval, CB, st_d);
+        count_launch();
+        const int nsteps = (L.wide_maxC + NB - 1) / NB;
         for (int t = 0; t < nsteps; t++) {
-            big_potrf_kernel<<<L.big_count, 256, 0, st>>>(S, list, Lval, t, st_d);
+            big_potrf_kernel<<<L.wide_count, 256, 0, st>>>(S, list, Lval, t, st_d);
             count_launch();
-            const int rem = L.big_maxN - t * NB;   // upper bound on rows below
+            const int rem = L.wide_maxN - t * NB;   // upper bound on rows below
             if (rem <= 0) continue;
-            dim3 gt((rem + 127) / 128, L.big_count);
+            dim3 gt((rem + 127) / 128, L.wide_count);
             big_trsm_kernel<<<gt, 128, 0, st>>>(S, list, Lval, t, st_d);
             count_launch();
             const long long nt = (rem + UT - 1) / UT;
-            dim3 gu((unsigned)(nt * (nt + 1) / 2), L.big_count);
+            dim3 gu((unsigned)(nt * (nt + 1) / 2), L.wide_count);
             big_update_kernel<<<gu, 256, 0, st>>>(S, list, Lval, CB, t, st_d);
             count_launch();
         }

@@ -148,13 +148,13 @@ void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int
     const bool wide = (mode == 0);
     for (size_t l = 0; l < plan.size(); l++) {
         const LevelPlan& L = plan[l];
-        const int solo = wide ? L.tiny_count + L.small_count : L.all_count;
+        const int solo = wide ? L.solo_count : L.all_count;
         if (solo) { fwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.all_begin, Lval, x, u, mode); count_launch(); }
         if (wide) launch_solve_wide_fwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
     }
     for (size_t l = plan.size(); l-- > 0;) {
         const LevelPlan& L = plan[l];
-        const int solo = wide ? L.tiny_count + L.small_count : L.all_count;
+        const int solo = wide ? L.solo_count : L.all_count;
         if (solo) { bwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.all_begin, Lval, x, u, mode); count_launch(); }
         if (wide) launch_solve_wide_bwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
     }

@@ -66,37 +66,56 @@ static void build_plan(Bundle& B) {
     std::vector<int> all_big;
     for (int l = 0; l < S.nlevels; l++) {
         LevelPlan& L = B.plan[l];
-        std::vector<int> tiny, small, big;
+        std::vector<int> cls[NFC];
         for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
-            int s = S.level_list[t];
-            int c = cols(s), N = rows(s);
-            L.all_maxN = std::max(L.all_maxN, N);
-            if (N <= TINY_N) { tiny.push_back(s); L.tiny_maxN = std::max(L.tiny_maxN, N); }
-            else if (N <= SMALL_N) { small.push_back(s); L.small_maxN = std::max(L.small_maxN, N); }
-            else { big.push_back(s); L.big_maxN = std::max(L.big_maxN, N); L.big_maxC = std::max(L.big_maxC, c); }
+            const int s = S.level_list[t];
+            const int c = cols(s), N = rows(s);
+            int fc;
+            if (N <= FC_MAXN[FC_T32]) fc = FC_T32;
+            else if (N <= FC_MAXN[FC_S64]) fc = FC_S64;
+            else if (N <= FC_MAXN[FC_S104]) fc = FC_S104;
+            else if (N <= FC_MAXN[FC_S152]) fc = FC_S152;
+            else if (c <= WB && (int64_t)N * c <= MID_PANEL) fc = FC_MID;
+            else if (c <= WB && (int64_t)N * c <= MIDL_PANEL) fc = FC_MIDL;
+            else fc = FC_BIG;
+            cls[fc].push_back(s);
+            L.maxN[fc] = std::max(L.maxN[fc], N);
+            L.maxC[fc] = std::max(L.maxC[fc], c);
+            L.maxPanel[fc] = std::max(L.maxPanel[fc], N * std::min(c, WB));
+            if (fc >= FC_MID) {
+                L.wide_maxN = std::max(L.wide_maxN, N);
+                L.wide_maxC = std::max(L.wide_maxC, c);
+                L.wide_maxR = std::max(L.wide_maxR, N - c);
+            }
         }
         // big fronts by pivot-column count, descending: outer step t touches a prefix
+        std::vector<int>& big = cls[FC_BIG];
         std::stable_sort(big.begin(), big.end(), [&](int a, int b) { return cols(a) > cols(b); });
-        const int nsteps = (L.big_maxC + WB - 1) / WB;
+        const int nsteps = (L.maxC[FC_BIG] + WB - 1) / WB;
         L.step_count.assign(nsteps, 0); L.step_maxN.assign(nsteps, 0);
         for (int s : big) {
             const int c = cols(s), N = rows(s);
             for (int t = 0; t * WB < c; t++) { L.step_count[t]++; L.step_maxN[t] = std::max(L.step_maxN[t], N); }
-            B.Xoff[s] = B.x_total;
-            B.x_total += (int64_t)ld_of(c) * c;
             all_big.push_back(s);
         }
-        L.all_begin = L.tiny_begin = (int)B.sched.size();
-        L.tiny_count = (int)tiny.size();
-        B.sched.insert(B.sched.end(), tiny.begin(), tiny.end());
-        L.small_begin = (int)B.sched.size();
-        L.small_count = (int)small.size();
-        B.sched.insert(B.sched.end(), small.begin(), small.end());
-        L.big_begin = (int)B.sched.size();
-        L.big_count = (int)big.size();
-        B.sched.insert(B.sched.end(), big.begin(), big.end());
-        L.all_count = L.tiny_count + L.small_count + L.big_count;
-        B.n_tiny += L.tiny_count; B.n_small += L.small_count; B.n_big += L.big_count;
+        L.all_begin = (int)B.sched.size();
+        for (int fc = 0; fc < NFC; fc++) {
+            L.begin[fc] = (int)B.sched.size();
+            L.count[fc] = (int)cls[fc].size();
+            B.sched.insert(B.sched.end(), cls[fc].begin(), cls[fc].end());
+            if (fc >= FC_MID)
+                for (int s : cls[fc]) {           // pivot-block inverse for the multi-CTA solves
+                    B.Xoff[s] = B.x_total;
+                    B.x_total += (int64_t)ld_of(cols(s)) * cols(s);
+                }
+        }
+        L.all_count = (int)B.sched.size() - L.all_begin;
+        L.solo_count = L.count[FC_T32] + L.count[FC_S64] + L.count[FC_S104] + L.count[FC_S152];
+        L.wide_begin = L.begin[FC_MID];
+        L.wide_count = L.all_count - L.solo_count;
+        B.n_tiny += L.count[FC_T32];
+        B.n_small += L.solo_count - L.count[FC_T32];
+        B.n_big += L.wide_count;
     }
     // pivot-block inverses: every big supernode with more than one WB block takes part in the
     // recursive merge; they are batched over the whole tree (independent of the levels)

@@ -75,24 +75,29 @@ struct DBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// Front classes of a level; the supernodes of a level are stored in d_sched in this order.
+//   T32 .. S152 : whole front (N x N) in shared memory, one CTA per front
+//   MID, MIDL   : N x c panel in shared memory (<= 96 KB / <= 192 KB), update block by tiles
+//   BIG         : blocked right-looking in HBM, outer block WB, FP64 tensor-core tiles
+enum FrontClass { FC_T32 = 0, FC_S64, FC_S104, FC_S152, FC_MID, FC_MIDL, FC_BIG, NFC };
+constexpr int FC_MAXN[4] = {32, 64, 104, 152};
+constexpr int SMALL_N = 152;          // 152*152*8 = 184,832 B of shared memory
+constexpr int MID_PANEL = 12000;      // doubles
+constexpr int MIDL_PANEL = 24000;     // doubles
+constexpr int NB = 32;                // block-column width of the LDL' big-front path
+constexpr int WB = 128;               // outer block width of the Cholesky big-front path (DMMA)
+
 // Per-level schedule built on the host from Symbolic.
 struct LevelPlan {
-    int tiny_begin = 0, tiny_count = 0;      // fronts with N <= TINY_N  (indices into d_sched)
-    int small_begin = 0, small_count = 0;    // fronts with N <= SMALL_N
-    int big_begin = 0, big_count = 0;        // the rest: blocked path in global memory
-    int small_maxN = 0, tiny_maxN = 0;
-    int big_maxN = 0, big_maxC = 0;
-    int all_begin = 0, all_count = 0;        // every supernode of the level (solves)
-    int all_maxN = 0;
+    int begin[NFC] = {0}, count[NFC] = {0}, maxN[NFC] = {0}, maxC[NFC] = {0}, maxPanel[NFC] = {0};
+    int all_begin = 0, all_count = 0;          // every supernode of the level
+    int solo_count = 0;                        // classes T32 .. S152 (a prefix of the level)
+    int wide_begin = 0, wide_count = 0;        // classes MID .. BIG (the rest)
+    int wide_maxN = 0, wide_maxC = 0, wide_maxR = 0;
     // big fronts are sorted by pivot-column count (descending); outer step t of the blocked
     // factorisation touches the first step_count[t] of them
     std::vector<int> step_count, step_maxN;
 };
-
-constexpr int TINY_N = 32;
-constexpr int SMALL_N = 152;   // 152*152*8 = 184,832 B of shared memory
-constexpr int NB = 32;         // block-column width of the LDL' big-front path
-constexpr int WB = 128;        // outer block width of the Cholesky big-front path (DMMA)
 
 // ---- kernels_assembly.cu
 void launch_sigma_T(const double* Jv, const int* Jrow, const double* y, const double* s,
@@ -117,8 +122,6 @@ void launch_ctl_single(DeltaState* st_d, double delta, int mode, cudaStream_t st
 cudaError_t factor_configure();
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode, cudaStream_t st);
-void launch_big_extend_add(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
-                           double* CB, DeltaState* st_d, cudaStream_t st);
 
 // ---- kernels_dense.cu  (Cholesky of big fronts on the FP64 tensor pipe, pivot-block inverses,
 //                         multi-CTA triangular solves for big supernodes)
@@ -129,8 +132,9 @@ struct TrtriPlan {
     std::vector<int> level_pairs;     // merge level l: max number of block pairs per supernode
 };
 cudaError_t dense_configure();
-void launch_big_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
-                           double* CB, double* Xinv, DeltaState* st_d, cudaStream_t st);
+// medium + big fronts of one level (Cholesky)
+void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
+                            double* CB, double* Xinv, DeltaState* st_d, cudaStream_t st);
 void launch_trtri(const DevSym& S, const TrtriPlan& T, const int* d_sched, const double* Lval,
                   double* Xinv, double* Twork, const DeltaState* st_d, cudaStream_t st);
 void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,

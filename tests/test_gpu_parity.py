@@ -112,3 +112,49 @@ def test_options_do_not_change_results(pkg, orc):
     _compare(pkg, orc, p, opts={"relax": 0})
     _compare(pkg, orc, p, opts={"nd_leaf": 16})
     _compare(pkg, orc, p, opts={"ordering": 1})
+
+
+def _full_size_properties(pkg, prob, expect_fac=None):
+    """BASELINE.json sizes: the oracle is too slow here, so check size-independent
+    properties of the result instead: the delta loop accepts the convex system at once,
+    the direction satisfies the Newton system it claims to solve (relative residual in
+    the inf norm, evaluated on the host with scipy from the inputs, not from device data)."""
+    pars = pkg.Class_parameters()
+    it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=0.0)
+    k = pkg.pick_KKT_solver(pars)
+    k.initialize(it)
+    k.form_system(it)
+    st, nf, delta = pkg.ipopt_strategy(it, k, pars)
+    assert st == "success"
+    if expect_fac is not None:
+        assert nf == expect_fac, (nf, delta)
+    sig = prob.y / prob.s
+    Hs = prob.H + sp.tril(prob.H, -1).T
+    for r in prob.rhs:
+        k.kkt_associate_rhs(it, pkg.System_rhs(*r))
+        k.compute_direction()
+        dx, dy, ds = k.dir.x, k.dir.y, k.dir.s
+        b = r[0] + prob.J.T @ (r[1] * sig + r[2] / prob.s)
+        Mdx = prob.J.T @ (sig * (prob.J @ dx)) + Hs @ dx + delta * dx
+        rel = np.abs(Mdx - b).max() / np.abs(b).max()
+        assert rel <= 1e-9, (prob.name, "schur residual", rel)
+        assert k.kkt_err_norm.ratio <= 1e-6, k.kkt_err_norm
+        Jdx = prob.J @ dx
+        assert np.allclose(ds, Jdx - r[1], rtol=1e-12, atol=1e-12 * np.abs(Jdx).max())
+    k.finalize()
+
+
+def test_full_size_sparse_qp(pkg):
+    _full_size_properties(pkg, pkg.problems.sparse_qp(), expect_fac=1)
+
+
+def test_full_size_chain(pkg):
+    _full_size_properties(pkg, pkg.problems.chain(nh=25000), expect_fac=1)
+
+
+def test_full_size_elec_dense(pkg):
+    _full_size_properties(pkg, pkg.problems.elec(400))
+
+
+def test_mid_size_pde(pkg):
+    _full_size_properties(pkg, pkg.problems.pde_control(40), expect_fac=1)
