@@ -197,166 +197,195 @@ __device__ __forceinline__ double* front_elem(const Front& d, double* Lval, doub
 
 // ---------------------------------------------------------------------------
 // Cholesky of a shared-memory panel (n rows, c <= 128 pivot columns) in 32-column
-// sub-blocks: the diagonal 32 x 32 block is factorised and inverted by one warp in
-// registers (shuffles, no block barrier), the rows below are multiplied by that
-// inverse, the remaining panel columns get the rank-32 update.  The inverse of the
-// whole c x c pivot block is left in global memory X (ldx) for the TRSM-as-GEMM of
-// the big fronts and for the multi-CTA triangular solves.
+// sub-blocks: the diagonal 32 x 32 block is factorised and inverted by one warp
+// (warp-synchronous, no block barrier), the rows below are multiplied by that
+// inverse, the remaining panel columns get the rank-32 update.  When Xs != nullptr
+// the inverse of the whole c x c pivot block is assembled in shared memory as
+// 32 x 32 blocks (block (I,J), I >= J, at Xs + (I(I+1)/2 + J) * INVBUF, ld 33): the
+// big fronts need it for the TRSM-as-GEMM and for the multi-CTA triangular solves.
+// Loops are kept rolled on purpose: the code runs once per block, so its size (not
+// its issue rate) is what the instruction cache sees.
 // ---------------------------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int INVLD = 33;
 constexpr int INVBUF = 32 * INVLD;           // doubles
-constexpr int TBUF = 3 * INVBUF;             // doubles: up to 3 block pairs in flight
 
-__device__ __forceinline__ bool warp_potrf32(double* P, int ld, int j0, int w, double* invbuf,
-                                             double* X, int ldx) {
-    const int lane = threadIdx.x & 31;
-    double a[32];
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-        double v = (j == lane) ? 1.0 : 0.0;                 // padding rows: identity
-        if (lane < w && j <= lane) v = P[(j0 + lane) + (size_t)(j0 + j) * ld];
-        a[j] = v;
-    }
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-        const double d = __shfl_sync(FULL, a[j], j);
-        if (!(d > 0.0)) ok = false;          // pivot <= 0 or NaN (julia.jl:39-41); uniform across the warp
-        const double rs = rsqrt(d);
-        const double lj = a[j] * rs;         // lane j: d * rsqrt(d) = sqrt(d)
-        a[j] = lj;
-#pragma unroll
-        for (int k = j + 1; k < 32; k++) {
-            const double lk = __shfl_sync(FULL, lj, k);
-            if (lane >= k) a[k] -= lj * lk;
+// Cholesky of the w x w (w <= 32) block at (j0, j0) of the shared-memory panel P, in place,
+// fused with the inverse of the factor (left in invbuf, ld 33), by the whole CTA:
+// per column two barriers; phase A scales column j of L and row j of X by 1/L[j,j],
+// phase B applies the rank-1 update to the trailing block columns and eliminates
+// L[i,j] X[j,:] from the later rows of X.  Every thread owns one element per phase.
+__device__ bool cta_potrf32_inv(double* P, int ld, int j0, int w, double* invbuf) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int i = tid & 31, q = tid >> 5, nq = nthr >> 5;
+    double* B = P + j0 + (size_t)j0 * ld;
+    for (int e = tid; e < INVBUF; e += nthr) invbuf[e] = ((e % INVLD) == (e / INVLD)) ? 1.0 : 0.0;
+    __syncthreads();
+    const bool rv = i < w;
+    for (int j = 0; j < w; j++) {
+        double* cj = B + (size_t)j * ld;
+        const double d = cj[j];              // final: the barrier below / the loop-end barrier ordered it
+        if (!(d > 0.0)) return false;        // pivot <= 0 or NaN (julia.jl:39-41); uniform across the CTA
+        const double rs = rsqrt(d);          // = 1 / L[j,j]
+        // phase A: column j of L (below the diagonal) and row j of X; the diagonal entry itself
+        // is rewritten in phase B so that late readers of d are safe
+        if (q == 0) { if (rv && i > j) cj[i] *= rs; }
+        else if (q == 1) { if (i <= j) invbuf[j + i * INVLD] *= rs; }     // X[j, 0..j]
+        __syncthreads();
+        if (rv && i > j) {
+            const double lij = cj[i];
+            for (int k = j + 1 + q; k <= i; k += nq) B[i + (size_t)k * ld] -= lij * cj[k];
+            for (int jc = q; jc <= j; jc += nq) invbuf[i + jc * INVLD] -= lij * invbuf[j + jc * INVLD];
         }
-    }
-    if (!ok) return false;
-#pragma unroll
-    for (int j = 0; j < 32; j++)
-        if (lane < w && j <= lane) P[(j0 + lane) + (size_t)(j0 + j) * ld] = a[j];
-    // inverse: lane j owns column j of X = L^-1 (forward substitution, rows broadcast by shuffles)
-    double dg = 1.0;
-#pragma unroll
-    for (int j = 0; j < 32; j++) if (lane == j) dg = a[j];
-    const double rd = 1.0 / dg;
-    double x[32];
-#pragma unroll
-    for (int k = 0; k < 32; k++) {
-        double acc = (k == lane) ? 1.0 : 0.0;
-#pragma unroll
-        for (int m = 0; m < k; m++) acc -= __shfl_sync(FULL, a[m], k) * x[m];
-        x[k] = acc * __shfl_sync(FULL, rd, k);
-    }
-#pragma unroll
-    for (int k = 0; k < 32; k++) {
-        invbuf[k + lane * INVLD] = x[k];
-        if (k >= lane && k < w) X[(j0 + k) + (size_t)(j0 + lane) * ldx] = x[k];
+        if (tid == 0) cj[j] = d * rs;        // sqrt(d)
+        __syncthreads();
     }
     return true;
 }
 
+__device__ __forceinline__ double* xs_block(double* Xs, int I, int J) { return Xs + (I * (I + 1) / 2 + J) * INVBUF; }
+
+// Warp-level FP64 tensor-core product on shared-memory operands (DMMA m8n8k4), 16 x 16 tile:
+//   acc += A[m0.., 0..K) * B^T, A element (m,k) at A[m + k*lda]; B element (n,k) at
+//   B[n + k*ldb] (B_KC = false) or B[k + n*ldb] (B_KC = true).  Rows >= M / N read as zero.
+template <bool B_KC>
+__device__ __forceinline__ void warp_tile16(double (&acc)[2][2][2], const double* A, int lda, int m0, int M,
+                                            const double* B, int ldb, int n0, int N, int K) {
+    const int lane = threadIdx.x & 31, q = lane & 3, g = lane >> 2;
+    const bool ma = m0 + g < M, mb = m0 + 8 + g < M, na = n0 + g < N, nb = n0 + 8 + g < N;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        const int kk = k0 + q;
+        const bool kv = kk < K;
+        const double a0 = (kv && ma) ? A[(m0 + g) + (size_t)kk * lda] : 0.0;
+        const double a1 = (kv && mb) ? A[(m0 + 8 + g) + (size_t)kk * lda] : 0.0;
+        double b0, b1;
+        if (B_KC) {
+            b0 = (kv && na) ? B[kk + (size_t)(n0 + g) * ldb] : 0.0;
+            b1 = (kv && nb) ? B[kk + (size_t)(n0 + 8 + g) * ldb] : 0.0;
+        } else {
+            b0 = (kv && na) ? B[(n0 + g) + (size_t)kk * ldb] : 0.0;
+            b1 = (kv && nb) ? B[(n0 + 8 + g) + (size_t)kk * ldb] : 0.0;
+        }
+        dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+        dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+        dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+        dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+    }
+}
+// MODE 0: C = acc, 1: C += acc, 2: C -= acc, 3: C = -acc
+template <int MODE>
+__device__ __forceinline__ void warp_tile16_store(const double (&acc)[2][2][2], double* C, int ldc, int m0, int M,
+                                                  int n0, int N) {
+    const int lane = threadIdx.x & 31, q = lane & 3, g = lane >> 2;
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int m = m0 + 8 * a + g, n = n0 + 8 * b + 2 * q + e;
+                if (m < M && n < N) {
+                    double* p = C + m + (size_t)n * ldc;
+                    const double v = acc[a][b][e];
+                    if (MODE == 0) *p = v; else if (MODE == 1) *p += v; else if (MODE == 2) *p -= v; else *p = -v;
+                }
+            }
+}
+
 // P: shared-memory panel, column-major (ld), n rows, c pivot columns (top c x c = pivot block).
-// invbuf: INVBUF doubles, tbuf: TBUF doubles, s_flag: shared int preset to 0.
-__device__ bool panel_chol_smem(double* P, int ld, int n, int c, double* invbuf, double* tbuf,
-                                double* X, int ldx, int* s_flag) {
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+// invbuf: INVBUF doubles; s_flag unused (kept for the callers' failure flag).
+template <bool PROF = false>
+__device__ bool panel_chol_smem(double* P, int ld, int n, int c, double* invbuf, double* Xs,
+                                long long* stamps = nullptr) {
+    int ns = 0;
+#define OPB_STAMP() do { if (PROF && threadIdx.x == 0) stamps[ns++] = clock64(); } while (0)
+    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, nwarp = nthr >> 5;
     for (int j0 = 0; j0 < c; j0 += 32) {
         const int w = min(32, c - j0);
-        if (warp == 0) {
-            if (!warp_potrf32(P, ld, j0, w, invbuf, X, ldx) && lane == 0) *s_flag = 1;
+        OPB_STAMP();
+        if (!cta_potrf32_inv(P, ld, j0, w, invbuf)) return false;
+        if (Xs) {
+            double* xb = xs_block(Xs, j0 >> 5, j0 >> 5);
+            for (int e = tid; e < INVBUF; e += nthr) xb[e] = invbuf[e];
         }
-        __syncthreads();
-        if (*s_flag) return false;
+        OPB_STAMP();
         const int i1 = j0 + w;
-        // rows below the diagonal block: L = A * inv(Ld)^T, one thread per row
-        for (int i = i1 + tid; i < n; i += nthr) {
-            double arow[32];
-#pragma unroll
-            for (int k = 0; k < 32; k++) arow[k] = (k < w) ? P[i + (size_t)(j0 + k) * ld] : 0.0;
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                if (j < w) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int k = 0; k <= j; k++) acc += arow[k] * invbuf[j + k * INVLD];
-                    P[i + (size_t)(j0 + j) * ld] = acc;
-                }
+        // rows below the diagonal block: L = A * inv(Ld)^T, in place; a warp owns 16 rows and all
+        // w columns, so it has read its rows completely before it overwrites them
+        {
+            const int nrt = (n - i1 + 15) / 16;
+            for (int it = warp; it < nrt; it += nwarp) {
+                const int m0 = i1 + 16 * it;
+                double acc0[2][2][2] = {}, acc1[2][2][2] = {};
+                warp_tile16<false>(acc0, P + (size_t)j0 * ld, ld, m0, n, invbuf, INVLD, 0, w, w);
+                if (w > 16) warp_tile16<false>(acc1, P + (size_t)j0 * ld, ld, m0, n, invbuf, INVLD, 16, w, w);
+                __syncwarp();
+                warp_tile16_store<0>(acc0, P + (size_t)j0 * ld, ld, m0, n, 0, w);
+                if (w > 16) warp_tile16_store<0>(acc1, P + (size_t)j0 * ld, ld, m0, n, 16, w);
             }
         }
         __syncthreads();
-        // rank-w update of the remaining panel columns (lower part): item = 4 columns x 32 rows
+        OPB_STAMP();
+        // rank-w update of the remaining panel columns [i1, c), rows [i1, n), lower tiles only
         if (i1 < c) {
-            const int nrc = (n - i1 + 31) / 32;
-            const int ncg = (c - i1 + 3) / 4;
-            for (int it = warp; it < ncg * nrc; it += nwarp) {
-                const int g = it / nrc, rc = it % nrc;
-                const int jb = i1 + 4 * g;
-                if (i1 + 32 * rc + 31 < jb) continue;
-                const int i = i1 + 32 * rc + lane;
-                const bool iv = i < n;
-                double acc[4] = {0.0, 0.0, 0.0, 0.0};
-                for (int k = 0; k < w; k++) {
-                    const double* col = P + (size_t)(j0 + k) * ld;
-                    const double pik = iv ? col[i] : 0.0;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int j = jb + q;
-                        acc[q] += pik * ((j < c) ? col[j] : 0.0);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int j = jb + q;
-                    if (j < c && iv && i >= j) P[i + (size_t)j * ld] -= acc[q];
-                }
+            const int ntm = (n - i1 + 15) / 16, ntn = (c - i1 + 15) / 16;
+            const double* Ablk = P + (size_t)j0 * ld;
+            for (int it = warp; it < ntm * ntn; it += nwarp) {
+                const int mt = it % ntm, nt = it / ntm;
+                if (mt < nt) continue;
+                double acc[2][2][2] = {};
+                warp_tile16<false>(acc, Ablk, ld, i1 + 16 * mt, n, Ablk, ld, i1 + 16 * nt, c, w);
+                warp_tile16_store<2>(acc, P, ld, i1 + 16 * mt, n, i1 + 16 * nt, c);
             }
         }
         __syncthreads();
     }
+    OPB_STAMP();
+    if (!Xs) return true;
     // off-diagonal blocks of X = inv(L11) by block forward substitution:
-    //   X_IJ = - X_II * sum_{K=J}^{I-1} L_IK X_KJ
+    //   T = sum_{K=J}^{I-1} L_IK X_KJ ;  X_IJ = - X_II T        (32 x 32 blocks, 4 warp tiles each)
     const int nb = (c + 31) >> 5;
     for (int dist = 1; dist < nb; dist++) {
-        const int npair = nb - dist;            // (J, J + dist), J = 0 .. npair-1; at most 3
-        for (int e = tid; e < npair * 1024; e += nthr) {
-            const int pr = e >> 10, ii = e & 31, jj = (e >> 5) & 31;
-            const int I = pr + dist, J = pr;
-            const int gi = 32 * I + ii, gj = 32 * J + jj;
-            double acc = 0.0;
-            if (gi < c) {
-                const double* xc = X + (size_t)gj * ldx;
-                for (int k = gj; k < 32 * I; k++) acc += P[gi + (size_t)k * ld] * xc[k];
-            }
-            tbuf[pr * INVBUF + ii + jj * INVLD] = acc;
+        const int npair = nb - dist;
+        // phase 1: T of pair p kept in the destination block X_IJ
+        for (int it = warp; it < npair * 4; it += nwarp) {
+            const int pr = it >> 2, mt = it & 1, nt = (it >> 1) & 1;
+            const int J = pr, I = pr + dist;
+            double acc[2][2][2] = {};
+            for (int K = J; K < I; K++)
+                warp_tile16<true>(acc, P + (size_t)(32 * K) * ld, ld, 32 * I + 16 * mt, c,
+                                  xs_block(Xs, K, J), INVLD, 16 * nt, 32, 32);
+            warp_tile16_store<0>(acc, xs_block(Xs, I, J), INVLD, 16 * mt, 32, 16 * nt, 32);
         }
         __syncthreads();
-        for (int e = tid; e < npair * 1024; e += nthr) {
-            const int pr = e >> 10, ii = e & 31, jj = (e >> 5) & 31;
-            const int I = pr + dist, J = pr;
-            const int gi = 32 * I + ii, gj = 32 * J + jj;
-            if (gi < c) {
-                double acc = 0.0;
-                const double* t = tbuf + pr * INVBUF + jj * INVLD;
-                for (int m = 0; m <= ii; m++) acc += X[gi + (size_t)(32 * I + m) * ldx] * t[m];
-                X[gi + (size_t)gj * ldx] = -acc;
-            }
+        // phase 2: X_IJ = - X_II * T, computed into registers by the warp that owns the whole
+        // 32 x 16 half block column, then written over T
+        for (int it = warp; it < npair * 2; it += nwarp) {
+            const int pr = it >> 1, nt = it & 1;
+            const int J = pr, I = pr + dist;
+            double acc0[2][2][2] = {}, acc1[2][2][2] = {};
+            warp_tile16<true>(acc0, xs_block(Xs, I, I), INVLD, 0, 32, xs_block(Xs, I, J), INVLD, 16 * nt, 32, 32);
+            warp_tile16<true>(acc1, xs_block(Xs, I, I), INVLD, 16, 32, xs_block(Xs, I, J), INVLD, 16 * nt, 32, 32);
+            __syncwarp();
+            warp_tile16_store<3>(acc0, xs_block(Xs, I, J), INVLD, 0, 32, 16 * nt, 32);
+            warp_tile16_store<3>(acc1, xs_block(Xs, I, J), INVLD, 16, 32, 16 * nt, 32);
         }
         __syncthreads();
     }
+    OPB_STAMP();
+#undef OPB_STAMP
     return true;
 }
 
 constexpr int PT = 512;              // threads of the panel kernels
-constexpr int LDD = WB + 1;
+constexpr int LDD = WB + 4;          // 132: fragment loads are bank-conflict free (LDD % 16 == 4)
+constexpr int XS_BLOCKS = 10;        // lower 32 x 32 blocks of a 128 x 128 triangle
 
 // diagonal block of outer step t of a big front: Cholesky + inverse
 __global__ void __launch_bounds__(PT)
 chol_diag_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval, double* __restrict__ Xinv,
                  int t, DeltaState* st) {
-    extern __shared__ double D[];          // LDD * WB + INVBUF + TBUF
-    __shared__ int s_flag;
+    extern __shared__ double D[];          // LDD * WB + INVBUF + XS_BLOCKS * INVBUF
     if (stop_requested(st)) return;
     const Front d = get_front(S, list[blockIdx.x]);
     const int j0 = t * WB;
@@ -364,44 +393,43 @@ chol_diag_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
     const int b = min(WB, d.c - j0);
     const int tid = threadIdx.x;
     double* invbuf = D + LDD * WB;
-    double* tbuf = invbuf + INVBUF;
+    double* Xs = invbuf + INVBUF;
     double* base = Lval + d.loff + j0 + (size_t)j0 * d.ld;
     for (int idx = tid; idx < b * b; idx += PT) {
         const int i = idx % b, j = idx / b;
         D[i + j * LDD] = (i >= j) ? base[i + (size_t)j * d.ld] : 0.0;
     }
-    if (tid == 0) s_flag = 0;
     __syncthreads();
-    double* X = Xinv + d.xoff + j0 + (size_t)j0 * d.ldx;
-    if (!panel_chol_smem(D, LDD, b, b, invbuf, tbuf, X, d.ldx, &s_flag)) {
+    if (!panel_chol_smem(D, LDD, b, b, invbuf, Xs)) {
         if (tid == 0) st->fail = 1;
         return;
     }
+    double* X = Xinv + d.xoff + j0 + (size_t)j0 * d.ldx;
     for (int idx = tid; idx < b * b; idx += PT) {
         const int i = idx % b, j = idx / b;
-        if (i >= j) base[i + (size_t)j * d.ld] = D[i + j * LDD];
+        if (i >= j) {
+            base[i + (size_t)j * d.ld] = D[i + j * LDD];
+            X[i + (size_t)j * d.ldx] = xs_block(Xs, i >> 5, j >> 5)[(i & 31) + (j & 31) * INVLD];
+        }
     }
 }
 
 // medium fronts: the whole N x c panel lives in shared memory.  Children's update blocks are
-// added into the panel columns (ascending child order), the panel is factorised, its pivot-block
-// inverse goes to Xinv; the update block of the front is produced later by front_cb_kernel.
+// added into the panel columns (ascending child order) and the panel is factorised; the update
+// block of the front is produced later by front_cb_kernel.
 __global__ void __launch_bounds__(PT)
 mid_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval,
-                 const double* __restrict__ CB, double* __restrict__ Xinv, DeltaState* st) {
-    extern __shared__ double P[];          // N * c + INVBUF + TBUF
-    __shared__ int s_flag;
+                 const double* __restrict__ CB, DeltaState* st) {
+    extern __shared__ double P[];          // N * c + INVBUF
     if (stop_requested(st)) return;
     const Front d = get_front(S, list[blockIdx.x]);
     const int N = d.N, c = d.c, tid = threadIdx.x;
     double* invbuf = P + (size_t)N * c;
-    double* tbuf = invbuf + INVBUF;
     double* panel = Lval + d.loff;
     for (int idx = tid; idx < N * c; idx += PT) {
         const int i = idx % N, j = idx / N;
         P[idx] = panel[i + (size_t)j * d.ld];
     }
-    if (tid == 0) s_flag = 0;
     __syncthreads();
     for (int k = S.child_ptr[d.s]; k < S.child_ptr[d.s + 1]; k++) {
         const int ch = S.child_list[k];
@@ -418,13 +446,13 @@ mid_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
         }
         __syncthreads();
     }
-    if (!panel_chol_smem(P, N, N, c, invbuf, tbuf, Xinv + d.xoff, d.ldx, &s_flag)) {
+    if (!panel_chol_smem(P, N, N, c, invbuf, nullptr)) {
         if (tid == 0) st->fail = 1;
         return;
     }
     for (int idx = tid; idx < N * c; idx += PT) {
         const int i = idx % N, j = idx / N;
-        panel[i + (size_t)j * d.ld] = P[idx];
+        if (i >= j) panel[i + (size_t)j * d.ld] = P[idx];      // the strictly upper part holds scratch
     }
 }
 
@@ -831,8 +859,8 @@ wide_bwd_tri_kernel(DevSym S, const int* __restrict__ list, const double* __rest
     if (lane == 0) x[d.first + k] = acc;
 }
 
-inline size_t diag_smem() { return (size_t)(LDD * WB + INVBUF + TBUF) * sizeof(double); }
-inline size_t mid_smem(int panel) { return (size_t)(panel + INVBUF + TBUF) * sizeof(double); }
+inline size_t diag_smem() { return (size_t)(LDD * WB + INVBUF + XS_BLOCKS * INVBUF) * sizeof(double); }
+inline size_t mid_smem(int panel) { return (size_t)(panel + INVBUF) * sizeof(double); }
 
 }  // namespace
 
@@ -857,7 +885,7 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
     // medium fronts: panel in shared memory
     for (int fc = FC_MID; fc <= FC_MIDL; fc++) {
         if (!L.count[fc]) continue;
-        mid_panel_kernel<<<L.count[fc], PT, mid_smem(L.maxPanel[fc]), st>>>(S, d_sched + L.begin[fc], Lval, CB, Xinv, st_d);
+        mid_panel_kernel<<<L.count[fc], PT, mid_smem(L.maxPanel[fc]), st>>>(S, d_sched + L.begin[fc], Lval, CB, st_d);
         count_launch();
     }
     // big fronts: blocked right-looking factorisation of the panel columns
@@ -916,23 +944,25 @@ void launch_trtri(const DevSym& S, const TrtriPlan& T, const int* d_sched, const
 
 void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
                            const double* Xinv, double* x, double* xnew, double* u, cudaStream_t st) {
-    if (!L.wide_count) return;
-    const int* list = d_sched + L.wide_begin;
-    wide_fwd_gather_kernel<<<L.wide_count, WT, 0, st>>>(S, list, x, u);
-    dim3 g1((L.wide_maxC + SLAB - 1) / SLAB, L.wide_count);
+    const int cnt = L.count[FC_BIG];
+    if (!cnt) return;
+    const int* list = d_sched + L.begin[FC_BIG];
+    wide_fwd_gather_kernel<<<cnt, WT, 0, st>>>(S, list, x, u);
+    dim3 g1((L.maxC[FC_BIG] + SLAB - 1) / SLAB, cnt);
     wide_fwd_tri_kernel<<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew);
-    dim3 g2((L.wide_maxN + SLAB - 1) / SLAB, L.wide_count);
+    dim3 g2((L.maxN[FC_BIG] + SLAB - 1) / SLAB, cnt);
     wide_fwd_upd_kernel<<<g2, WT, 0, st>>>(S, list, Lval, x, xnew, u);
     count_launch(3);
 }
 
 void launch_solve_wide_bwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
                            const double* Xinv, double* x, double* xnew, double* u, cudaStream_t st) {
-    if (!L.wide_count) return;
-    const int* list = d_sched + L.wide_begin;
-    dim3 g0((L.wide_maxR + WT) / WT, L.wide_count);
+    const int cnt = L.count[FC_BIG];
+    if (!cnt) return;
+    const int* list = d_sched + L.begin[FC_BIG];
+    dim3 g0((L.maxN[FC_BIG] + WT) / WT, cnt);
     wide_bwd_gather_kernel<<<g0, WT, 0, st>>>(S, list, x, u);
-    dim3 g1((L.wide_maxC + KG - 1) / KG, L.wide_count);
+    dim3 g1((L.maxC[FC_BIG] + KG - 1) / KG, cnt);
     wide_bwd_upd_kernel<<<g1, WT, 0, st>>>(S, list, Lval, x, xnew, u);
     wide_bwd_tri_kernel<<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew);
     count_launch(3);

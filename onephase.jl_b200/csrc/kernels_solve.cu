@@ -143,18 +143,19 @@ cudaError_t solve_configure() { return cudaSuccess; }
 void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                   const double* Lval, const double* Xinv, double* x, double* xnew, double* u, int mode,
                   cudaStream_t st) {
-    // Cholesky: big supernodes take the multi-CTA path through inv(L11) (kernels_dense.cu);
+    // Cholesky: BIG supernodes take the multi-CTA path through inv(L11) (kernels_dense.cu), the
+    // other classes (front or panel fits in shared memory) are solved by one CTA each;
     // LDL': every supernode is solved by one CTA.
     const bool wide = (mode == 0);
     for (size_t l = 0; l < plan.size(); l++) {
         const LevelPlan& L = plan[l];
-        const int solo = wide ? L.solo_count : L.all_count;
+        const int solo = wide ? L.all_count - L.count[FC_BIG] : L.all_count;
         if (solo) { fwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.all_begin, Lval, x, u, mode); count_launch(); }
         if (wide) launch_solve_wide_fwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
     }
     for (size_t l = plan.size(); l-- > 0;) {
         const LevelPlan& L = plan[l];
-        const int solo = wide ? L.solo_count : L.all_count;
+        const int solo = wide ? L.all_count - L.count[FC_BIG] : L.all_count;
         if (solo) { bwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.all_begin, Lval, x, u, mode); count_launch(); }
         if (wide) launch_solve_wide_bwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
     }

@@ -103,7 +103,7 @@ static void build_plan(Bundle& B) {
             L.begin[fc] = (int)B.sched.size();
             L.count[fc] = (int)cls[fc].size();
             B.sched.insert(B.sched.end(), cls[fc].begin(), cls[fc].end());
-            if (fc >= FC_MID)
+            if (fc == FC_BIG)
                 for (int s : cls[fc]) {           // pivot-block inverse for the multi-CTA solves
                     B.Xoff[s] = B.x_total;
                     B.x_total += (int64_t)ld_of(cols(s)) * cols(s);

@@ -83,7 +83,7 @@ enum FrontClass { FC_T32 = 0, FC_S64, FC_S104, FC_S152, FC_MID, FC_MIDL, FC_BIG,
 constexpr int FC_MAXN[4] = {32, 64, 104, 152};
 constexpr int SMALL_N = 152;          // 152*152*8 = 184,832 B of shared memory
 constexpr int MID_PANEL = 12000;      // doubles
-constexpr int MIDL_PANEL = 24000;     // doubles
+constexpr int MIDL_PANEL = 26000;     // doubles
 constexpr int NB = 32;                // block-column width of the LDL' big-front path
 constexpr int WB = 128;               // outer block width of the Cholesky big-front path (DMMA)
 
