@@ -211,33 +211,89 @@ constexpr int INVLD = 33;
 constexpr int INVBUF = 32 * INVLD;           // doubles
 
 // Cholesky of the w x w (w <= 32) block at (j0, j0) of the shared-memory panel P, in place,
-// fused with the inverse of the factor (left in invbuf, ld 33), by the whole CTA:
-// per column two barriers; phase A scales column j of L and row j of X by 1/L[j,j],
-// phase B applies the rank-1 update to the trailing block columns and eliminates
-// L[i,j] X[j,:] from the later rows of X.  Every thread owns one element per phase.
-__device__ bool cta_potrf32_inv(double* P, int ld, int j0, int w, double* invbuf) {
+// fused with the inverse of the factor (left in invbuf, ld 33).  Columns are taken eight at a
+// time: warp 0 factorises the 8-column panel in registers (lane = row, shuffles, no barrier)
+// and finalises the matching eight rows of X (lane = column); then the whole CTA applies the
+// rank-8 update to the trailing columns of the block and to the later rows of X.  Two block
+// barriers per eight columns; the register code is 8 x 8 unrolled, i.e. small.
+constexpr int PW = 8;
+__device__ bool cta_potrf32_inv(double* P, int ld, int j0, int w, double* invbuf, int* s_fail) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int i = tid & 31, q = tid >> 5, nq = nthr >> 5;
     double* B = P + j0 + (size_t)j0 * ld;
     for (int e = tid; e < INVBUF; e += nthr) invbuf[e] = ((e % INVLD) == (e / INVLD)) ? 1.0 : 0.0;
+    if (tid == 0) *s_fail = 0;
     __syncthreads();
     const bool rv = i < w;
-    for (int j = 0; j < w; j++) {
-        double* cj = B + (size_t)j * ld;
-        const double d = cj[j];              // final: the barrier below / the loop-end barrier ordered it
-        if (!(d > 0.0)) return false;        // pivot <= 0 or NaN (julia.jl:39-41); uniform across the CTA
-        const double rs = rsqrt(d);          // = 1 / L[j,j]
-        // phase A: column j of L (below the diagonal) and row j of X; the diagonal entry itself
-        // is rewritten in phase B so that late readers of d are safe
-        if (q == 0) { if (rv && i > j) cj[i] *= rs; }
-        else if (q == 1) { if (i <= j) invbuf[j + i * INVLD] *= rs; }     // X[j, 0..j]
-        __syncthreads();
-        if (rv && i > j) {
-            const double lij = cj[i];
-            for (int k = j + 1 + q; k <= i; k += nq) B[i + (size_t)k * ld] -= lij * cj[k];
-            for (int jc = q; jc <= j; jc += nq) invbuf[i + jc * INVLD] -= lij * invbuf[j + jc * INVLD];
+    for (int jp = 0; jp < w; jp += PW) {
+        if (q == 0) {
+            double p[PW], rs[PW];
+#pragma unroll
+            for (int t = 0; t < PW; t++) {
+                const int j = jp + t;
+                p[t] = (rv && j < w && i >= j) ? B[i + (size_t)j * ld] : ((i == j) ? 1.0 : 0.0);
+            }
+            bool ok = true;
+#pragma unroll
+            for (int t = 0; t < PW; t++) {
+                const int j = jp + t;
+                const double d = __shfl_sync(FULL, p[t], j & 31);
+                if (!(d > 0.0)) ok = false;          // pivot <= 0 or NaN (julia.jl:39-41)
+                rs[t] = rsqrt(d);                    // = 1 / L[j,j]
+                const double lt = (i >= j) ? p[t] * rs[t] : 0.0;     // lane j: d * rsqrt(d) = sqrt(d)
+                p[t] = lt;
+#pragma unroll
+                for (int u = t + 1; u < PW; u++) {
+                    const double lu = __shfl_sync(FULL, lt, (jp + u) & 31);
+                    p[u] -= lt * lu;                 // rows above jp+u hold junk that is never stored
+                }
+            }
+            if (!ok) { if (i == 0) *s_fail = 1; }
+            else {
+#pragma unroll
+                for (int t = 0; t < PW; t++) {
+                    const int j = jp + t;
+                    if (rv && j < w && i >= j) B[i + (size_t)j * ld] = p[t];
+                }
+                // rows jp .. jp+7 of X (lane = column): scale by 1/L[j,j], eliminate from the later panel rows
+                double xr[PW];
+#pragma unroll
+                for (int t = 0; t < PW; t++) xr[t] = invbuf[((jp + t) & 31) + i * INVLD];
+#pragma unroll
+                for (int t = 0; t < PW; t++) {
+                    xr[t] *= rs[t];
+#pragma unroll
+                    for (int u = t + 1; u < PW; u++) {
+                        const double lut = __shfl_sync(FULL, p[t], (jp + u) & 31);     // L[jp+u, jp+t]
+                        xr[u] -= lut * xr[t];
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < PW; t++)
+                    if (jp + t < w) invbuf[(jp + t) + i * INVLD] = xr[t];
+            }
         }
-        if (tid == 0) cj[j] = d * rs;        // sqrt(d)
+        __syncthreads();
+        if (*s_fail) return false;
+        // rank-8 update of the trailing columns of L and of the later rows of X
+        const int i1 = jp + PW;
+        if (rv && i >= i1) {
+            double li[PW];
+#pragma unroll
+            for (int t = 0; t < PW; t++) li[t] = B[i + (size_t)(jp + t) * ld];
+            for (int k = i1 + q; k <= i; k += nq) {
+                double acc = 0.0;
+#pragma unroll
+                for (int t = 0; t < PW; t++) acc += li[t] * B[k + (size_t)(jp + t) * ld];
+                B[i + (size_t)k * ld] -= acc;
+            }
+            for (int jc = q; jc < i1; jc += nq) {
+                double acc = 0.0;
+#pragma unroll
+                for (int t = 0; t < PW; t++) acc += li[t] * invbuf[(jp + t) + jc * INVLD];
+                invbuf[i + jc * INVLD] -= acc;
+            }
+        }
         __syncthreads();
     }
     return true;
@@ -293,9 +349,9 @@ __device__ __forceinline__ void warp_tile16_store(const double (&acc)[2][2][2], 
 }
 
 // P: shared-memory panel, column-major (ld), n rows, c pivot columns (top c x c = pivot block).
-// invbuf: INVBUF doubles; s_flag unused (kept for the callers' failure flag).
+// invbuf: INVBUF doubles; s_fail: one shared int.
 template <bool PROF = false>
-__device__ bool panel_chol_smem(double* P, int ld, int n, int c, double* invbuf, double* Xs,
+__device__ bool panel_chol_smem(double* P, int ld, int n, int c, double* invbuf, double* Xs, int* s_fail,
                                 long long* stamps = nullptr) {
     int ns = 0;
 #define OPB_STAMP() do { if (PROF && threadIdx.x == 0) stamps[ns++] = clock64(); } while (0)
@@ -303,7 +359,7 @@ __device__ bool panel_chol_smem(double* P, int ld, int n, int c, double* invbuf,
     for (int j0 = 0; j0 < c; j0 += 32) {
         const int w = min(32, c - j0);
         OPB_STAMP();
-        if (!cta_potrf32_inv(P, ld, j0, w, invbuf)) return false;
+        if (!cta_potrf32_inv(P, ld, j0, w, invbuf, s_fail)) return false;
         if (Xs) {
             double* xb = xs_block(Xs, j0 >> 5, j0 >> 5);
             for (int e = tid; e < INVBUF; e += nthr) xb[e] = invbuf[e];
@@ -386,6 +442,7 @@ __global__ void __launch_bounds__(PT)
 chol_diag_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval, double* __restrict__ Xinv,
                  int t, DeltaState* st) {
     extern __shared__ double D[];          // LDD * WB + INVBUF + XS_BLOCKS * INVBUF
+    __shared__ int s_fail;
     if (stop_requested(st)) return;
     const Front d = get_front(S, list[blockIdx.x]);
     const int j0 = t * WB;
@@ -395,22 +452,24 @@ chol_diag_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
     double* invbuf = D + LDD * WB;
     double* Xs = invbuf + INVBUF;
     double* base = Lval + d.loff + j0 + (size_t)j0 * d.ld;
-    for (int idx = tid; idx < b * b; idx += PT) {
-        const int i = idx % b, j = idx / b;
-        D[i + j * LDD] = (i >= j) ? base[i + (size_t)j * d.ld] : 0.0;
+    {
+        const int i = tid & (WB - 1);
+        for (int j = tid / WB; j < b; j += PT / WB)
+            if (i < b) D[i + j * LDD] = (i >= j) ? base[i + (size_t)j * d.ld] : 0.0;
     }
     __syncthreads();
-    if (!panel_chol_smem(D, LDD, b, b, invbuf, Xs)) {
+    if (!panel_chol_smem(D, LDD, b, b, invbuf, Xs, &s_fail)) {
         if (tid == 0) st->fail = 1;
         return;
     }
     double* X = Xinv + d.xoff + j0 + (size_t)j0 * d.ldx;
-    for (int idx = tid; idx < b * b; idx += PT) {
-        const int i = idx % b, j = idx / b;
-        if (i >= j) {
-            base[i + (size_t)j * d.ld] = D[i + j * LDD];
-            X[i + (size_t)j * d.ldx] = xs_block(Xs, i >> 5, j >> 5)[(i & 31) + (j & 31) * INVLD];
-        }
+    {
+        const int i = tid & (WB - 1);
+        for (int j = tid / WB; j < b; j += PT / WB)
+            if (i < b && i >= j) {
+                base[i + (size_t)j * d.ld] = D[i + j * LDD];
+                X[i + (size_t)j * d.ldx] = xs_block(Xs, i >> 5, j >> 5)[(i & 31) + (j & 31) * INVLD];
+            }
     }
 }
 
@@ -421,6 +480,7 @@ __global__ void __launch_bounds__(PT)
 mid_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval,
                  const double* __restrict__ CB, DeltaState* st) {
     extern __shared__ double P[];          // N * c + INVBUF
+    __shared__ int s_fail;
     if (stop_requested(st)) return;
     const Front d = get_front(S, list[blockIdx.x]);
     const int N = d.N, c = d.c, tid = threadIdx.x;
@@ -446,7 +506,7 @@ mid_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
         }
         __syncthreads();
     }
-    if (!panel_chol_smem(P, N, N, c, invbuf, nullptr)) {
+    if (!panel_chol_smem(P, N, N, c, invbuf, nullptr, &s_fail)) {
         if (tid == 0) st->fail = 1;
         return;
     }

@@ -10,6 +10,7 @@ using namespace opb;
 
 __global__ void __launch_bounds__(PT) prof_kernel(double* A, int b, int lda, long long* stamps, int* fail) {
     extern __shared__ double D[];
+    __shared__ int s_fail;
     const int tid = threadIdx.x;
     double* invbuf = D + LDD * WB;
     double* Xs = invbuf + INVBUF;
@@ -19,7 +20,7 @@ __global__ void __launch_bounds__(PT) prof_kernel(double* A, int b, int lda, lon
     for (int idx = tid; idx < b * b; idx += PT) { const int i = idx % b, j = idx / b; D[i + j * LDD] = (i >= j) ? base[i + (size_t)j * lda] : 0.0; }
     __syncthreads();
     if (tid == 0) st[1] = clock64();
-    bool ok = panel_chol_smem<true>(D, LDD, b, b, invbuf, Xs, st + 2);
+    bool ok = panel_chol_smem<true>(D, LDD, b, b, invbuf, Xs, &s_fail, st + 2);
     if (!ok) { if (tid == 0) *fail = 1; return; }
     if (tid == 0) st[40] = clock64();
     for (int idx = tid; idx < b * b; idx += PT) { const int i = idx % b, j = idx / b; if (i >= j) base[i + (size_t)j * lda] = D[i + j * LDD]; }
