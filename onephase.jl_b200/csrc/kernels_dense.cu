@@ -452,10 +452,9 @@ chol_diag_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
     double* invbuf = D + LDD * WB;
     double* Xs = invbuf + INVBUF;
     double* base = Lval + d.loff + j0 + (size_t)j0 * d.ld;
-    {
-        const int i = tid & (WB - 1);
-        for (int j = tid / WB; j < b; j += PT / WB)
-            if (i < b) D[i + j * LDD] = (i >= j) ? base[i + (size_t)j * d.ld] : 0.0;
+    for (int idx = tid; idx < b * b; idx += PT) {
+        const int i = idx % b, j = idx / b;
+        D[i + j * LDD] = (i >= j) ? base[i + (size_t)j * d.ld] : 0.0;
     }
     __syncthreads();
     if (!panel_chol_smem(D, LDD, b, b, invbuf, Xs, &s_fail)) {
@@ -463,13 +462,12 @@ chol_diag_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
         return;
     }
     double* X = Xinv + d.xoff + j0 + (size_t)j0 * d.ldx;
-    {
-        const int i = tid & (WB - 1);
-        for (int j = tid / WB; j < b; j += PT / WB)
-            if (i < b && i >= j) {
-                base[i + (size_t)j * d.ld] = D[i + j * LDD];
-                X[i + (size_t)j * d.ldx] = xs_block(Xs, i >> 5, j >> 5)[(i & 31) + (j & 31) * INVLD];
-            }
+    for (int idx = tid; idx < b * b; idx += PT) {
+        const int i = idx % b, j = idx / b;
+        if (i >= j) {
+            base[i + (size_t)j * d.ld] = D[i + j * LDD];
+            X[i + (size_t)j * d.ldx] = xs_block(Xs, i >> 5, j >> 5)[(i & 31) + (j & 31) * INVLD];
+        }
     }
 }
 
@@ -762,21 +760,27 @@ trtri_merge_kernel(DevSym S, const int* __restrict__ list, const double* __restr
 //   forward :  gather children -> x1 = X b1 -> u -= L21 x1
 //   backward:  u = x[rows] -> b1' = x1 - L21' u -> x1 = X' b1'
 // ---------------------------------------------------------------------------
-constexpr int WT = 256;
+constexpr int WT = 512;
 constexpr int SLAB = 32;      // rows per CTA in the row-oriented products
 constexpr int KG = WT / 32;   // k-groups (warps)
 
+// children's update vectors into this supernode's right-hand side; a CTA owns a range of
+// destination rows, children are applied in ascending order (deterministic, no atomics)
+constexpr int GR = 2048;      // destination rows per CTA
 __global__ void __launch_bounds__(WT)
 wide_fwd_gather_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ x, double* __restrict__ u) {
-    const int s = list[blockIdx.x];
+    const int s = list[blockIdx.y];
     const int first = S.sfirst[s];
     const int c = S.sfirst[s + 1] - first;
     const int64_t rp = S.rowptr[s];
     const int r = (int)(S.rowptr[s + 1] - rp);
+    const int row0 = blockIdx.x * GR;
+    if (row0 >= c + r) return;
+    const int row1 = min(c + r, row0 + GR);
     double* xs = x + first;
     double* us = u + rp;
     const int tid = threadIdx.x;
-    for (int t = tid; t < r; t += WT) us[t] = 0.0;
+    for (int i = max(row0, c) + tid; i < row1; i += WT) us[i - c] = 0.0;
     __syncthreads();
     for (int k = S.child_ptr[s]; k < S.child_ptr[s + 1]; k++) {
         const int ch = S.child_list[k];
@@ -784,7 +788,13 @@ wide_fwd_gather_kernel(DevSym S, const int* __restrict__ list, double* __restric
         const int rc = (int)(S.rowptr[ch + 1] - rpc);
         const int* __restrict__ relc = S.rel + rpc;
         const double* uc = u + rpc;
-        for (int t = tid; t < rc; t += WT) {
+        int lo = 0, hi = rc;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < row0) lo = mid + 1; else hi = mid; }
+        const int t0 = lo;
+        hi = rc;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < row1) lo = mid + 1; else hi = mid; }
+        const int t1 = lo;
+        for (int t = t0 + tid; t < t1; t += WT) {
             const int dst = relc[t];
             const double v = uc[t];
             if (dst < c) xs[dst] += v; else us[dst - c] += v;
@@ -809,10 +819,12 @@ wide_fwd_tri_kernel(DevSym S, const int* __restrict__ list, const double* __rest
     double acc = 0.0;
     if (i < d.c) {
         int k = w;
-        for (; k + 3 * KG < kend; k += 4 * KG) {
-            const double v0 = X[i + (size_t)k * d.ldx], v1 = X[i + (size_t)(k + KG) * d.ldx];
-            const double v2 = X[i + (size_t)(k + 2 * KG) * d.ldx], v3 = X[i + (size_t)(k + 3 * KG) * d.ldx];
-            acc += v0 * xs[k] + v1 * xs[k + KG] + v2 * xs[k + 2 * KG] + v3 * xs[k + 3 * KG];
+        for (; k + 7 * KG < kend; k += 8 * KG) {
+            double v[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) v[t] = X[i + (size_t)(k + t * KG) * d.ldx];
+#pragma unroll
+            for (int t = 0; t < 8; t++) acc += v[t] * xs[k + t * KG];
         }
         for (; k < kend; k += KG) acc += X[i + (size_t)k * d.ldx] * xs[k];   // upper part of X is zero
     }
@@ -845,10 +857,12 @@ wide_fwd_upd_kernel(DevSym S, const int* __restrict__ list, const double* __rest
     double acc = 0.0;
     if (i >= d.c && i < d.N) {
         int k = w;
-        for (; k + 3 * KG < d.c; k += 4 * KG) {
-            const double v0 = L[i + (size_t)k * d.ld], v1 = L[i + (size_t)(k + KG) * d.ld];
-            const double v2 = L[i + (size_t)(k + 2 * KG) * d.ld], v3 = L[i + (size_t)(k + 3 * KG) * d.ld];
-            acc += v0 * xn[k] + v1 * xn[k + KG] + v2 * xn[k + 2 * KG] + v3 * xn[k + 3 * KG];
+        for (; k + 7 * KG < d.c; k += 8 * KG) {
+            double v[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) v[t] = L[i + (size_t)(k + t * KG) * d.ld];
+#pragma unroll
+            for (int t = 0; t < 8; t++) acc += v[t] * xn[k + t * KG];
         }
         for (; k < d.c; k += KG) acc += L[i + (size_t)k * d.ld] * xn[k];
     }
@@ -1007,7 +1021,8 @@ void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sch
     const int cnt = L.count[FC_BIG];
     if (!cnt) return;
     const int* list = d_sched + L.begin[FC_BIG];
-    wide_fwd_gather_kernel<<<cnt, WT, 0, st>>>(S, list, x, u);
+    dim3 gg((L.maxN[FC_BIG] + GR - 1) / GR, cnt);
+    wide_fwd_gather_kernel<<<gg, WT, 0, st>>>(S, list, x, u);
     dim3 g1((L.maxC[FC_BIG] + SLAB - 1) / SLAB, cnt);
     wide_fwd_tri_kernel<<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew);
     dim3 g2((L.maxN[FC_BIG] + SLAB - 1) / SLAB, cnt);

@@ -15,10 +15,26 @@ namespace {
 constexpr int ST = 256;        // threads per CTA
 constexpr int SB = 32;         // column block
 
+constexpr int DLD = SB + 1;
+
+// stage the b x b diagonal block at (j0, j0) of a panel in shared memory, plus 1/diag
+__device__ __forceinline__ void stage_diag(const double* __restrict__ panel, int ld, int j0, int b,
+                                           double* Dd, double* rdiag, int mode) {
+    for (int e = threadIdx.x; e < SB * SB; e += ST) {
+        const int i = e & (SB - 1), j = e >> 5;
+        if (i < b && j < b && i >= j) Dd[i + j * DLD] = panel[(j0 + i) + (size_t)(j0 + j) * ld];
+    }
+    __syncthreads();
+    if (threadIdx.x < b) rdiag[threadIdx.x] = (mode == 0) ? 1.0 / Dd[threadIdx.x * (DLD + 1)] : 1.0;
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(ST)
 fwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lval,
            double* __restrict__ x, double* __restrict__ u, int mode) {
     __shared__ double yb[SB];
+    __shared__ double Dd[SB * DLD];
+    __shared__ double rdiag[SB];
     const int s = list[blockIdx.x];
     const int first = S.sfirst[s];
     const int c = S.sfirst[s + 1] - first;
@@ -46,24 +62,30 @@ fwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
     }
     for (int j0 = 0; j0 < c; j0 += SB) {
         const int b = min(SB, c - j0);
+        stage_diag(panel, ld, j0, b, Dd, rdiag, mode);
         if (tid < 32) {
             const int lane = tid;
             double xv = (lane < b) ? xs[j0 + lane] : 0.0;
             for (int q = 0; q < b; q++) {
-                double lpq = (lane >= q && lane < b) ? panel[(j0 + lane) + (size_t)(j0 + q) * ld] : 0.0;
-                double dq = __shfl_sync(0xffffffffu, lpq, q);
-                double xq = __shfl_sync(0xffffffffu, xv, q);
-                double val = (mode == 0) ? xq / dq : xq;
+                const double val = __shfl_sync(0xffffffffu, xv, q) * rdiag[q];
                 if (lane == q) xv = val;
-                else if (lane > q) xv -= lpq * val;
+                else if (lane > q && lane < b) xv -= Dd[lane + q * DLD] * val;
             }
             if (lane < b) { xs[j0 + lane] = xv; yb[lane] = xv; }
         }
         __syncthreads();
         for (int i = j0 + b + tid; i < N; i += ST) {
-            double acc = 0.0;
             const double* pr = panel + i + (size_t)j0 * ld;
-            for (int q = 0; q < b; q++) acc += pr[(size_t)q * ld] * yb[q];
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int q = 0;
+            for (; q + 3 < b; q += 4) {
+                a0 += pr[(size_t)q * ld] * yb[q];
+                a1 += pr[(size_t)(q + 1) * ld] * yb[q + 1];
+                a2 += pr[(size_t)(q + 2) * ld] * yb[q + 2];
+                a3 += pr[(size_t)(q + 3) * ld] * yb[q + 3];
+            }
+            for (; q < b; q++) a0 += pr[(size_t)q * ld] * yb[q];
+            const double acc = (a0 + a1) + (a2 + a3);
             if (i < c) xs[i] -= acc; else us[i - c] -= acc;
         }
         __syncthreads();
@@ -74,6 +96,8 @@ __global__ void __launch_bounds__(ST)
 bwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lval,
            double* __restrict__ x, double* __restrict__ u, int mode) {
     __shared__ double yb[SB];
+    __shared__ double Dd[SB * DLD];
+    __shared__ double rdiag[SB];
     const int s = list[blockIdx.x];
     const int first = S.sfirst[s];
     const int c = S.sfirst[s + 1] - first;
@@ -95,25 +119,26 @@ bwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
         const int b = min(SB, c - j0);
         for (int q = warp; q < b; q += ST / 32) {
             const double* col = panel + (size_t)(j0 + q) * ld;
-            double acc = 0.0;
-            for (int i = j0 + b + lane; i < N; i += 32) {
-                const double f = (i < c) ? xs[i] : us[i - c];
-                acc += col[i] * f;
+            double a0 = 0.0, a1 = 0.0;
+            int i = j0 + b + lane;
+            for (; i + 32 < N; i += 64) {
+                const double f0 = (i < c) ? xs[i] : us[i - c];
+                const double f1 = (i + 32 < c) ? xs[i + 32] : us[i + 32 - c];
+                a0 += col[i] * f0;
+                a1 += col[i + 32] * f1;
             }
+            for (; i < N; i += 32) a0 += col[i] * ((i < c) ? xs[i] : us[i - c]);
+            double acc = a0 + a1;
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) yb[q] = xs[j0 + q] - acc;
         }
-        __syncthreads();
+        stage_diag(panel, ld, j0, b, Dd, rdiag, mode);     // ends with a barrier: yb is complete too
         if (tid < 32) {
             double xv = (lane < b) ? yb[lane] : 0.0;
             for (int q = b - 1; q >= 0; q--) {
-                // L[j0+q, j0+lane], lane <= q
-                double lql = (lane <= q) ? panel[(j0 + q) + (size_t)(j0 + lane) * ld] : 0.0;
-                double dq = __shfl_sync(0xffffffffu, lql, q);
-                double xq = __shfl_sync(0xffffffffu, xv, q);
-                double val = (mode == 0) ? xq / dq : xq;
+                const double val = __shfl_sync(0xffffffffu, xv, q) * rdiag[q];
                 if (lane == q) xv = val;
-                else if (lane < q) xv -= lql * val;
+                else if (lane < q) xv -= Dd[q + lane * DLD] * val;      // L[j0+q, j0+lane]
             }
             if (lane < b) xs[j0 + lane] = xv;
         }

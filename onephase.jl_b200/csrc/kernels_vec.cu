@@ -25,55 +25,80 @@ __global__ void rhs_m_kernel(DirBuffers B) {
     if (k < B.m) B.tm[k] = B.primal_r[k] * B.sigma[k] + B.comp_r[k] / B.s[k];
 }
 
+// Sparse dot products of one row with a dense vector.  W = 1: one thread per row;
+// W = 32: one warp per row (long rows, e.g. the dense Hessian of COPS elec), lanes stride
+// the row and the partial sums are combined with shuffles (every lane gets the result).
+template <int W>
+__device__ __forceinline__ double wsum(double acc) {
+    if (W == 32)
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
+}
+template <int W>
 __device__ __forceinline__ double jt_dot(const DirBuffers& B, int j, const double* v) {
     double acc = 0.0;
-    for (int64_t p = B.Jp[j]; p < B.Jp[j + 1]; p++) acc += B.Jv[p] * v[B.Jrow[p]];
-    return acc;
+    const int l = (W == 32) ? (threadIdx.x & 31) : 0;
+    for (int64_t p = B.Jp[j] + l; p < B.Jp[j + 1]; p += W) acc += B.Jv[p] * v[B.Jrow[p]];
+    return wsum<W>(acc);
 }
+template <int W>
 __device__ __forceinline__ double j_dot(const DirBuffers& B, int k, const double* v) {
     double acc = 0.0;
-    for (int64_t q = B.Rp[k]; q < B.Rp[k + 1]; q++) acc += B.Rval[q] * v[B.Rcol[q]];
-    return acc;
+    const int l = (W == 32) ? (threadIdx.x & 31) : 0;
+    for (int64_t q = B.Rp[k] + l; q < B.Rp[k + 1]; q += W) acc += B.Rval[q] * v[B.Rcol[q]];
+    return wsum<W>(acc);
 }
+template <int W>
 __device__ __forceinline__ double h_dot(const DirBuffers& B, int i, const double* v) {
     double acc = 0.0;
-    for (int64_t q = B.Sp[i]; q < B.Sp[i + 1]; q++) acc += B.Hv[B.Spos[q]] * v[B.Scol[q]];
-    return acc;
+    const int l = (W == 32) ? (threadIdx.x & 31) : 0;
+    for (int64_t q = B.Sp[i] + l; q < B.Sp[i + 1]; q += W) acc += B.Hv[B.Spos[q]] * v[B.Scol[q]];
+    return wsum<W>(acc);
 }
+template <int W>
+__device__ __forceinline__ int row_of() { return (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / W); }
+template <int W>
+__device__ __forceinline__ bool writer() { return W == 1 || (threadIdx.x & 31) == 0; }
 
+template <int W>
 __global__ void rhs_n_kernel(DirBuffers B) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = row_of<W>();
     if (j >= B.n) return;
-    double v = B.dual_r[j] + jt_dot(B, j, B.tm);
-    B.b[j] = v; B.res[j] = v; B.dx[j] = 0.0;
+    double v = B.dual_r[j] + jt_dot<W>(B, j, B.tm);
+    if (writer<W>()) { B.b[j] = v; B.res[j] = v; B.dx[j] = 0.0; }
 }
 
+template <int W>
 __global__ void res_m_kernel(DirBuffers B) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < B.m) B.tm[k] = B.sigma[k] * j_dot(B, k, B.dx);
+    const int k = row_of<W>();
+    if (k >= B.m) return;
+    const double v = B.sigma[k] * j_dot<W>(B, k, B.dx);
+    if (writer<W>()) B.tm[k] = v;
 }
 
+template <int W>
 __global__ void res_n_kernel(DirBuffers B) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = row_of<W>();
     if (j >= B.n) return;
     const double delta = B.st_d->delta;
-    double jac_res = jt_dot(B, j, B.tm);
-    double hess_res = h_dot(B, j, B.dx) + delta * B.dx[j];
-    B.res[j] = B.b[j] - (jac_res + hess_res);
+    double jac_res = jt_dot<W>(B, j, B.tm);
+    double hess_res = h_dot<W>(B, j, B.dx) + delta * B.dx[j];
+    if (writer<W>()) B.res[j] = B.b[j] - (jac_res + hess_res);
 }
 
 __global__ void red_reset_kernel(unsigned long long* red) { if (threadIdx.x < 8) red[threadIdx.x] = 0ull; }
 
+template <int W>
 __global__ void recover_m_kernel(DirBuffers B) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = row_of<W>();
     double eP = 0.0, eM = 0.0, rP = 0.0, rC = 0.0;
     if (k < B.m) {
-        const double jd = j_dot(B, k, B.dx);
+        const double jd = j_dot<W>(B, k, B.dx);
         const double pr = B.primal_r[k], cr = B.comp_r[k], yk = B.y[k], sk = B.s[k];
         const double sym_p = pr + cr / yk;
         const double dy = -(jd - sym_p) * B.sigma[k];
         const double ds = jd - pr;
-        B.dy[k] = dy; B.ds[k] = ds;
+        if (writer<W>()) { B.dy[k] = dy; B.ds[k] = ds; }
         eP = jd - ds - pr;
         eM = sk * dy + yk * ds - cr;
         rP = pr; rC = cr;
@@ -84,15 +109,16 @@ __global__ void recover_m_kernel(DirBuffers B) {
     max_abs_to(B.red + 5, rC);
 }
 
+template <int W>
 __global__ void recover_n_kernel(DirBuffers B) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = row_of<W>();
     double eD = 0.0, rD = 0.0;
     if (j < B.n) {
         const double delta = B.st_d->delta;
         const double dxj = B.dx[j];
         const double delta_err = delta * dxj;
-        const double H_err = h_dot(B, j, B.dx);
-        const double J_err = jt_dot(B, j, B.dy);
+        const double H_err = h_dot<W>(B, j, B.dx);
+        const double J_err = jt_dot<W>(B, j, B.dy);
         rD = B.dual_r[j];
         eD = (delta_err + H_err - J_err) - rD;
     }
@@ -114,20 +140,35 @@ inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
 
+// rows * W threads
+inline unsigned nblkw(int64_t rows, int W) { return (unsigned)((rows * W + 255) / 256); }
+
 void launch_schur_rhs(const DirBuffers& B, cudaStream_t st) {
     if (B.m > 0) { rhs_m_kernel<<<nblk(B.m), 256, 0, st>>>(B); count_launch(); }
-    rhs_n_kernel<<<nblk(B.n), 256, 0, st>>>(B); count_launch();
+    if (B.wide_n) rhs_n_kernel<32><<<nblkw(B.n, 32), 256, 0, st>>>(B);
+    else rhs_n_kernel<1><<<nblkw(B.n, 1), 256, 0, st>>>(B);
+    count_launch();
 }
 
 void launch_residual(const DirBuffers& B, cudaStream_t st) {
-    if (B.m > 0) { res_m_kernel<<<nblk(B.m), 256, 0, st>>>(B); count_launch(); }
-    res_n_kernel<<<nblk(B.n), 256, 0, st>>>(B); count_launch();
+    if (B.m > 0) {
+        if (B.wide_m) res_m_kernel<32><<<nblkw(B.m, 32), 256, 0, st>>>(B);
+        else res_m_kernel<1><<<nblkw(B.m, 1), 256, 0, st>>>(B);
+        count_launch();
+    }
+    if (B.wide_n) res_n_kernel<32><<<nblkw(B.n, 32), 256, 0, st>>>(B);
+    else res_n_kernel<1><<<nblkw(B.n, 1), 256, 0, st>>>(B);
+    count_launch();
 }
 
 void launch_recover_and_error(const DirBuffers& B, cudaStream_t st) {
     red_reset_kernel<<<1, 32, 0, st>>>(B.red);
-    if (B.m > 0) recover_m_kernel<<<nblk(B.m), 256, 0, st>>>(B);
-    recover_n_kernel<<<nblk(B.n), 256, 0, st>>>(B);
+    if (B.m > 0) {
+        if (B.wide_m) recover_m_kernel<32><<<nblkw(B.m, 32), 256, 0, st>>>(B);
+        else recover_m_kernel<1><<<nblkw(B.m, 1), 256, 0, st>>>(B);
+    }
+    if (B.wide_n) recover_n_kernel<32><<<nblkw(B.n, 32), 256, 0, st>>>(B);
+    else recover_n_kernel<1><<<nblkw(B.n, 1), 256, 0, st>>>(B);
     kkt_err_finish_kernel<<<1, 1, 0, st>>>(B);
     count_launch(4);
 }

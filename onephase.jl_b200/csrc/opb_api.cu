@@ -559,6 +559,8 @@ static DirBuffers dir_buffers(opb_handle* h) {
     D.dual_r = h->dual_r.p; D.primal_r = h->primal_r.p; D.comp_r = h->comp_r.p;
     D.b = h->b.p; D.res = h->res.p; D.dx = h->dx.p; D.dy = h->dy.p; D.ds = h->ds.p;
     D.tm = h->tm.p; D.tm2 = nullptr; D.red = h->red.p; D.st_d = h->d_state;
+    D.wide_n = ((double)(B.P.nnzJ + (int64_t)B.P.Scol.size()) >= 24.0 * D.n) ? 1 : 0;
+    D.wide_m = (D.m > 0 && (double)B.P.nnzJ >= 24.0 * D.m) ? 1 : 0;
     return D;
 }
 

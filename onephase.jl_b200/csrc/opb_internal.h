@@ -165,6 +165,7 @@ struct DirBuffers {
     double *b, *res, *dx, *dy, *ds, *tm, *tm2;
     unsigned long long* red;   // 8 slots of max-reduction scratch
     DeltaState* st_d;
+    int wide_n, wide_m;        // long rows: one warp per row in the n- / m-sized product kernels
 };
 void launch_schur_rhs(const DirBuffers& B, cudaStream_t st);
 void launch_residual(const DirBuffers& B, cudaStream_t st);          // res = b - (J'(S.(J dx)) + Hsym dx + delta dx)
