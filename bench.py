@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the kernels-only timings of the other BASELINE shapes")
     ap.add_argument("--phase-repeat", type=int, default=3)
     ap.add_argument("--ncu", action="store_true",
                     help="profiling run: resident steps only (no e2e, phase or CPU legs); never a bench value")
@@ -213,6 +214,16 @@ def main():
     lib0 = pkg.launch_count()
 
     prob = make_problem(pkg, args.workload, seed=rank)          # one independent instance per GPU
+    # the e2e leg copies its inputs from PINNED host memory every step
+    def pinned(a):
+        t = torch.empty(a.shape[0], dtype=torch.float64, pin_memory=True)
+        v = t.numpy(); v[:] = a
+        return v
+    import scipy.sparse as sp
+    prob.J = sp.csc_matrix((pinned(prob.J.data), prob.J.indices, prob.J.indptr), shape=prob.J.shape)
+    prob.H = sp.csc_matrix((pinned(prob.H.data), prob.H.indices, prob.H.indptr), shape=prob.H.shape)
+    prob.y = pinned(prob.y); prob.s = pinned(prob.s)
+    prob.rhs = [tuple(pinned(v) for v in r) for r in prob.rhs]
     pars = pkg.Class_parameters(device=local)
     it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=prob.delta_prev)
     k = pkg.pick_KKT_solver(pars)
@@ -331,12 +342,55 @@ def main():
             roofline = {"bound": "hbm", "kernel": "direction (3 x triangular solves + residuals)",
                         "achieved": dir_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dir_gbs / hbm_peak,
                         "traffic": None, "peak_source": hbm_src}
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")))
+            traffic = tr.get(args.workload, {}).get("factor_bytes_per_attempt" if roofline["bound"] == "tensor"
+                                                    else "direction_bytes")
+        except Exception:
+            pass
+        roofline["traffic"] = traffic
         extra_rooflines = {
             "assembly": {"bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak},
             "factor": {"bound": "tensor", "achieved": fac_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fac_tflops / fp64_peak},
             "solve_pair": {"bound": "hbm", "achieved": solve_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": solve_gbs / hbm_peak},
             "direction": {"bound": "hbm", "achieved": dir_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dir_gbs / hbm_peak},
         }
+
+    # ---------------- the other BASELINE.json shapes, kernels only (rank 0, N = 1) ----------------
+    others = {}
+    if rank == 0 and world == 1 and not args.no_extra:
+        for wname in ("c2_chain_n100k", "c4_elec_n1200", "c5_pde_40"):
+            if wname == args.workload:
+                continue
+            try:
+                p2 = make_problem(pkg, wname, seed=0)
+                it2 = pkg.Class_iterate(p2.J, p2.H, p2.y, p2.s, delta=p2.delta_prev)
+                k2 = pkg.pick_KKT_solver(pars); k2.initialize(it2)
+                k2._h.set_stream(stream.cuda_stream)
+                k2.form_system(it2)
+                h2 = k2._h
+                h2.upload_values(p2.J.data, p2.H.data, p2.y, p2.s); h2.upload_rhs(*p2.rhs[0])
+
+                def step2():
+                    h2.form_resident(); h2.delta_loop_resident(*dl_args)
+                    for _ in range(N_DIRECTIONS):
+                        h2.direction_resident(N_REFINE)
+                for _ in range(3):
+                    step2()
+                torch.cuda.synchronize()
+                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(5):
+                    step2()
+                b.record(); torch.cuda.synchronize()
+                d2, nf2, st2, err2 = h2.sync_state()
+                others[wname] = {"ms_per_iter": a.elapsed_time(b) / 5, "n": p2.n, "m": p2.m, "num_fac": nf2,
+                                 "N_err": float(err2[5]), "factor_flops": h2.info("flops"),
+                                 "nnz_L": int(h2.info("nnzL_true"))}
+                k2.finalize()
+            except Exception as e:      # never lose the headline line to an extra
+                others[wname] = {"error": str(e)[:200]}
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
@@ -397,6 +451,7 @@ def main():
             "roofline": roofline,
             "rooflines_by_phase": extra_rooflines,
             "cpu_baseline": cpu,
+            "other_workloads_kernels_only": others,
             "lib_launches_total": pkg.launch_count() - lib0,
         }
         print(json.dumps(out))

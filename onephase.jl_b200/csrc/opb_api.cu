@@ -164,6 +164,17 @@ struct opb_handle {
     DeltaState h_state{};
     size_t numeric_bytes = 0;
     uint64_t csc_hash = 0;
+    // CUDA graphs of the launch-bound sequences (one factorisation attempt, one direction, one
+    // solve): captured once per structure, replayed afterwards
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; int key = -1; };
+    GraphSlot g_attempt, g_direction, g_solve;
+    bool use_graphs = true;
+    void drop_graphs() {
+        for (GraphSlot* g : {&g_attempt, &g_direction, &g_solve}) {
+            if (g->exec) cudaGraphExecDestroy(g->exec);
+            *g = GraphSlot();
+        }
+    }
 
     int fail(int code, const std::string& msg) { err = msg; return code; }
     int cuda_fail(cudaError_t e, const char* where) {
@@ -178,6 +189,32 @@ struct opb_handle {
         cudaError_t e__ = (call);                             \
         if (e__ != cudaSuccess) return h->cuda_fail(e__, #call); \
     } while (0)
+
+// Replay `enqueue` through a CUDA graph captured on first use (key distinguishes variants).
+template <class F>
+static void run_captured(opb_handle* h, opb_handle::GraphSlot& slot, int key, F&& enqueue) {
+    if (!h->use_graphs) { enqueue(); return; }
+    if (slot.exec && slot.key != key) { cudaGraphExecDestroy(slot.exec); slot = opb_handle::GraphSlot(); }
+    if (!slot.exec) {
+        const long long l0 = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError(); h->use_graphs = false; enqueue(); return;
+        }
+        enqueue();
+        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&slot.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        slot.launches = g_launches.load() - l0;
+        g_launches.store(l0);
+        slot.key = key;
+        if (e != cudaSuccess) {      // capture not possible here: fall back to plain launches
+            cudaGetLastError(); slot = opb_handle::GraphSlot(); h->use_graphs = false; enqueue(); return;
+        }
+    }
+    cudaGraphLaunch(slot.exec, h->stream);
+    count_launch((int)slot.launches);
+}
 
 static const char* kVersion = "onephase_b200 0.1 (sm_100a)";
 
@@ -223,6 +260,7 @@ int opb_destroy(opb_handle* h) {
                                 &h->dx, &h->dy, &h->ds, &h->tm, &h->xw, &h->xw2, &h->uw, &h->userval, &h->Xinv, &h->Twork};
         for (auto* b : bufs) b->release();
         h->red.release();
+        h->drop_graphs();
         if (h->d_state_raw) cudaFree(h->d_state_raw);
         if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     }
@@ -250,6 +288,7 @@ int opb_set_option(opb_handle* h, const char* key, double v) {
     else if (k == "relax") h->opt.relax_enable = (int)v;
     else if (k == "relax_small") h->opt.relax_small = v;
     else if (k == "attempts_per_sync") h->attempts_per_sync = std::max(1, (int)v);
+    else if (k == "graphs") { h->use_graphs = v != 0; h->drop_graphs(); }
     else return h->fail(OPB_ERR_INVALID, "unknown option " + k);
     return OPB_OK;
 }
@@ -301,6 +340,7 @@ static int upload_bundle(opb_handle* h, Bundle& B) {
 }
 
 static int alloc_numeric(opb_handle* h) {
+    h->drop_graphs();       // buffers and schedules may change
     Bundle& B = *h->B;
     const Symbolic& S = B.S;
     const int n = S.n;
@@ -415,7 +455,7 @@ static int stage_form(opb_handle* h) {
     return OPB_OK;
 }
 
-static void enqueue_attempt(opb_handle* h) {
+static void enqueue_attempt_raw(opb_handle* h) {
     Bundle& B = *h->B;
     cudaStream_t st = h->stream;
     launch_ctl_begin(h->d_state, st);
@@ -425,6 +465,10 @@ static void enqueue_attempt(opb_handle* h) {
     if (h->mode == OPB_MODE_CHOLESKY && B.trtri.count)
         launch_trtri(B.dev, B.trtri, B.d_sched.p, h->Lval.p, h->Xinv.p, h->Twork.p, h->d_state, st);
     launch_ctl_end(h->d_state, st);
+}
+
+static void enqueue_attempt(opb_handle* h) {
+    run_captured(h, h->g_attempt, h->mode, [&] { enqueue_attempt_raw(h); });
 }
 
 static int read_state(opb_handle* h) {
@@ -571,16 +615,18 @@ int opb_direction_resident(opb_handle* h, int n_refine) {
     Bundle& B = *h->B;
     cudaStream_t st = h->stream;
     DirBuffers D = dir_buffers(h);
-    launch_schur_rhs(D, st);
-    for (int it = 0; it < n_refine; it++) {
-        launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, D.n, st);
-        launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode, st);
-        launch_permute_out_add(h->xw.p, B.d_perm.p, h->dx.p, D.n, 1, st);
-        // the reference also evaluates the residual after the last correction but only
-        // prints it (schur.jl:177-179); it does not influence the direction
-        if (it + 1 < n_refine) launch_residual(D, st);
-    }
-    launch_recover_and_error(D, st);
+    run_captured(h, h->g_direction, n_refine * 2 + h->mode, [&] {
+        launch_schur_rhs(D, st);
+        for (int it = 0; it < n_refine; it++) {
+            launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, D.n, st);
+            launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode, st);
+            launch_permute_out_add(h->xw.p, B.d_perm.p, h->dx.p, D.n, 1, st);
+            // the reference also evaluates the residual after the last correction but only
+            // prints it (schur.jl:177-179); it does not influence the direction
+            if (it + 1 < n_refine) launch_residual(D, st);
+        }
+        launch_recover_and_error(D, st);
+    });
     CK(cudaGetLastError());
     return OPB_OK;
 }
@@ -603,11 +649,12 @@ int opb_solve_resident(opb_handle* h, int nsolves) {
     int rc = need_device(h); if (rc) return rc;
     if (!h->B || h->ready != opb_handle::FACTORED) return h->fail(OPB_ERR_STATE, "no factor");
     Bundle& B = *h->B;
-    for (int k = 0; k < nsolves; k++) {
-        launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, B.S.n, h->stream);
-        launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode, h->stream);
-        launch_permute_out_add(h->xw.p, B.d_perm.p, h->b.p, B.S.n, 0, h->stream);
-    }
+    for (int k = 0; k < nsolves; k++)
+        run_captured(h, h->g_solve, h->mode, [&] {
+            launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, B.S.n, h->stream);
+            launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode, h->stream);
+            launch_permute_out_add(h->xw.p, B.d_perm.p, h->b.p, B.S.n, 0, h->stream);
+        });
     CK(cudaGetLastError());
     return OPB_OK;
 }

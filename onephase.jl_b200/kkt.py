@@ -199,6 +199,8 @@ class Schur_B200_KKT_solver:
         self._delta = 0.0
         self._diag_min = np.nan
         self._pattern_key = None
+        self._pattern_ident = None
+        self._pattern_refs = None
 
     # -- initialize!(kkt_solver, it)  kkt_system_solver.jl:21-25
     def initialize(self, initial_it):
@@ -213,16 +215,23 @@ class Schur_B200_KKT_solver:
     def set_permutation(self, perm):
         self._h.set_permutation(perm)
         self._pattern_key = None
+        self._pattern_ident = None
 
     # -- form_system!  schur.jl:47-62
     def form_system(self, it, timer=None):
         J = _csc(it.J); H = _csc(it.H)
-        key = (J.shape, J.indptr.tobytes() if J.nnz < 1 << 16 else hash(J.indptr.tobytes()),
-               hash(J.indices.tobytes()), hash(H.indptr.tobytes()), hash(H.indices.tobytes()))
-        if key != self._pattern_key:
-            # pattern changed (Class_cutest.jl:490-502 can drop numerical zeros): new symbolic analysis
-            self._h.set_structure(J.shape[1], J.shape[0], J.indptr, J.indices, H.indptr, H.indices, 0)
-            self._pattern_key = key
+        # pattern identity: same index arrays as last time (the usual case: the iterate's cached
+        # matrices keep their structure) -> no hashing; otherwise compare pattern hashes
+        ident = (id(J.indptr), id(J.indices), id(H.indptr), id(H.indices), J.shape, J.nnz, H.nnz)
+        if ident != self._pattern_ident:
+            key = (J.shape, hash(J.indptr.tobytes()), hash(J.indices.tobytes()),
+                   hash(H.indptr.tobytes()), hash(H.indices.tobytes()))
+            if key != self._pattern_key:
+                # pattern changed (Class_cutest.jl:490-502 can drop numerical zeros): new symbolic analysis
+                self._h.set_structure(J.shape[1], J.shape[0], J.indptr, J.indices, H.indptr, H.indices, 0)
+                self._pattern_key = key
+            self._pattern_ident = ident
+            self._pattern_refs = (J.indptr, J.indices, H.indptr, H.indices)   # keep the ids alive
         self.schur_diag, self._diag_min = self._h.form(J.data, H.data, it.y, it.s)
         self.factor_it = it
         self.Q = None
