@@ -286,6 +286,7 @@ int opb_set_option(opb_handle* h, const char* key, double v) {
     if (k == "nd_leaf") h->opt.nd_leaf = (int)v;
     else if (k == "ordering") h->opt.ordering = (int)v;
     else if (k == "relax") h->opt.relax_enable = (int)v;
+    else if (k == "metis_max_n") h->opt.metis_max_n = (int)v;
     else if (k == "relax_small") h->opt.relax_small = v;
     else if (k == "attempts_per_sync") h->attempts_per_sync = std::max(1, (int)v);
     else if (k == "graphs") { h->use_graphs = v != 0; h->drop_graphs(); }
@@ -367,7 +368,7 @@ static int alloc_numeric(opb_handle* h) {
 
 static std::string cache_key(int device, const SymOptions& o, bool has_perm, uint64_t h1, uint64_t h2) {
     char buf[160];
-    snprintf(buf, sizeof buf, "%d|%d|%d|%d|%d|%016llx|%016llx", device, o.nd_leaf, o.ordering, o.relax_enable,
+    snprintf(buf, sizeof buf, "%d|%d|%d|%d|%d|%d|%016llx|%016llx", device, o.nd_leaf, o.ordering, o.metis_max_n, o.relax_enable,
              has_perm ? 1 : 0, (unsigned long long)h1, (unsigned long long)h2);
     return buf;
 }

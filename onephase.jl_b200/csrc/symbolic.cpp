@@ -15,6 +15,15 @@
 #include <cstring>
 #include <numeric>
 
+// METIS nested dissection from the static library that ships with the CUDA toolkit
+// (/usr/local/cuda/lib64/libmetis_static.a, the one cuSOLVER's csrmetisnd uses; idx_t is 64-bit).
+// Host-side symbolic analysis only.
+extern "C" {
+int METIS_NodeND(int64_t* nvtxs, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, int64_t* options,
+                 int64_t* perm, int64_t* iperm);
+int METIS_SetDefaultOptions(int64_t* options);
+}
+
 namespace opb {
 
 uint64_t pattern_hash(int64_t n, const int64_t* p, const int64_t* i, int64_t nnz) {
@@ -568,6 +577,45 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
     S.n = n;
     // ---- ordering
     std::vector<int> perm0(n);
+    auto metis_order = [&](std::vector<int>& out) -> bool {
+        // METIS_NodeND on the adjacency graph of M
+        Graph G;
+        build_graph(n, Mp, Mi, G);
+        std::vector<int64_t> xadj(G.xadj.begin(), G.xadj.end()), adj(G.adj.begin(), G.adj.end());
+        std::vector<int64_t> mperm(n), miperm(n), options(64);
+        METIS_SetDefaultOptions(options.data());
+        int64_t nv = n;
+        out.resize(n);
+        if (n <= 1) { if (n == 1) out[0] = 0; return true; }
+        if (METIS_NodeND(&nv, xadj.data(), adj.data(), nullptr, options.data(), mperm.data(), miperm.data()) != 1) return false;
+        for (int k = 0; k < n; k++) out[k] = (int)mperm[k];
+        return true;
+    };
+    auto own_order = [&](std::vector<int>& out) {
+        Graph G;
+        build_graph(n, Mp, Mi, G);
+        nd_order(G, opt.nd_leaf, out);
+    };
+    // factorisation flops (sum of squared column counts) of a candidate ordering
+    auto flops_of = [&](const std::vector<int>& pm) {
+        std::vector<int> ip(n), par, post, pm2(n), ip2(n);
+        for (int k = 0; k < n; k++) ip[pm[k]] = k;
+        std::vector<int64_t> Bp_, Up_, cc_;
+        std::vector<int> Bi_, Ui_;
+        permuted_lower(n, Mp, Mi, ip, Bp_, Bi_);
+        transpose_lower(n, Bp_, Bi_, Up_, Ui_);
+        etree(n, Up_, Ui_, par);
+        postorder(n, par, post);
+        for (int k = 0; k < n; k++) pm2[k] = pm[post[k]];
+        for (int k = 0; k < n; k++) ip2[pm2[k]] = k;
+        permuted_lower(n, Mp, Mi, ip2, Bp_, Bi_);
+        transpose_lower(n, Bp_, Bi_, Up_, Ui_);
+        etree(n, Up_, Ui_, par);
+        colcounts(n, Bp_, Bi_, par, cc_);
+        double f = 0;
+        for (int j = 0; j < n; j++) f += (double)cc_[j] * (double)cc_[j];
+        return f;
+    };
     if (user_perm) {
         std::vector<char> seen(n, 0);
         for (int k = 0; k < n; k++) {
@@ -577,10 +625,18 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
         }
     } else if (opt.ordering == 1) {
         std::iota(perm0.begin(), perm0.end(), 0);
+    } else if (opt.ordering == 3) {
+        if (!metis_order(perm0)) { S.error = "METIS_NodeND failed"; return false; }
+    } else if (opt.ordering == 0) {
+        own_order(perm0);
     } else {
-        Graph G;
-        build_graph(n, Mp, Mi, G);
-        nd_order(G, opt.nd_leaf, perm0);
+        // auto (default): the level-structure nested dissection of this file and, for graphs that
+        // METIS orders in seconds, METIS_NodeND; keep the ordering with fewer factorisation flops
+        own_order(perm0);
+        if (n <= opt.metis_max_n) {
+            std::vector<int> pm;
+            if (metis_order(pm) && flops_of(pm) < flops_of(perm0)) perm0.swap(pm);
+        }
     }
     std::vector<int> iperm0(n);
     for (int k = 0; k < n; k++) iperm0[perm0[k]] = k;

@@ -15,7 +15,9 @@ inline int64_t panel_ld(int64_t N) { return (N + 1) & ~(int64_t)1; }
 
 struct SymOptions {
     int nd_leaf = 96;          // nested dissection stops at parts of this size
-    int ordering = 0;          // 0 = nested dissection + min-degree leaves, 1 = natural, 2 = user perm
+    int ordering = 4;          // 4 = auto (best of 0 and 3), 0 = level-structure nested dissection +
+                               // min-degree leaves, 1 = natural, 3 = METIS_NodeND; a user permutation wins
+    int metis_max_n = 400000;  // auto: try METIS only up to this many variables
     double relax_small = 8;    // always merge a last child when merged width <= this
     double relax_z16 = 0.8, relax_z32 = 0.3, relax_z64 = 0.1, relax_zinf = 0.05;
     int relax_enable = 1;
