@@ -14,6 +14,8 @@
 //
 // Replaces CHOLMOD's supernodal numeric factorisation and solve behind
 // cholesky(Symmetric(Q,:L)) and F \ rhs (linear_system_solvers/julia.jl:34,99-113).
+#include <algorithm>
+
 #include "opb_internal.h"
 
 namespace opb {
@@ -803,22 +805,29 @@ wide_fwd_gather_kernel(DevSym S, const int* __restrict__ list, double* __restric
     }
 }
 
-// xnew[i] = sum_{k <= i} X[i,k] * xs[k]   for the pivot rows of the slab
+// The pivot block of a big supernode is inverted in diagonal blocks of XB columns (the recursive
+// merge stops there: inverting a 20000-column separator in one piece would cost 2/3 c^3 flops).
+// The solves walk those blocks: per block one triangular product with its inverse and one
+// rectangular product with the columns of L below / right of it.
+
+// xnew[i] = sum_{k in [b0, i]} X[i,k] * xs[k]   for the pivot rows i of block blk
 __global__ void __launch_bounds__(WT)
 wide_fwd_tri_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Xinv,
-                    const double* __restrict__ x, double* __restrict__ xnew) {
+                    const double* __restrict__ x, double* __restrict__ xnew, int blk) {
     __shared__ double red[KG][SLAB];
     const Front d = get_front(S, list[blockIdx.y]);
-    const int i0 = blockIdx.x * SLAB;
-    if (i0 >= d.c) return;
+    const int b0 = blk * XB;
+    const int b1 = min(d.c, b0 + XB);
+    const int i0 = b0 + blockIdx.x * SLAB;
+    if (i0 >= b1) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = i0 + lane;
     const double* X = Xinv + d.xoff;
     const double* xs = x + d.first;
-    const int kend = min(d.c, i0 + SLAB);
+    const int kend = min(b1, i0 + SLAB);
     double acc = 0.0;
-    if (i < d.c) {
-        int k = w;
+    if (i < b1) {
+        int k = b0 + w;
         for (; k + 7 * KG < kend; k += 8 * KG) {
             double v[8];
 #pragma unroll
@@ -830,7 +839,7 @@ wide_fwd_tri_kernel(DevSym S, const int* __restrict__ list, const double* __rest
     }
     red[w][lane] = acc;
     __syncthreads();
-    if (w == 0 && i < d.c) {
+    if (w == 0 && i < b1) {
         double v = 0.0;
 #pragma unroll
         for (int g = 0; g < KG; g++) v += red[g][lane];
@@ -838,43 +847,48 @@ wide_fwd_tri_kernel(DevSym S, const int* __restrict__ list, const double* __rest
     }
 }
 
-// rows i < c: xs[i] = xnew[i];  rows i >= c: us[i-c] -= sum_k L[i,k] * xnew[k]
+// rows of block blk: xs[i] = xnew[i];  rows below it (later pivot rows and the rows >= c):
+// rhs[i] -= sum_{k in block} L[i,k] * xnew[k]
 __global__ void __launch_bounds__(WT)
 wide_fwd_upd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lval,
-                    double* __restrict__ x, const double* __restrict__ xnew, double* __restrict__ u) {
+                    double* __restrict__ x, const double* __restrict__ xnew, double* __restrict__ u, int blk) {
     __shared__ double red[KG][SLAB];
     const Front d = get_front(S, list[blockIdx.y]);
-    const int i0 = blockIdx.x * SLAB;
+    const int b0 = blk * XB;
+    if (b0 >= d.c) return;
+    const int b1 = min(d.c, b0 + XB);
+    const int i0 = b0 + blockIdx.x * SLAB;
     if (i0 >= d.N) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i = i0 + lane;
     const double* xn = xnew + d.first;
-    if (i0 + SLAB <= d.c) {          // pure pivot rows: publish the forward solution
+    if (i0 + SLAB <= b1) {           // rows inside the block: publish the forward solution
         if (w == 0) x[d.first + i] = xn[i];
         return;
     }
     const double* L = Lval + d.loff;
     double acc = 0.0;
-    if (i >= d.c && i < d.N) {
-        int k = w;
-        for (; k + 7 * KG < d.c; k += 8 * KG) {
+    if (i >= b1 && i < d.N) {
+        int k = b0 + w;
+        for (; k + 7 * KG < b1; k += 8 * KG) {
             double v[8];
 #pragma unroll
             for (int t = 0; t < 8; t++) v[t] = L[i + (size_t)(k + t * KG) * d.ld];
 #pragma unroll
             for (int t = 0; t < 8; t++) acc += v[t] * xn[k + t * KG];
         }
-        for (; k < d.c; k += KG) acc += L[i + (size_t)k * d.ld] * xn[k];
+        for (; k < b1; k += KG) acc += L[i + (size_t)k * d.ld] * xn[k];
     }
     red[w][lane] = acc;
     __syncthreads();
     if (w == 0 && i < d.N) {
-        if (i < d.c) x[d.first + i] = xn[i];
+        if (i < b1) x[d.first + i] = xn[i];
         else {
             double v = 0.0;
 #pragma unroll
             for (int g = 0; g < KG; g++) v += red[g][lane];
-            u[S.rowptr[d.s] + (i - d.c)] -= v;
+            if (i < d.c) x[d.first + i] -= v;
+            else u[S.rowptr[d.s] + (i - d.c)] -= v;
         }
     }
 }
@@ -889,45 +903,60 @@ wide_bwd_gather_kernel(DevSym S, const int* __restrict__ list, const double* __r
     if (t < r) u[rp + t] = x[S.rowidx[rp + t]];
 }
 
-// xnew[k] = xs[k] - sum_t L[c+t, k] * us[t]      (one warp per pivot column)
+// xnew[k] = xs[k] - sum_{i >= b1} L[i,k] * f[i]  for the columns k of block blk, where f is the
+// final solution on the later pivot rows and the ancestors' values on the rows >= c
 __global__ void __launch_bounds__(WT)
 wide_bwd_upd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lval,
-                    const double* __restrict__ x, double* __restrict__ xnew, const double* __restrict__ u) {
+                    const double* __restrict__ x, double* __restrict__ xnew, const double* __restrict__ u, int blk) {
     const Front d = get_front(S, list[blockIdx.y]);
+    const int b0 = blk * XB;
+    const int b1 = min(d.c, b0 + XB);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int k = blockIdx.x * KG + w;
-    if (k >= d.c) return;
-    const double* col = Lval + d.loff + d.c + (size_t)k * d.ld;
+    const int k = b0 + blockIdx.x * KG + w;
+    if (k >= b1) return;
+    const double* col = Lval + d.loff + (size_t)k * d.ld;
+    const double* xs = x + d.first;
     const double* us = u + S.rowptr[d.s];
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    // later pivot rows [b1, c)
+    int i = b1 + lane;
+    for (; i + 96 < d.c; i += 128) {
+        a0 += col[i] * xs[i]; a1 += col[i + 32] * xs[i + 32];
+        a2 += col[i + 64] * xs[i + 64]; a3 += col[i + 96] * xs[i + 96];
+    }
+    for (; i < d.c; i += 32) a0 += col[i] * xs[i];
+    // rows below the pivot block
+    const double* colr = col + d.c;
     int t = lane;
     for (; t + 96 < d.r; t += 128) {
-        a0 += col[t] * us[t]; a1 += col[t + 32] * us[t + 32];
-        a2 += col[t + 64] * us[t + 64]; a3 += col[t + 96] * us[t + 96];
+        a0 += colr[t] * us[t]; a1 += colr[t + 32] * us[t + 32];
+        a2 += colr[t + 64] * us[t + 64]; a3 += colr[t + 96] * us[t + 96];
     }
-    for (; t < d.r; t += 32) a0 += col[t] * us[t];
+    for (; t < d.r; t += 32) a0 += colr[t] * us[t];
     double acc = (a0 + a1) + (a2 + a3);
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) xnew[d.first + k] = x[d.first + k] - acc;
+    if (lane == 0) xnew[d.first + k] = xs[k] - acc;
 }
 
-// xs[k] = sum_{i >= k} X[i,k] * xnew[i]
+// xs[k] = sum_{i in [k, b1)} X[i,k] * xnew[i]  for the columns k of block blk
 __global__ void __launch_bounds__(WT)
 wide_bwd_tri_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Xinv,
-                    double* __restrict__ x, const double* __restrict__ xnew) {
+                    double* __restrict__ x, const double* __restrict__ xnew, int blk) {
     const Front d = get_front(S, list[blockIdx.y]);
+    const int b0 = blk * XB;
+    const int b1 = min(d.c, b0 + XB);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int k = blockIdx.x * KG + w;
-    if (k >= d.c) return;
+    const int k = b0 + blockIdx.x * KG + w;
+    if (k >= b1) return;
     const double* col = Xinv + d.xoff + (size_t)k * d.ldx;
     const double* xn = xnew + d.first;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int i = (k & ~31) + lane;      // aligned start; entries above the diagonal are zero
-    for (; i + 96 < d.c; i += 128) {
+    for (; i + 96 < b1; i += 128) {
         a0 += col[i] * xn[i]; a1 += col[i + 32] * xn[i + 32];
         a2 += col[i + 64] * xn[i + 64]; a3 += col[i + 96] * xn[i + 96];
     }
-    for (; i < d.c; i += 32) a0 += col[i] * xn[i];
+    for (; i < b1; i += 32) a0 += col[i] * xn[i];
     double acc = (a0 + a1) + (a2 + a3);
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) x[d.first + k] = acc;
@@ -1023,11 +1052,16 @@ void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sch
     const int* list = d_sched + L.begin[FC_BIG];
     dim3 gg((L.maxN[FC_BIG] + GR - 1) / GR, cnt);
     wide_fwd_gather_kernel<<<gg, WT, 0, st>>>(S, list, x, u);
-    dim3 g1((L.maxC[FC_BIG] + SLAB - 1) / SLAB, cnt);
-    wide_fwd_tri_kernel<<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew);
-    dim3 g2((L.maxN[FC_BIG] + SLAB - 1) / SLAB, cnt);
-    wide_fwd_upd_kernel<<<g2, WT, 0, st>>>(S, list, Lval, x, xnew, u);
-    count_launch(3);
+    count_launch();
+    const int nblk = (L.maxC[FC_BIG] + XB - 1) / XB;
+    for (int blk = 0; blk < nblk; blk++) {
+        const int cb = std::min(XB, L.maxC[FC_BIG] - blk * XB);
+        dim3 g1((cb + SLAB - 1) / SLAB, cnt);
+        wide_fwd_tri_kernel<<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
+        dim3 g2((L.maxN[FC_BIG] - blk * XB + SLAB - 1) / SLAB, cnt);
+        wide_fwd_upd_kernel<<<g2, WT, 0, st>>>(S, list, Lval, x, xnew, u, blk);
+        count_launch(2);
+    }
 }
 
 void launch_solve_wide_bwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
@@ -1037,10 +1071,15 @@ void launch_solve_wide_bwd(const DevSym& S, const LevelPlan& L, const int* d_sch
     const int* list = d_sched + L.begin[FC_BIG];
     dim3 g0((L.maxN[FC_BIG] + WT) / WT, cnt);
     wide_bwd_gather_kernel<<<g0, WT, 0, st>>>(S, list, x, u);
-    dim3 g1((L.maxC[FC_BIG] + KG - 1) / KG, cnt);
-    wide_bwd_upd_kernel<<<g1, WT, 0, st>>>(S, list, Lval, x, xnew, u);
-    wide_bwd_tri_kernel<<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew);
-    count_launch(3);
+    count_launch();
+    const int nblk = (L.maxC[FC_BIG] + XB - 1) / XB;
+    for (int blk = nblk - 1; blk >= 0; blk--) {
+        const int cb = std::min(XB, L.maxC[FC_BIG] - blk * XB);
+        dim3 g1((cb + KG - 1) / KG, cnt);
+        wide_bwd_upd_kernel<<<g1, WT, 0, st>>>(S, list, Lval, x, xnew, u, blk);
+        wide_bwd_tri_kernel<<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
+        count_launch(2);
+    }
 }
 
 }  // namespace opb

@@ -129,7 +129,7 @@ static void build_plan(Bundle& B) {
     B.sched.insert(B.sched.end(), multi.begin(), multi.end());
     if (!multi.empty()) {
         const int maxc = cols(multi[0]);
-        for (int l = 0; (WB << l) < maxc; l++) {
+        for (int l = 0; (WB << l) < std::min(maxc, XB); l++) {
             const int Sz = WB << l;
             int cnt = 0;
             for (int s : multi) if (cols(s) > Sz) cnt++;

@@ -86,6 +86,7 @@ constexpr int MID_PANEL = 12000;      // doubles
 constexpr int MIDL_PANEL = 26000;     // doubles
 constexpr int NB = 32;                // block-column width of the LDL' big-front path
 constexpr int WB = 128;               // outer block width of the Cholesky big-front path (DMMA)
+constexpr int XB = 2048;              // pivot blocks are inverted in diagonal blocks of this many columns
 
 // Per-level schedule built on the host from Symbolic.
 struct LevelPlan {
