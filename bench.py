@@ -39,7 +39,7 @@ WORKLOADS = {
     "c5_pde_40": ("pde_control", dict(N=40), dict(N=24)),
     "c3_small": ("sparse_qp", dict(n=20_000, m_gen=10_000), dict(n=20_000, m_gen=10_000)),
 }
-DEFAULT_WORKLOAD = "c3_sparse_qp_n200k"
+DEFAULT_WORKLOAD = "c5_pde_100"
 N_DIRECTIONS = 2
 N_REFINE = 3
 
@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the kernels-only timings of the other BASELINE shapes")
     ap.add_argument("--phase-repeat", type=int, default=3)
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="library tuning option passed to opb_set_option (e.g. outer_block=1024)")
     ap.add_argument("--ncu", action="store_true",
                     help="profiling run: resident steps only (no e2e, phase or CPU legs); never a bench value")
     args = ap.parse_args()
@@ -230,6 +232,9 @@ def main():
     k.initialize(it)
     stream = torch.cuda.current_stream()
     k._h.set_stream(stream.cuda_stream)
+    for kv in args.opt:
+        key, val = kv.split("=")
+        k._h.set_option(key, float(val))
     t0 = time.perf_counter()
     k.form_system(it)                                           # symbolic analysis happens here, once
     t_symbolic = time.perf_counter() - t0
@@ -360,7 +365,7 @@ def main():
     # ---------------- the other BASELINE.json shapes, kernels only (rank 0, N = 1) ----------------
     others = {}
     if rank == 0 and world == 1 and not args.no_extra:
-        for wname in ("c2_chain_n100k", "c4_elec_n1200", "c5_pde_40"):
+        for wname in ("c2_chain_n100k", "c3_sparse_qp_n200k", "c4_elec_n1200"):
             if wname == args.workload:
                 continue
             try:

@@ -35,6 +35,9 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     const unsigned addr = smem_u32(bar);
     unsigned ok;
@@ -82,13 +85,18 @@ constexpr int LDM = BM + 4;   // [BK][LDM]: fragment reads are bank-conflict fre
 constexpr int LDK = BK + 4;   // [BN][LDK]
 constexpr int A_STAGE = BK * LDM;                                  // 2112 doubles
 constexpr int B_STAGE = (BN * LDK > BK * LDM) ? BN * LDK : BK * LDM;  // 2560 doubles
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_CWARPS = 8;                      // compute warps (2 x 4)
+constexpr int GEMM_THREADS = (GEMM_CWARPS + 1) * 32;   // + one producer warp that only issues the TMA copies
 
 struct GemmSmem {
     double A[STAGES][A_STAGE];
     double B[STAGES][B_STAGE];
-    unsigned long long full[STAGES];
+    unsigned long long full[STAGES];    // producer -> compute warps: the stage has landed (tx bytes)
+    unsigned long long empty[STAGES];   // compute warps -> producer: the stage has been read
 };
+
+// true for the threads that hold accumulators after gemm_mainloop
+__device__ __forceinline__ bool gemm_compute_warp() { return threadIdx.x < GEMM_CWARPS * 32; }
 
 template <bool B_KC>
 __device__ __forceinline__ void gemm_issue(GemmSmem& sm, int stage, int kb, const double* Ag, int lda, int mrows,
@@ -114,57 +122,76 @@ __device__ __forceinline__ void gemm_issue(GemmSmem& sm, int stage, int kb, cons
     }
 }
 
+// one k-step (4 columns) of the warp tile: 12 fragment loads, 32 DMMAs
+template <bool B_KC, bool TAIL>
+__device__ __forceinline__ void gemm_kstep(const double* As, const double* Bs, int kk, bool kvalid,
+                                           double (&acc)[8][4][2]) {
+    double av[8], bv[4];
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++) {
+        const double v = As[kk * LDM + mt * 8];
+        av[mt] = (!TAIL || kvalid) ? v : 0.0;
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) {
+        const double v = B_KC ? Bs[(nt * 8) * LDK + kk] : Bs[kk * LDM + nt * 8];
+        bv[nt] = (!TAIL || kvalid) ? v : 0.0;
+    }
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], bv[nt]);
+}
+
+// Warp-specialised main loop: warp GEMM_CWARPS streams the operands (TMA bulk copies, `full`
+// barriers), warps 0..7 run the DMMAs and hand the stage back through the `empty` barriers; no
+// block-wide barrier inside the K loop.  On return every stage has been consumed (block barrier),
+// so the caller may reuse the shared memory; acc is valid on the compute warps only.
 template <bool B_KC>
 __device__ __forceinline__ void gemm_mainloop(GemmSmem& sm, const double* Ag, int lda, int mrows,
                                               const double* Bg, int ldb, int nrows, int K,
                                               double (&acc)[8][4][2]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;     // 2 x 4 warps
-    const int q = lane & 3, g = lane >> 2;
 #pragma unroll
     for (int a = 0; a < 8; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; s++) mbar_init(&sm.full[s], 1);
+        for (int s = 0; s < STAGES; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], GEMM_CWARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int nkb = (K + BK - 1) / BK;
-    if (warp == 0)
-        for (int s = 0; s < STAGES - 1 && s < nkb; s++)
-            gemm_issue<B_KC>(sm, s, s, Ag, lda, mrows, Bg, ldb, nrows, K, lane);
-    for (int kb = 0; kb < nkb; kb++) {
-        const int stage = kb % STAGES;
-        if (warp == 0 && kb + STAGES - 1 < nkb)
-            gemm_issue<B_KC>(sm, (kb + STAGES - 1) % STAGES, kb + STAGES - 1, Ag, lda, mrows, Bg, ldb, nrows, K, lane);
-        mbar_wait(&sm.full[stage], (unsigned)((kb / STAGES) & 1));
-        const double* As = sm.A[stage];
-        const double* Bs = sm.B[stage];
-        const int nk = min(BK, K - kb * BK);
-        const int nsteps = (nk + 3) >> 2;
-        for (int ks = 0; ks < nsteps; ks++) {
-            const int kk = ks * 4 + q;
-            const bool kvalid = kk < nk;
-            double av[8], bv[4];
-#pragma unroll
-            for (int mt = 0; mt < 8; mt++) {
-                double v = As[kk * LDM + wm * 64 + mt * 8 + g];
-                av[mt] = kvalid ? v : 0.0;
-            }
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-                double v = B_KC ? Bs[(wn * 32 + nt * 8 + g) * LDK + kk] : Bs[kk * LDM + wn * 32 + nt * 8 + g];
-                bv[nt] = kvalid ? v : 0.0;
-            }
-#pragma unroll
-            for (int mt = 0; mt < 8; mt++)
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], bv[nt]);
+    if (warp == GEMM_CWARPS) {
+        for (int kb = 0; kb < nkb; kb++) {
+            const int stage = kb % STAGES;
+            if (kb >= STAGES) mbar_wait(&sm.empty[stage], (unsigned)(((kb / STAGES) - 1) & 1));
+            gemm_issue<B_KC>(sm, stage, kb, Ag, lda, mrows, Bg, ldb, nrows, K, lane);
         }
-        __syncthreads();
+    } else {
+        const int wm = warp >> 2, wn = warp & 3;     // 2 x 4 warps, warp tile 64 x 32
+        const int q = lane & 3, g = lane >> 2;
+        const int aoff = wm * 64 + g;
+        const int boff = B_KC ? (wn * 32 + g) * LDK : wn * 32 + g;
+        for (int kb = 0; kb < nkb; kb++) {
+            const int stage = kb % STAGES;
+            mbar_wait(&sm.full[stage], (unsigned)((kb / STAGES) & 1));
+            const double* As = sm.A[stage] + aoff;
+            const double* Bs = sm.B[stage] + boff;
+            const int nk = K - kb * BK;
+            if (nk >= BK) {
+#pragma unroll
+                for (int ks = 0; ks < BK / 4; ks++) gemm_kstep<B_KC, false>(As, Bs, ks * 4 + q, true, acc);
+            } else {
+#pragma unroll 1
+                for (int ks = 0; ks * 4 < nk; ks++) gemm_kstep<B_KC, true>(As, Bs, ks * 4 + q, ks * 4 + q < nk, acc);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        }
     }
+    __syncthreads();
 }
 
 // coordinates of accumulator element (mt, nt, e) inside the 128 x 128 tile
@@ -572,6 +599,7 @@ chol_trsm_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
     const double* Bg = Xinv + d.xoff + j0 + (size_t)j0 * d.ldx;
     double acc[8][4][2];
     gemm_mainloop<false>(sm, Ag, d.ld, mrows, Bg, d.ldx, b, b, acc);
+    if (!gemm_compute_warp()) return;
 #pragma unroll
     for (int mt = 0; mt < 8; mt++) {
         const int i = row0 + acc_row(mt);
@@ -586,40 +614,44 @@ chol_trsm_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
     }
 }
 
-// right-looking update of the remaining PANEL columns [j1, c):  L[i,k] -= sum L[i,blk] L[k,blk]
-// (the update block of the front is formed once, at the end, by front_cb_kernel)
+// right-looking update of PANEL columns [cbeg, min(cend, c)) with the finished columns
+// [k0, k0+klen):  L[i,k] -= sum_p L[i,p] L[k,p]   (i >= k).
+// Two-level blocking: after every WB-wide block only the columns up to the end of the enclosing
+// outer block are updated (klen = WB); the columns beyond it get ONE rank-`outer` update when the
+// outer block is complete (klen = outer), so the bulk of the panel flops runs with a long K loop
+// and the panel is read-modify-written c/outer instead of c/WB times.
+// cbeg and k0 are multiples of WB.  (The update block of the front is formed once, at the end,
+// by front_cb_kernel.)
 __global__ void __launch_bounds__(GEMM_THREADS)
 chol_panel_update_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval,
-                         int t, DeltaState* st) {
+                         int k0, int klen, int cbeg, int cend, DeltaState* st) {
     extern __shared__ __align__(16) unsigned char smraw[];
     GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smraw);
     if (stop_requested(st)) return;
     const Front d = get_front(S, list[blockIdx.y]);
-    const int j0 = t * WB;
-    if (j0 >= d.c) return;
-    const int b = min(WB, d.c - j0);
-    const int j1 = j0 + b;
-    if (j1 >= d.c) return;                 // no panel columns left
-    const int j1e = j1 & ~1;
-    const int nrow = (d.N - j1e + BM - 1) / BM;
-    const int ncol = (d.c - j1e + BN - 1) / BN;
+    if (cbeg >= d.c) return;               // no panel columns left
+    const int ce = min(cend, d.c);
+    const int kl = min(klen, d.c - k0);
+    const int nrow = (d.N - cbeg + BM - 1) / BM;
+    const int ncol = (ce - cbeg + BN - 1) / BN;
     int tp = blockIdx.x, I = -1, J = 0;
     for (; J < ncol; J++) {
         if (tp < nrow - J) { I = J + tp; break; }
         tp -= nrow - J;
     }
     if (I < 0) return;
-    const int ri = j1e + I * BM, rj = j1e + J * BN;
-    const double* Ag = Lval + d.loff + ri + (size_t)j0 * d.ld;
-    const double* Bg = Lval + d.loff + rj + (size_t)j0 * d.ld;
+    const int ri = cbeg + I * BM, rj = cbeg + J * BN;
+    const double* Ag = Lval + d.loff + ri + (size_t)k0 * d.ld;
+    const double* Bg = Lval + d.loff + rj + (size_t)k0 * d.ld;
     double acc[8][4][2];
-    gemm_mainloop<false>(sm, Ag, d.ld, min(BM, d.N - ri), Bg, d.ld, min(BN, d.N - rj), b, acc);
+    gemm_mainloop<false>(sm, Ag, d.ld, min(BM, d.N - ri), Bg, d.ld, min(BN, d.N - rj), kl, acc);
+    if (!gemm_compute_warp()) return;
 #pragma unroll
     for (int nt = 0; nt < 4; nt++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             const int k = rj + acc_col(nt, e);
-            if (k < j1 || k >= d.c) continue;
+            if (k >= ce) continue;
             double* colp = Lval + d.loff + (size_t)k * d.ld;
 #pragma unroll
             for (int mt = 0; mt < 8; mt++) {
@@ -656,12 +688,14 @@ front_cb_kernel(DevSym S, const int* __restrict__ list, const double* __restrict
     gemm_mainloop<false>(sm, Ag, d.ld, min(BM, d.N - ri), Bg, d.ld, min(BN, d.N - rj), d.c, acc);
     // the stage buffers are free now: reuse them as the 128 x 128 tile (ld 129)
     double* T = reinterpret_cast<double*>(smraw);
+    if (gemm_compute_warp()) {
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++)
+        for (int mt = 0; mt < 8; mt++)
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++)
+            for (int nt = 0; nt < 4; nt++)
 #pragma unroll
-            for (int e = 0; e < 2; e++) T[acc_row(mt) + acc_col(nt, e) * TLD] = -acc[mt][nt][e];
+                for (int e = 0; e < 2; e++) T[acc_row(mt) + acc_col(nt, e) * TLD] = -acc[mt][nt][e];
+    }
     __syncthreads();
     const int tid = threadIdx.x;
     for (int k = S.child_ptr[d.s]; k < S.child_ptr[d.s + 1]; k++) {
@@ -742,6 +776,7 @@ trtri_merge_kernel(DevSym S, const int* __restrict__ list, const double* __restr
         gemm_mainloop<true>(sm, Ag, d.ldx, mrows, Bg, d.ldx, BN, kend - a1, acc);
         out = Xinv + d.xoff;
     }
+    if (!gemm_compute_warp()) return;
     const double sgn = phase == 0 ? 1.0 : -1.0;
 #pragma unroll
     for (int mt = 0; mt < 8; mt++) {
@@ -983,7 +1018,7 @@ cudaError_t dense_configure() {
 }
 
 void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
-                            double* CB, double* Xinv, DeltaState* st_d, cudaStream_t st) {
+                            double* CB, double* Xinv, DeltaState* st_d, int outer_block, cudaStream_t st) {
     if (!L.wide_count) return;
     // medium fronts: panel in shared memory
     for (int fc = FC_MID; fc <= FC_MIDL; fc++) {
@@ -997,28 +1032,37 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
         dim3 gea((L.maxN[FC_BIG] + EAP_RB - 1) / EAP_RB, L.count[FC_BIG]);
         big_extend_add_panel_kernel<<<gea, 256, 0, st>>>(S, list, Lval, CB, st_d);
         count_launch();
-        for (size_t t = 0; t < L.step_count.size(); t++) {
+        const int sub = std::max(1, outer_block / WB);          // WB blocks per outer block
+        const int nsteps = (int)L.step_count.size();
+        auto update = [&](int k0, int klen, int cbeg, int cend) {
+            // fronts with panel columns beyond cbeg: a prefix of the list (sorted by c descending)
+            const int tb = cbeg / WB;
+            if (tb >= nsteps || L.step_count[tb] <= 0) return;
+            const int cnt2 = L.step_count[tb];
+            const int nrow = (L.step_maxN[tb] - cbeg + BM - 1) / BM;
+            const int ncol = (std::min(cend, L.maxC[FC_BIG]) - cbeg + BN - 1) / BN;
+            long long tiles = 0;
+            for (int J = 0; J < ncol && J < nrow; J++) tiles += nrow - J;
+            if (tiles <= 0) return;
+            dim3 gu((unsigned)tiles, cnt2);
+            chol_panel_update_kernel<<<gu, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, list, Lval, k0, klen, cbeg, cend, st_d);
+            count_launch();
+        };
+        for (int t = 0; t < nsteps; t++) {
             const int cnt = L.step_count[t];
             if (cnt <= 0) break;
             const int maxN = L.step_maxN[t];
-            chol_diag_kernel<<<cnt, PT, diag_smem(), st>>>(S, list, Lval, Xinv, (int)t, st_d);
+            chol_diag_kernel<<<cnt, PT, diag_smem(), st>>>(S, list, Lval, Xinv, t, st_d);
             count_launch();
-            const int rem = maxN - (int)t * WB;     // rows from the start of the block (upper bound)
+            const int rem = maxN - t * WB;     // rows from the start of the block (upper bound)
             if (rem <= 0) continue;
             const int nrow = (rem + BM - 1) / BM + 1;
             dim3 gt(nrow, cnt);
-            chol_trsm_kernel<<<gt, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, list, Lval, Xinv, (int)t, st_d);
+            chol_trsm_kernel<<<gt, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, list, Lval, Xinv, t, st_d);
             count_launch();
-            if (t + 1 < L.step_count.size() && L.step_count[t + 1] > 0) {
-                // only fronts with pivot columns beyond this block have panel columns to update
-                const int cnt2 = L.step_count[t + 1];
-                const int ncol = (L.maxC[FC_BIG] - (int)(t + 1) * WB + BN - 1) / BN + 1;
-                long long tiles = 0;
-                for (int J = 0; J < ncol && J < nrow; J++) tiles += nrow - J;
-                dim3 gu((unsigned)tiles, cnt2);
-                chol_panel_update_kernel<<<gu, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, list, Lval, (int)t, st_d);
-                count_launch();
-            }
+            const int ob_end = (t / sub + 1) * sub * WB;        // first column after the enclosing outer block
+            if ((t + 1) * WB < ob_end) update(t * WB, WB, (t + 1) * WB, ob_end);
+            else update((t / sub) * sub * WB, sub * WB, ob_end, 1 << 30);
         }
     }
     // update blocks of all medium and big fronts, written once

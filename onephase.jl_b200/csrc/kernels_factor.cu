@@ -360,7 +360,8 @@ cudaError_t factor_configure() {
 }
 
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
-                          double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode, cudaStream_t st) {
+                          double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
+                          int outer_block, cudaStream_t st) {
     for (const LevelPlan& L : plan) {
         if (L.count[FC_T32]) {
             front_small_kernel<64><<<L.count[FC_T32], 64, small_smem(L.maxN[FC_T32]), st>>>(
@@ -376,7 +377,7 @@ void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, c
         if (!L.wide_count) continue;
         if (mode == 0) {
             // Cholesky: panels in shared memory / blocked on the FP64 tensor pipe (kernels_dense.cu)
-            launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, st);
+            launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, outer_block, st);
             continue;
         }
         // LDL' fallback: scalar blocked path over every front that does not fit in shared memory

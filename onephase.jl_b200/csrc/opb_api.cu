@@ -151,6 +151,7 @@ struct opb_handle {
     SymOptions opt;
     std::vector<int64_t> user_perm;
     int attempts_per_sync = 2;
+    int outer_block = OUTER_BLOCK;
     std::shared_ptr<Bundle> B;
     bool cached_hit = false;
     // numeric state
@@ -289,6 +290,7 @@ int opb_set_option(opb_handle* h, const char* key, double v) {
     else if (k == "metis_max_n") h->opt.metis_max_n = (int)v;
     else if (k == "relax_small") h->opt.relax_small = v;
     else if (k == "attempts_per_sync") h->attempts_per_sync = std::max(1, (int)v);
+    else if (k == "outer_block") { h->outer_block = std::max(WB, ((int)v / WB) * WB); h->drop_graphs(); }
     else if (k == "graphs") { h->use_graphs = v != 0; h->drop_graphs(); }
     else return h->fail(OPB_ERR_INVALID, "unknown option " + k);
     return OPB_OK;
@@ -462,7 +464,8 @@ static void enqueue_attempt_raw(opb_handle* h) {
     launch_ctl_begin(h->d_state, st);
     launch_scatter_fronts(h->Mval.p, B.d_amap.p, B.d_dpos.p, h->sdiag.p, h->Lval.p, B.S.nnzL,
                           B.Mp[B.S.n], B.S.n, h->d_state, 1, st);
-    launch_factor_levels(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->Xinv.p, h->d_state, h->mode, st);
+    launch_factor_levels(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->Xinv.p, h->d_state, h->mode,
+                         h->outer_block, st);
     if (h->mode == OPB_MODE_CHOLESKY && B.trtri.count)
         launch_trtri(B.dev, B.trtri, B.d_sched.p, h->Lval.p, h->Xinv.p, h->Twork.p, h->d_state, st);
     launch_ctl_end(h->d_state, st);

@@ -85,7 +85,8 @@ constexpr int SMALL_N = 152;          // 152*152*8 = 184,832 B of shared memory
 constexpr int MID_PANEL = 12000;      // doubles
 constexpr int MIDL_PANEL = 26000;     // doubles
 constexpr int NB = 32;                // block-column width of the LDL' big-front path
-constexpr int WB = 128;               // outer block width of the Cholesky big-front path (DMMA)
+constexpr int WB = 128;               // block width of the Cholesky big-front path (DMMA)
+constexpr int OUTER_BLOCK = 1024;     // default outer block of the two-level panel update (multiple of WB)
 constexpr int XB = 2048;              // pivot blocks are inverted in diagonal blocks of this many columns
 
 // Per-level schedule built on the host from Symbolic.
@@ -122,7 +123,8 @@ void launch_ctl_single(DeltaState* st_d, double delta, int mode, cudaStream_t st
 // ---- kernels_factor.cu
 cudaError_t factor_configure();
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
-                          double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode, cudaStream_t st);
+                          double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
+                          int outer_block, cudaStream_t st);
 
 // ---- kernels_dense.cu  (Cholesky of big fronts on the FP64 tensor pipe, pivot-block inverses,
 //                         multi-CTA triangular solves for big supernodes)
@@ -135,7 +137,7 @@ struct TrtriPlan {
 cudaError_t dense_configure();
 // medium + big fronts of one level (Cholesky)
 void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
-                            double* CB, double* Xinv, DeltaState* st_d, cudaStream_t st);
+                            double* CB, double* Xinv, DeltaState* st_d, int outer_block, cudaStream_t st);
 void launch_trtri(const DevSym& S, const TrtriPlan& T, const int* d_sched, const double* Lval,
                   double* Xinv, double* Twork, const DeltaState* st_d, cudaStream_t st);
 void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
