@@ -14,7 +14,10 @@ One "step" = one outer IPM iteration's linear algebra on one synthetic instance
           box's host cores, on a bounded sample of the same workload.
 
 Multi-GPU (torchrun): the path shards by instance -- one independent solve per GPU,
-no data-path collective ("replicas", scaling = weak).  value = wall ms / (N * K).
+no data-path collective ("replicas", scaling = weak).  value = wall ms / (N * K).  The same
+line carries `sharded_single_instance`: ONE instance whose elimination-tree subtrees are mapped
+to the N GPUs (top separators pull their children's update blocks over NVLink).
+`--shard` makes that the headline instead (scaling = strong, value = ms per iteration).
 """
 import argparse
 import json
@@ -149,6 +152,83 @@ def cpu_iteration(orc, pkg, prob, perm, reuse_symbolic=False, F=None):
                 total_ms=(t3 - t0) * 1e3, num_fac=nf), F
 
 
+def measure_sharded(pkg, torch, dist, args, local, world, workload):
+    """ONE instance of `workload` over all `world` GPUs: subtrees of the elimination
+    tree mapped to ranks, top separators pulling their children's update blocks over NVLink.
+    Every rank makes the same calls with the same data; time = max over ranks (CUDA events)."""
+    prob = make_problem(pkg, workload, seed=0)
+    pars = pkg.Class_parameters(device=local)
+    it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=prob.delta_prev)
+    k = pkg.pick_KKT_solver(pars, shard=pkg.DistShard())
+    k.initialize(it)
+    stream = torch.cuda.current_stream()
+    k._h.set_stream(stream.cuda_stream)
+    for kv in args.opt:
+        key, val = kv.split("=")
+        k._h.set_option(key, float(val))
+    k.form_system(it)
+    h = k._h
+    d = pars.delta
+    dl_args = (prob.delta_prev, d.zero, d.min, d.max, d.start, d.inc, d.dec, 500)
+    rhs = [pkg.System_rhs(*r) for r in prob.rhs[:N_DIRECTIONS]]
+
+    def e2e_step():
+        k.form_system(it)
+        pkg.ipopt_strategy(it, k, pars)
+        for r in rhs:
+            k.kkt_associate_rhs(it, r)
+            k.compute_direction()
+
+    def resident_step():
+        h.form_resident()
+        h.delta_loop_resident(*dl_args)
+        for _ in range(N_DIRECTIONS):
+            h.direction_resident(N_REFINE)
+
+    def timed(fn, reps, warm):
+        for _ in range(warm):
+            fn()
+        dist.barrier(); torch.cuda.synchronize()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        dist.barrier(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    steps = max(2, min(args.steps, 5))
+    e2e_step()
+    t0 = time.perf_counter()
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    dist.barrier(); torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    h.upload_values(prob.J.data, prob.H.data, prob.y, prob.s)
+    h.upload_rhs(*prob.rhs[0])
+    ms = timed(resident_step, steps, 2)
+    fac = timed(lambda: h.delta_loop_resident(*dl_args), 2, 0)
+    sol = timed(lambda: h.solve_resident(1), 3, 1)
+    delta_res, nf_res, st_res, kkt_err = h.sync_state()
+    t = torch.tensor([ms, e2e_ms, fac, sol], device=torch.device("cuda", local), dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    loads = torch.zeros(world, device=torch.device("cuda", local), dtype=torch.float64)
+    loads[dist.get_rank()] = h.info("shard_load")
+    dist.all_reduce(loads)
+    out = {"workload": workload, "n_gpus": world, "ms_per_iter": float(t[0]), "e2e_ms_per_iter": float(t[1]),
+           "factor_ms": float(t[2]) / max(nf_res, 1), "solve_pair_ms": float(t[3]), "num_fac": nf_res,
+           "N_err": float(kkt_err[5]), "scaling": "strong",
+           "rank_flops": [float(v) for v in loads], "top_flops": h.info("shard_top_flops"),
+           "barrier_levels": int(h.info("shard_barriers")),
+           "how": "subtree-to-GPU mapping by factorisation flops; update blocks, forward update vectors and the "
+                  "solution cross GPUs through peer-mapped HBM (CUDA IPC over NVLink) inside the consuming kernels; "
+                  "flag barriers on the stream; no collective in the data path"}
+    k.finalize()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -191,6 +271,8 @@ def main():
     ap.add_argument("--phase-repeat", type=int, default=3)
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="library tuning option passed to opb_set_option (e.g. outer_block=1024)")
+    ap.add_argument("--shard", action="store_true",
+                    help="N > 1: one instance sharded over the N GPUs (strong scaling) instead of N replicas")
     ap.add_argument("--ncu", action="store_true",
                     help="profiling run: resident steps only (no e2e, phase or CPU legs); never a bench value")
     args = ap.parse_args()
@@ -215,7 +297,9 @@ def main():
     pkg = graft.package()
     lib0 = pkg.launch_count()
 
-    prob = make_problem(pkg, args.workload, seed=rank)          # one independent instance per GPU
+    sharded = bool(args.shard and world > 1)
+    # replicas: one independent instance per GPU;  --shard: the SAME instance on every rank
+    prob = make_problem(pkg, args.workload, seed=0 if sharded else rank)
     # the e2e leg copies its inputs from PINNED host memory every step
     def pinned(a):
         t = torch.empty(a.shape[0], dtype=torch.float64, pin_memory=True)
@@ -228,7 +312,7 @@ def main():
     prob.rhs = [tuple(pinned(v) for v in r) for r in prob.rhs]
     pars = pkg.Class_parameters(device=local)
     it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=prob.delta_prev)
-    k = pkg.pick_KKT_solver(pars)
+    k = pkg.pick_KKT_solver(pars, shard=pkg.DistShard() if sharded else None)
     k.initialize(it)
     stream = torch.cuda.current_stream()
     k._h.set_stream(stream.cuda_stream)
@@ -310,7 +394,7 @@ def main():
                               "launches": int(launches), "num_fac": nf_res}))
         k.finalize()
         return
-    if rank == 0:
+    if rank == 0 or sharded:        # a sharded instance needs every rank in every call
         def timed(fn, reps):
             fn(); torch.cuda.synchronize()
             a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
@@ -331,7 +415,7 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        fp64_peak = measure_fp64_peak(torch, dev)
+        fp64_peak = measure_fp64_peak(torch, dev) * (world if sharded else 1)
         fac_tflops = cnt["F_chol"] / (phases["factor_ms"] * 1e-3) / 1e12
         asm_gbs = cnt["B_asm"] / (phases["form_ms"] * 1e-3) / 1e9
         solve_gbs = cnt["B_solve"] / (phases["solve_pair_ms"] * 1e-3) / 1e9
@@ -433,9 +517,9 @@ def main():
     if rank == 0:
         gen, kw, kws = WORKLOADS[args.workload]
         out = {
-            "metric": "kkt_factor_solve_ms_per_iter", "value": ms_step / world, "unit": "ms/iter",
+            "metric": "kkt_factor_solve_ms_per_iter", "value": ms_step if sharded else ms_step / world, "unit": "ms/iter",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": False, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": args.workload, "generator": gen, "generator_args": kw,
                        "n": n, "m": m, "nnz_J": int(prob.J.nnz), "nnz_M_lower": int(h.info("nnzM")),
@@ -444,11 +528,14 @@ def main():
                        "max_front": int(h.info("max_front")),
                        "directions_per_iter": N_DIRECTIONS, "refine": N_REFINE, "num_fac": nf_res,
                        "delta": delta_res, "N_err": float(kkt_err[5]),
-                       "instances": world, "parallelism": "one independent instance per GPU (replicas)",
+                       "instances": 1 if sharded else world,
+                       "parallelism": ("one instance, elimination-tree subtrees mapped to %d GPUs, top separators over "
+                                       "NVLink peer memory" % world) if sharded else
+                                      "one independent instance per GPU (replicas)",
                        "l2_policy": "working set larger than L2: factor L alone is %.0f MB and is streamed by every "
                                     "factorisation and solve" % (8 * h.info("nnzL") / 1e6),
                        "symbolic_s_once": t_symbolic},
-            "e2e": {"value": e2e_ms / world, "unit": "ms/iter", "h2d_bytes_per_step": int(h2d),
+            "e2e": {"value": e2e_ms if sharded else e2e_ms / world, "unit": "ms/iter", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -459,8 +546,19 @@ def main():
             "other_workloads_kernels_only": others,
             "lib_launches_total": pkg.launch_count() - lib0,
         }
-        print(json.dumps(out))
     k.finalize()
+    del k, h
+    torch.cuda.empty_cache()
+    if world > 1 and not sharded and not args.no_extra:
+        # the same line also carries ONE instance sharded over the N GPUs
+        try:
+            sh = measure_sharded(pkg, torch, dist, args, local, world, args.workload)
+        except Exception as e:      # never lose the headline line to an extra
+            sh = {"error": str(e)[:300]}
+        if rank == 0:
+            out["sharded_single_instance"] = sh
+    if rank == 0:
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 

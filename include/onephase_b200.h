@@ -125,6 +125,25 @@ int opb_solve_resident(opb_handle* h, int nsolves);   /* triangular solves only,
 /* blocks until the stream is idle and reads the controller state */
 int opb_sync_state(opb_handle* h, double* delta_out, int* num_fac_out, int* status_out, double* kkt_err_out);
 
+/* --- one instance sharded over the GPUs of a box (no counterpart in the
+ * reference, which is single-threaded CPU code: julia.jl:21-113 factorises and solves on one
+ * core).  One process (or at least one handle) per GPU, all of them making the SAME sequence
+ * of calls with the SAME data (SPMD).  Independent subtrees of the elimination tree are mapped
+ * to ranks by factorisation flops; the top separators are owned by one rank each and pull
+ * their children's update blocks from the owners' HBM over NVLink (peer-mapped memory, no
+ * collective library); every rank ends up with the full direction.  Cholesky mode only.
+ *   opb_shard_init    before opb_set_structure: this handle is rank `rank` of `world` (<= 8)
+ *   opb_shard_export  after every opb_set_structure: OPB_SHARD_BLOB_BYTES bytes describing this
+ *                     rank's peer-visible buffers (CUDA IPC handles); exchange them between the
+ *                     ranks by any means (the Python host uses torch.distributed.all_gather)
+ *   opb_shard_attach  map the buffers of rank `peer` from its blob
+ * Extra info keys: shard_rank, shard_world, shard_load (flops owned by this rank),
+ * shard_top_flops, shard_barriers; symbolic arrays: owner, top. */
+#define OPB_SHARD_BLOB_BYTES 320
+int opb_shard_init(opb_handle* h, int rank, int world);
+int opb_shard_export(opb_handle* h, unsigned char* blob);
+int opb_shard_attach(opb_handle* h, int peer, const unsigned char* blob);
+
 /* --- introspection --- */
 /* keys: n, m, nnzJ, nnzH, nnzM, npairs, nnzL, nnzL_true, flops, nsuper, nlevels,
  *       max_front, cb_total, n_tiny, n_small, n_big, device_bytes, symbolic_cached */

@@ -30,7 +30,9 @@ EXPORTS = [
     "opb_upload_values", "opb_upload_rhs", "opb_form_resident", "opb_delta_loop_resident",
     "opb_direction_resident", "opb_solve_resident", "opb_sync_state", "opb_get_info",
     "opb_get_symbolic", "opb_get_L_values", "opb_launch_count", "opb_version",
+    "opb_shard_init", "opb_shard_export", "opb_shard_attach",
 ]
+SHARD_BLOB_BYTES = 320
 
 
 class OPBError(RuntimeError):
@@ -84,6 +86,9 @@ def load():
     L.opb_get_symbolic.argtypes = [vp, ctypes.c_char_p, c_i64p, i64]
     L.opb_get_symbolic.restype = i64
     L.opb_get_L_values.argtypes = [vp, c_f64p, i64]
+    L.opb_shard_init.argtypes = [vp, ci, ci]
+    L.opb_shard_export.argtypes = [vp, ctypes.c_char_p]
+    L.opb_shard_attach.argtypes = [vp, ci, ctypes.c_char_p]
     L.opb_launch_count.restype = ctypes.c_longlong
     L.opb_version.restype = ctypes.c_char_p
     _lib = L
@@ -153,6 +158,19 @@ class Handle:
         Jp, Ji, Hp, Hi = i64(Jp), i64(Ji), i64(Hp), i64(Hi)
         self.check(self.L.opb_set_structure(self.h, n, m, pi(Jp), pi(Ji), pi(Hp), pi(Hi), index_base))
         self.n, self.m = int(n), int(m)
+
+    # --- one instance sharded over several GPUs (include/onephase_b200.h, opb_shard_*)
+    def shard_init(self, rank, world):
+        self.check(self.L.opb_shard_init(self.h, int(rank), int(world)))
+
+    def shard_export(self):
+        buf = ctypes.create_string_buffer(SHARD_BLOB_BYTES)
+        self.check(self.L.opb_shard_export(self.h, buf))
+        return buf.raw
+
+    def shard_attach(self, peer, blob):
+        assert len(blob) == SHARD_BLOB_BYTES
+        self.check(self.L.opb_shard_attach(self.h, int(peer), blob))
 
     # --- numeric
     def form(self, Jx, Hx, y, s, want_diag=True):

@@ -229,4 +229,25 @@ void launch_ctl_single(DeltaState* st_d, double delta, int mode, cudaStream_t st
     count_launch();
 }
 
+// Force-load every kernel of this translation unit (CUDA loads kernels lazily, and a load may
+// synchronise the context: that must not happen while another stream waits in a cross-rank barrier).
+cudaError_t preload_assembly() {
+    cudaFuncAttributes a;
+    cudaError_t e;
+    e = cudaFuncGetAttributes(&a, sigma_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, scale_T_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, assemble_M_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, diag_reset_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, diag_extract_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, diag_finish_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, gather_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, zero_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, scatter_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, ctl_begin_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, ctl_end_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, ctl_init_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, ctl_single_kernel); if (e != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
 }  // namespace opb

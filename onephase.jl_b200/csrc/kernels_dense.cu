@@ -523,7 +523,7 @@ mid_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
         const int64_t rp = S.rowptr[ch];
         const int rc = (int)(S.rowptr[ch + 1] - rp);
         const int* __restrict__ relc = S.rel + rp;
-        const double* __restrict__ cb = CB + S.CBoff[ch];
+        const double* __restrict__ cb = child_cb(S, CB, ch);
         int lo = 0, hi = rc;               // uc = number of child rows that land on pivot columns
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < c) lo = mid + 1; else hi = mid; }
         const int uc = lo;
@@ -559,7 +559,7 @@ big_extend_add_panel_kernel(DevSym S, const int* __restrict__ list, double* __re
         const int64_t rp = S.rowptr[ch];
         const int rc = (int)(S.rowptr[ch + 1] - rp);
         const int* __restrict__ relc = S.rel + rp;
-        const double* __restrict__ cb = CB + S.CBoff[ch];
+        const double* __restrict__ cb = child_cb(S, CB, ch);
         int lo = 0, hi = rc;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < row0) lo = mid + 1; else hi = mid; }
         const int t0 = lo;
@@ -718,7 +718,7 @@ front_cb_kernel(DevSym S, const int* __restrict__ list, const double* __restrict
         const int u1 = lo;
         const int nt2 = t1 - t0, nu = u1 - u0;
         if (nt2 <= 0 || nu <= 0) continue;          // uniform across the CTA
-        const double* __restrict__ cb = CB + S.CBoff[ch];
+        const double* __restrict__ cb = child_cb(S, CB, ch);
         for (int idx = tid; idx < nt2 * nu; idx += GEMM_THREADS) {
             const int tt = t0 + idx % nt2, u = u0 + idx / nt2;
             if (tt >= u) T[(relc[tt] - ri) + (relc[u] - rj) * TLD] += cb[tt + (size_t)u * rc];
@@ -824,7 +824,7 @@ wide_fwd_gather_kernel(DevSym S, const int* __restrict__ list, double* __restric
         const int64_t rpc = S.rowptr[ch];
         const int rc = (int)(S.rowptr[ch + 1] - rpc);
         const int* __restrict__ relc = S.rel + rpc;
-        const double* uc = u + rpc;
+        const double* uc = child_u(S, u, ch);
         int lo = 0, hi = rc;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < row0) lo = mid + 1; else hi = mid; }
         const int t0 = lo;
@@ -1124,6 +1124,27 @@ void launch_solve_wide_bwd(const DevSym& S, const LevelPlan& L, const int* d_sch
         wide_bwd_tri_kernel<<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
         count_launch(2);
     }
+}
+
+// Force-load every kernel of this translation unit (CUDA loads kernels lazily, and a load may
+// synchronise the context: that must not happen while another stream waits in a cross-rank barrier).
+cudaError_t preload_dense() {
+    cudaFuncAttributes a;
+    cudaError_t e;
+    e = cudaFuncGetAttributes(&a, big_extend_add_panel_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, chol_diag_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, chol_panel_update_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, chol_trsm_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, front_cb_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, mid_panel_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, trtri_merge_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_bwd_gather_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_bwd_tri_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_bwd_upd_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_fwd_gather_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_fwd_tri_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_fwd_upd_kernel); if (e != cudaSuccess) return e;
+    return cudaSuccess;
 }
 
 }  // namespace opb

@@ -103,7 +103,7 @@ front_small_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ 
         const int64_t rp = S.rowptr[ch];
         const int rc = (int)(S.rowptr[ch + 1] - rp);
         const int* __restrict__ relc = S.rel + rp;
-        const double* __restrict__ cb = CB + S.CBoff[ch];
+        const double* __restrict__ cb = child_cb(S, CB, ch);
         for (int j = 0; j < rc; j++) {
             const int pj = relc[j];
             for (int i = j + tid; i < rc; i += THREADS)
@@ -154,7 +154,7 @@ big_extend_add_kernel(DevSym S, const int* __restrict__ list, double* __restrict
         const int64_t rp = S.rowptr[ch];
         const int rc = (int)(S.rowptr[ch + 1] - rp);
         const int* __restrict__ relc = S.rel + rp;
-        const double* __restrict__ cb = CB + S.CBoff[ch];
+        const double* __restrict__ cb = child_cb(S, CB, ch);
         // rows t of the child with row0 <= rel[t] < row1 (rel is ascending)
         int lo = 0, hi = rc;
         while (lo < hi) { int mid = (lo + hi) >> 1; if (relc[mid] < row0) lo = mid + 1; else hi = mid; }
@@ -361,8 +361,10 @@ cudaError_t factor_configure() {
 
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
-                          int outer_block, cudaStream_t st) {
+                          int outer_block, const ShardCtx* shard, cudaStream_t st) {
     for (const LevelPlan& L : plan) {
+        // sharded instance: the update blocks of children on other ranks must be complete
+        if (shard && L.barrier_before) launch_shard_barrier(*shard, st);
         if (L.count[FC_T32]) {
             front_small_kernel<64><<<L.count[FC_T32], 64, small_smem(L.maxN[FC_T32]), st>>>(
                 S, d_sched + L.begin[FC_T32], Lval, CB, st_d);
@@ -407,6 +409,21 @@ void launch_ldlt_inertia(const DevSym& S, const double* Lval, const int64_t* dpo
     (void)S;
     ldlt_inertia_kernel<<<(n + 255) / 256, 256, 0, st>>>(Lval, dpos, n, st_d);
     count_launch();
+}
+
+// Force-load every kernel of this translation unit (CUDA loads kernels lazily, and a load may
+// synchronise the context: that must not happen while another stream waits in a cross-rank barrier).
+cudaError_t preload_factor() {
+    cudaFuncAttributes a;
+    cudaError_t e;
+    e = cudaFuncGetAttributes(&a, front_small_kernel<64>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, front_small_kernel<256>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, big_extend_add_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, big_potrf_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, big_trsm_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, big_update_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, ldlt_inertia_kernel); if (e != cudaSuccess) return e;
+    return cudaSuccess;
 }
 
 }  // namespace opb

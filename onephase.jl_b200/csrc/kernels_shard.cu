@@ -1,0 +1,119 @@
+// One KKT instance sharded over several B200s: the pieces that cross GPUs.
+//
+// Independent subtrees of the supernodal elimination tree are factorised and solved by
+// different ranks (one process per GPU); only the top separators couple them.  Nothing here
+// calls a collective library: the buffers that cross ranks (update blocks, forward update
+// vectors, the solution vector, a few flag words) are peer-mapped (CUDA IPC over NVLink), the
+// consuming kernels read their children's data straight from the owner's HBM (child_cb /
+// child_u in opb_internal.h), and the ordering between ranks is a flag barrier on the stream:
+//
+//   shard_barrier_kernel   every rank publishes (epoch, fail) into each peer's flag array with
+//                          system-scope release stores, then spins on its own array until every
+//                          peer has published the same epoch.  The fail bits are OR-ed into the
+//                          local DeltaState, so a non-positive pivot on any rank stops the
+//                          attempt everywhere and the delta rule takes the same decision on
+//                          every rank without a host round trip.
+//   push_* kernels         backward sweep: the owner of a top supernode writes its part of the
+//                          solution into every peer's vector; at the end every rank publishes
+//                          the columns it owns, so the full solution is resident everywhere.
+//
+// The kernels are stream-ordered and capturable in CUDA graphs (the epoch lives in device memory).
+#include "opb_internal.h"
+
+namespace opb {
+
+namespace {
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+
+__global__ void __launch_bounds__(32)
+shard_barrier_kernel(ShardCtx C) {
+    DeltaState* st = C.state;
+    __shared__ unsigned long long s_epoch;
+    const int lane = threadIdx.x;
+    if (lane == 0) { s_epoch = *C.epoch + 1; *C.epoch = s_epoch; }
+    __syncwarp();
+    const unsigned long long e = s_epoch;
+    const int slot = (int)(e & 1) * MAX_SHARD;
+    const int myfail = *(volatile int*)&st->fail ? 1 : 0;
+    __threadfence_system();                      // everything this rank wrote before the barrier
+    int peerfail = 0;
+    if (lane < C.world && lane != C.rank) {
+        st_release_sys(C.flags_peer[lane] + slot + C.rank, (e << 1) | (unsigned long long)myfail);
+        const long long t0 = clock64();
+        unsigned long long v;
+        for (;;) {
+            v = ld_acquire_sys(C.flags_local + slot + lane);
+            if ((v >> 1) >= e) break;
+            if (clock64() - t0 > C.timeout_clocks) { *C.error = 1; peerfail = 1; break; }
+            __nanosleep(200);
+        }
+        if ((v >> 1) == e && (v & 1)) peerfail = 1;
+    }
+    peerfail = __any_sync(0xffffffffu, peerfail);
+    if (lane == 0 && peerfail) st->fail = 1;
+    __threadfence_system();
+}
+
+// x of the listed supernodes that are flagged `top` -> every peer's vector
+__global__ void __launch_bounds__(256)
+push_supernodes_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ x) {
+    const int s = list[blockIdx.y];
+    const int first = S.sfirst[s];
+    const int c = S.sfirst[s + 1] - first;
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= c) return;
+    const double v = x[first + k];
+    for (int p = 0; p < S.world; p++)
+        if (p != S.rank) S.x_peer[p][first + k] = v;
+}
+
+// every column this rank owns -> every peer's vector (end of the backward sweep)
+__global__ void __launch_bounds__(256)
+push_owned_kernel(DevSym S, const int* __restrict__ colowner, const double* __restrict__ x) {
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= S.n || colowner[k] != S.rank) return;
+    const double v = x[k];
+    for (int p = 0; p < S.world; p++)
+        if (p != S.rank) S.x_peer[p][k] = v;
+}
+
+}  // namespace
+
+void launch_shard_barrier(const ShardCtx& C, cudaStream_t st) {
+    shard_barrier_kernel<<<1, 32, 0, st>>>(C);
+    count_launch();
+}
+
+void launch_push_supernodes(const DevSym& S, const int* list, int count, int maxc, const double* x, cudaStream_t st) {
+    if (count <= 0 || maxc <= 0) return;
+    dim3 g((maxc + 255) / 256, count);
+    push_supernodes_kernel<<<g, 256, 0, st>>>(S, list, x);
+    count_launch();
+}
+
+void launch_push_owned(const DevSym& S, const int* colowner, const double* x, cudaStream_t st) {
+    push_owned_kernel<<<(S.n + 255) / 256, 256, 0, st>>>(S, colowner, x);
+    count_launch();
+}
+
+// Force-load every kernel of this translation unit (CUDA loads kernels lazily, and a load may
+// synchronise the context: that must not happen while another stream waits in a cross-rank barrier).
+cudaError_t preload_shard() {
+    cudaFuncAttributes a;
+    cudaError_t e;
+    e = cudaFuncGetAttributes(&a, shard_barrier_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, push_supernodes_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, push_owned_kernel); if (e != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+}  // namespace opb

@@ -52,7 +52,7 @@ fwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
         const int64_t rpc = S.rowptr[ch];
         const int rc = (int)(S.rowptr[ch + 1] - rpc);
         const int* __restrict__ relc = S.rel + rpc;
-        const double* uc = u + rpc;
+        const double* uc = child_u(S, u, ch);
         for (int t = tid; t < rc; t += ST) {
             const int dst = relc[t];
             const double v = uc[t];
@@ -167,13 +167,19 @@ cudaError_t solve_configure() { return cudaSuccess; }
 
 void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                   const double* Lval, const double* Xinv, double* x, double* xnew, double* u, int mode,
-                  cudaStream_t st) {
+                  const ShardCtx* shard, const int* colowner, cudaStream_t st) {
     // Cholesky: BIG supernodes take the multi-CTA path through inv(L11) (kernels_dense.cu), the
     // other classes (front or panel fits in shared memory) are solved by one CTA each;
     // LDL': every supernode is solved by one CTA.
+    // Sharded instance: a rank runs the supernodes it owns.  Forward, a level whose supernodes
+    // have children on other ranks waits at a barrier and reads those children's update vectors
+    // from the owners' HBM; backward, the owner of a top supernode pushes its part of the solution
+    // to every peer before the ranks below continue, and at the end every rank publishes the
+    // columns it owns.
     const bool wide = (mode == 0);
     for (size_t l = 0; l < plan.size(); l++) {
         const LevelPlan& L = plan[l];
+        if (shard && L.barrier_before) launch_shard_barrier(*shard, st);
         const int solo = wide ? L.all_count - L.count[FC_BIG] : L.all_count;
         if (solo) { fwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.all_begin, Lval, x, u, mode); count_launch(); }
         if (wide) launch_solve_wide_fwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
@@ -183,6 +189,14 @@ void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int
         const int solo = wide ? L.all_count - L.count[FC_BIG] : L.all_count;
         if (solo) { bwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.all_begin, Lval, x, u, mode); count_launch(); }
         if (wide) launch_solve_wide_bwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
+        if (shard) {
+            launch_push_supernodes(S, d_sched + L.push_begin, L.push_count, L.push_maxc, x, st);
+            if (L.barrier_before) launch_shard_barrier(*shard, st);
+        }
+    }
+    if (shard) {
+        launch_push_owned(S, colowner, x, st);
+        launch_shard_barrier(*shard, st);
     }
 }
 
@@ -193,6 +207,18 @@ void launch_permute_in(const double* b, const int* perm, double* x, int n, cudaS
 void launch_permute_out_add(const double* x, const int* perm, double* dst, int n, int accumulate, cudaStream_t st) {
     permute_out_kernel<<<(n + 255) / 256, 256, 0, st>>>(x, perm, dst, n, accumulate);
     count_launch();
+}
+
+// Force-load every kernel of this translation unit (CUDA loads kernels lazily, and a load may
+// synchronise the context: that must not happen while another stream waits in a cross-rank barrier).
+cudaError_t preload_solve() {
+    cudaFuncAttributes a;
+    cudaError_t e;
+    e = cudaFuncGetAttributes(&a, fwd_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, bwd_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, permute_in_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, permute_out_kernel); if (e != cudaSuccess) return e;
+    return cudaSuccess;
 }
 
 }  // namespace opb

@@ -173,4 +173,25 @@ void launch_recover_and_error(const DirBuffers& B, cudaStream_t st) {
     count_launch(4);
 }
 
+// Force-load every kernel of this translation unit (CUDA loads kernels lazily, and a load may
+// synchronise the context: that must not happen while another stream waits in a cross-rank barrier).
+cudaError_t preload_vec() {
+    cudaFuncAttributes a;
+    cudaError_t e;
+    e = cudaFuncGetAttributes(&a, rhs_m_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, rhs_n_kernel<1>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, rhs_n_kernel<32>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, res_m_kernel<1>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, res_m_kernel<32>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, res_n_kernel<1>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, res_n_kernel<32>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, red_reset_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, recover_m_kernel<1>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, recover_m_kernel<32>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, recover_n_kernel<1>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, recover_n_kernel<32>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, kkt_err_finish_kernel); if (e != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
 }  // namespace opb

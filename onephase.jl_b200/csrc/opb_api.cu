@@ -3,6 +3,8 @@
 // done on the host; without a CUDA device the numeric entry points fail.
 #include <cuda_runtime.h>
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -30,6 +32,11 @@ struct Bundle {
     int64_t x_total = 0;
     TrtriPlan trtri;
     int n_tiny = 0, n_small = 0, n_big = 0;
+    // one instance sharded over `world` GPUs: this bundle holds the schedule of `rank`
+    int rank = 0, world = 1;
+    ShardMap shard;
+    std::vector<int> colowner;   // per permuted column: owning rank
+    DBuf<int> d_owner, d_colowner;
     int device = -1;
     size_t device_bytes = 0;
     // device copies
@@ -46,6 +53,7 @@ struct Bundle {
         d_Mp.release(); d_src.release(); d_Xoff.release(); d_pair_ptr.release(); d_Jp.release(); d_Rp.release(); d_Sp.release();
         d_pairA.release(); d_pairB.release(); d_hmap.release(); d_Jrow.release(); d_Rcol.release();
         d_Rpos.release(); d_Scol.release(); d_Spos.release();
+        d_owner.release(); d_colowner.release();
     }
 };
 
@@ -64,12 +72,17 @@ static void build_plan(Bundle& B) {
     auto cols = [&](int s) { return S.sfirst[s + 1] - S.sfirst[s]; };
     auto rows = [&](int s) { return cols(s) + (int)(S.rowptr[s + 1] - S.rowptr[s]); };
     std::vector<int> all_big;
+    const bool sharded = B.world > 1;
     for (int l = 0; l < S.nlevels; l++) {
         LevelPlan& L = B.plan[l];
         std::vector<int> cls[NFC];
+        std::vector<int> push;
+        if (sharded) L.barrier_before = B.shard.level_barrier[l];
         for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
             const int s = S.level_list[t];
+            if (sharded && B.shard.owner[s] != B.rank) continue;      // another rank's supernode
             const int c = cols(s), N = rows(s);
+            if (sharded && B.shard.top[s]) { push.push_back(s); L.push_maxc = std::max(L.push_maxc, c); }
             int fc;
             if (N <= FC_MAXN[FC_T32]) fc = FC_T32;
             else if (N <= FC_MAXN[FC_S64]) fc = FC_S64;
@@ -110,6 +123,9 @@ static void build_plan(Bundle& B) {
                 }
         }
         L.all_count = (int)B.sched.size() - L.all_begin;
+        L.push_begin = (int)B.sched.size();
+        L.push_count = (int)push.size();
+        B.sched.insert(B.sched.end(), push.begin(), push.end());
         L.solo_count = L.count[FC_T32] + L.count[FC_S64] + L.count[FC_S104] + L.count[FC_S152];
         L.wide_begin = L.begin[FC_MID];
         L.wide_count = L.all_count - L.solo_count;
@@ -152,6 +168,7 @@ struct opb_handle {
     std::vector<int64_t> user_perm;
     int attempts_per_sync = 2;
     int outer_block = OUTER_BLOCK;
+    double barrier_timeout_s = 20.0;     // sharded instance: a rank that waits longer reports an error
     std::shared_ptr<Bundle> B;
     bool cached_hit = false;
     // numeric state
@@ -175,6 +192,21 @@ struct opb_handle {
             if (g->exec) cudaGraphExecDestroy(g->exec);
             *g = GraphSlot();
         }
+    }
+
+    // ---- one instance sharded over several GPUs (opb_shard_*)
+    int shard_rank = 0, shard_world = 1;
+    DevSym dev{};                        // B->dev plus this handle's peer pointers
+    ShardCtx sctx{};
+    unsigned long long* d_flags = nullptr;   // [2][MAX_SHARD] flags, [16] epoch, [17] error
+    bool peer_ok[MAX_SHARD] = {false};
+    void* peer_ipc[MAX_SHARD][4] = {{nullptr}};
+    std::string peer_blob[MAX_SHARD];
+    bool sharded() const { return shard_world > 1; }
+    const ShardCtx* shard_ctx() const { return shard_world > 1 ? &sctx : nullptr; }
+    void close_peer(int p) {
+        for (int k = 0; k < 4; k++) if (peer_ipc[p][k]) { cudaIpcCloseMemHandle(peer_ipc[p][k]); peer_ipc[p][k] = nullptr; }
+        peer_ok[p] = false; peer_blob[p].clear();
     }
 
     int fail(int code, const std::string& msg) { err = msg; return code; }
@@ -247,6 +279,11 @@ int opb_create(opb_handle** out, int device_id, unsigned flags) {
         if (e != cudaSuccess) return h->cuda_fail(e, "dense_configure (is this an sm_100a device?)");
         e = h->red.alloc(8);
         if (e != cudaSuccess) return h->cuda_fail(e, "cudaMalloc(red)");
+        for (auto pre : {preload_assembly, preload_vec, preload_solve, preload_factor, preload_dense, preload_shard}) {
+            e = pre();
+            if (e != cudaSuccess) return h->cuda_fail(e, "kernel preload (is this an sm_100a device?)");
+        }
+
     }
     return OPB_OK;
 }
@@ -262,6 +299,8 @@ int opb_destroy(opb_handle* h) {
         for (auto* b : bufs) b->release();
         h->red.release();
         h->drop_graphs();
+        for (int p = 0; p < MAX_SHARD; p++) h->close_peer(p);
+        if (h->d_flags) cudaFree(h->d_flags);
         if (h->d_state_raw) cudaFree(h->d_state_raw);
         if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     }
@@ -291,6 +330,7 @@ int opb_set_option(opb_handle* h, const char* key, double v) {
     else if (k == "relax_small") h->opt.relax_small = v;
     else if (k == "attempts_per_sync") h->attempts_per_sync = std::max(1, (int)v);
     else if (k == "outer_block") { h->outer_block = std::max(WB, ((int)v / WB) * WB); h->drop_graphs(); }
+    else if (k == "barrier_timeout_s") { h->barrier_timeout_s = v; h->sctx.timeout_clocks = (long long)(v * 2.0e9); h->drop_graphs(); }
     else if (k == "graphs") { h->use_graphs = v != 0; h->drop_graphs(); }
     else return h->fail(OPB_ERR_INVALID, "unknown option " + k);
     return OPB_OK;
@@ -300,6 +340,92 @@ int opb_set_permutation(opb_handle* h, int64_t n, const int64_t* perm) {
     if (!h) return OPB_ERR_INVALID;
     if (!perm || n <= 0) { h->user_perm.clear(); return OPB_OK; }
     h->user_perm.assign(perm, perm + n);
+    return OPB_OK;
+}
+
+// ---- one instance over several GPUs ---------------------------------------
+// blob layout: [0] pid, [8] CB, [16] u, [24] x, [32] flags (raw device pointers, valid inside the
+// exporting process), [64 + 64 k] cudaIpcMemHandle_t of the same four buffers
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "blob layout");
+static_assert(OPB_SHARD_BLOB_BYTES >= 64 + 4 * 64, "blob layout");
+
+int opb_shard_init(opb_handle* h, int rank, int world) {
+    if (!h) return OPB_ERR_INVALID;
+    if (world < 1 || world > MAX_SHARD || rank < 0 || rank >= world) return h->fail(OPB_ERR_INVALID, "bad rank / world");
+    if (h->B) return h->fail(OPB_ERR_STATE, "opb_shard_init must precede opb_set_structure");
+    h->shard_rank = rank; h->shard_world = world;
+    if (h->device >= 0 && world > 1) {
+        cudaSetDevice(h->device);
+        if (!h->d_flags) CK(cudaMalloc((void**)&h->d_flags, 32 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(h->d_flags, 0, 32 * sizeof(unsigned long long), h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->sctx = ShardCtx();
+        h->sctx.rank = rank; h->sctx.world = world;
+        h->sctx.flags_local = h->d_flags;
+        h->sctx.flags_peer[rank] = h->d_flags;
+        h->sctx.epoch = h->d_flags + 2 * MAX_SHARD;
+        h->sctx.error = reinterpret_cast<int*>(h->d_flags + 2 * MAX_SHARD + 1);
+        h->sctx.state = h->d_state;
+        h->sctx.timeout_clocks = (long long)(h->barrier_timeout_s * 2.0e9);
+    }
+    return OPB_OK;
+}
+
+int opb_shard_export(opb_handle* h, unsigned char* blob) {
+    if (!h || !blob) return OPB_ERR_INVALID;
+    if (h->device < 0) return h->fail(OPB_ERR_NO_DEVICE, "host-only handle");
+    if (!h->sharded() || !h->B) return h->fail(OPB_ERR_STATE, "opb_shard_init + opb_set_structure first");
+    cudaSetDevice(h->device);
+    memset(blob, 0, OPB_SHARD_BLOB_BYTES);
+    const uint64_t pid = (uint64_t)getpid();
+    void* ptrs[4] = {h->CB.p, h->uw.p, h->xw.p, h->d_flags};
+    memcpy(blob, &pid, 8);
+    for (int k = 0; k < 4; k++) {
+        memcpy(blob + 8 + 8 * k, &ptrs[k], 8);
+        cudaIpcMemHandle_t ih;
+        CK(cudaIpcGetMemHandle(&ih, ptrs[k]));
+        memcpy(blob + 64 + 64 * k, &ih, 64);
+    }
+    return OPB_OK;
+}
+
+int opb_shard_attach(opb_handle* h, int peer, const unsigned char* blob) {
+    if (!h || !blob) return OPB_ERR_INVALID;
+    if (h->device < 0) return h->fail(OPB_ERR_NO_DEVICE, "host-only handle");
+    if (!h->sharded() || !h->B) return h->fail(OPB_ERR_STATE, "opb_shard_init + opb_set_structure first");
+    if (peer < 0 || peer >= h->shard_world || peer == h->shard_rank) return h->fail(OPB_ERR_INVALID, "bad peer");
+    cudaSetDevice(h->device);
+    h->drop_graphs();
+    const std::string nb(reinterpret_cast<const char*>(blob), OPB_SHARD_BLOB_BYTES);
+    void* ptrs[4];
+    uint64_t pid;
+    memcpy(&pid, blob, 8);
+    if (pid == (uint64_t)getpid()) {
+        // same process (several handles on one or more devices): the raw pointers are usable.
+        // Graph instantiation / first launch may synchronise the whole context; with a peer of
+        // the same context waiting in a barrier for THIS thread's next launch that would stall
+        // until the barrier times out, so same-process peers use plain launches.  (Between
+        // processes the ranks' contexts are independent and the graphs stay on.)
+        h->use_graphs = false;
+        h->close_peer(peer);
+        for (int k = 0; k < 4; k++) memcpy(&ptrs[k], blob + 8 + 8 * k, 8);
+    } else if (h->peer_blob[peer] == nb && h->peer_ipc[peer][0]) {
+        for (int k = 0; k < 4; k++) ptrs[k] = h->peer_ipc[peer][k];     // same allocations as before
+    } else {
+        h->close_peer(peer);
+        for (int k = 0; k < 4; k++) {
+            cudaIpcMemHandle_t ih;
+            memcpy(&ih, blob + 64 + 64 * k, 64);
+            CK(cudaIpcOpenMemHandle(&ptrs[k], ih, cudaIpcMemLazyEnablePeerAccess));
+            h->peer_ipc[peer][k] = ptrs[k];
+        }
+    }
+    h->peer_blob[peer] = nb;
+    h->dev.cb_peer[peer] = static_cast<double*>(ptrs[0]);
+    h->dev.u_peer[peer] = static_cast<double*>(ptrs[1]);
+    h->dev.x_peer[peer] = static_cast<double*>(ptrs[2]);
+    h->sctx.flags_peer[peer] = static_cast<unsigned long long*>(ptrs[3]);
+    h->peer_ok[peer] = true;
     return OPB_OK;
 }
 
@@ -314,6 +440,7 @@ static int upload_bundle(opb_handle* h, Bundle& B) {
     CK(B.d_child_list.upload(S.child_list, st)); CK(B.d_perm.upload(S.perm, st));
     CK(B.d_sched.upload(B.sched, st));
     CK(B.d_Xoff.upload(B.Xoff, st));
+    if (B.world > 1) { CK(B.d_owner.upload(B.shard.owner, st)); CK(B.d_colowner.upload(B.colowner, st)); }
     {
         // diagonal entries carry a flag so the scatter kernel adds delta to them
         std::vector<int64_t> amap = S.amap;
@@ -339,6 +466,8 @@ static int upload_bundle(opb_handle* h, Bundle& B) {
     B.dev.rel = B.d_rel.p; B.dev.Loff = B.d_Loff.p; B.dev.CBoff = B.d_CBoff.p;
     B.dev.sparent = B.d_sparent.p; B.dev.child_ptr = B.d_child_ptr.p; B.dev.child_list = B.d_child_list.p;
     B.dev.perm = B.d_perm.p; B.dev.Xoff = B.d_Xoff.p;
+    B.dev.owner = B.world > 1 ? B.d_owner.p : nullptr;
+    B.dev.rank = B.rank; B.dev.world = B.world;
     return OPB_OK;
 }
 
@@ -365,13 +494,22 @@ static int alloc_numeric(opb_handle* h) {
         CK(h->dual_r.alloc(n)); CK(h->primal_r.alloc(m)); CK(h->comp_r.alloc(m));
         CK(h->dy.alloc(m)); CK(h->ds.alloc(m)); CK(h->tm.alloc(m));
     }
+    h->dev = B.dev;
+    if (h->sharded()) {
+        // own buffers; the peers' are attached by opb_shard_attach (again after every new structure)
+        h->dev.cb_peer[h->shard_rank] = h->CB.p; h->dev.u_peer[h->shard_rank] = h->uw.p;
+        h->dev.x_peer[h->shard_rank] = h->xw.p;
+        for (int p = 0; p < h->shard_world; p++) if (p != h->shard_rank) h->peer_ok[p] = false;
+    }
     return OPB_OK;
 }
 
-static std::string cache_key(int device, const SymOptions& o, bool has_perm, uint64_t h1, uint64_t h2) {
-    char buf[160];
-    snprintf(buf, sizeof buf, "%d|%d|%d|%d|%d|%d|%016llx|%016llx", device, o.nd_leaf, o.ordering, o.metis_max_n, o.relax_enable,
-             has_perm ? 1 : 0, (unsigned long long)h1, (unsigned long long)h2);
+static std::string cache_key(const opb_handle* h, uint64_t h1, uint64_t h2) {
+    const SymOptions& o = h->opt;
+    char buf[200];
+    snprintf(buf, sizeof buf, "%d|%d|%d|%d|%d|%d|%d/%d|%016llx|%016llx", h->device, o.nd_leaf, o.ordering, o.metis_max_n,
+             o.relax_enable, h->user_perm.empty() ? 0 : 1, h->shard_rank, h->shard_world,
+             (unsigned long long)h1, (unsigned long long)h2);
     return buf;
 }
 
@@ -395,8 +533,21 @@ static int finish_structure(opb_handle* h, std::shared_ptr<Bundle> B, const std:
     const int64_t* up = h->user_perm.empty() ? nullptr : h->user_perm.data();
     if (up && (int64_t)h->user_perm.size() != (int64_t)(B->Mp.size() - 1))
         return h->fail(OPB_ERR_INVALID, "permutation length does not match n");
-    if (!analyze((int)(B->Mp.size() - 1), B->Mp, B->Mi, h->opt, up, B->S))
-        return h->fail(OPB_ERR_INTERNAL, "symbolic analysis failed: " + B->S.error);
+    {
+        // METIS keeps process-wide random-number state: concurrent analyses (several handles driven
+        // by host threads) would not be reproducible, and the ranks of a sharded instance must
+        // derive the SAME ordering.  One analysis at a time.
+        static std::mutex analyze_mu;
+        std::lock_guard<std::mutex> g(analyze_mu);
+        if (!analyze((int)(B->Mp.size() - 1), B->Mp, B->Mi, h->opt, up, B->S))
+            return h->fail(OPB_ERR_INTERNAL, "symbolic analysis failed: " + B->S.error);
+    }
+    B->rank = h->shard_rank; B->world = h->shard_world;
+    if (B->world > 1) {
+        shard_map(B->S, B->world, B->shard);
+        B->colowner.resize(B->S.n);
+        for (int j = 0; j < B->S.n; j++) B->colowner[j] = B->shard.owner[B->S.col2super[j]];
+    }
     build_plan(*B);
     if (h->device >= 0) {
         cudaSetDevice(h->device);
@@ -421,7 +572,7 @@ int opb_set_structure(opb_handle* h, int64_t n, int64_t m, const int64_t* Jp, co
     uint64_t h1 = pattern_hash(n, Jp, Ji, nnzJ) ^ (uint64_t)m * 0x9e3779b97f4a7c15ull;
     uint64_t h2 = pattern_hash(n, Hp, Hi, nnzH) + (uint64_t)base;
     if (!h->user_perm.empty()) h2 ^= pattern_hash(0, h->user_perm.data(), h->user_perm.data(), (int64_t)h->user_perm.size());
-    std::string key = "S|" + cache_key(h->device, h->opt, !h->user_perm.empty(), h1, h2);
+    std::string key = "S|" + cache_key(h, h1, h2);
     if (auto B = cache_get(key)) {
         if (B->S.n == n && B->P.m == m && B->P.nnzJ == nnzJ && B->P.nnzH == nnzH) {
             h->B = B; h->cached_hit = true; h->ready = opb_handle::NOT_READY;
@@ -442,6 +593,10 @@ static int need_device(opb_handle* h) {
     if (!h) return OPB_ERR_INVALID;
     if (h->device < 0) return h->fail(OPB_ERR_NO_DEVICE, "numeric call on a host-only handle (no CPU fallback)");
     cudaSetDevice(h->device);
+    if (h->sharded() && h->B)
+        for (int p = 0; p < h->shard_world; p++)
+            if (p != h->shard_rank && !h->peer_ok[p])
+                return h->fail(OPB_ERR_STATE, "sharded handle: peer buffers not attached (opb_shard_export / opb_shard_attach after opb_set_structure)");
     return OPB_OK;
 }
 
@@ -464,10 +619,12 @@ static void enqueue_attempt_raw(opb_handle* h) {
     launch_ctl_begin(h->d_state, st);
     launch_scatter_fronts(h->Mval.p, B.d_amap.p, B.d_dpos.p, h->sdiag.p, h->Lval.p, B.S.nnzL,
                           B.Mp[B.S.n], B.S.n, h->d_state, 1, st);
-    launch_factor_levels(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->Xinv.p, h->d_state, h->mode,
-                         h->outer_block, st);
+    launch_factor_levels(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->Xinv.p, h->d_state, h->mode,
+                         h->outer_block, h->shard_ctx(), st);
     if (h->mode == OPB_MODE_CHOLESKY && B.trtri.count)
-        launch_trtri(B.dev, B.trtri, B.d_sched.p, h->Lval.p, h->Xinv.p, h->Twork.p, h->d_state, st);
+        launch_trtri(h->dev, B.trtri, B.d_sched.p, h->Lval.p, h->Xinv.p, h->Twork.p, h->d_state, st);
+    // sharded: every rank learns about a failed pivot anywhere before the delta rule is applied
+    if (h->sharded()) launch_shard_barrier(h->sctx, st);
     launch_ctl_end(h->d_state, st);
 }
 
@@ -477,7 +634,20 @@ static void enqueue_attempt(opb_handle* h) {
 
 static int read_state(opb_handle* h) {
     CK(cudaMemcpyAsync(&h->h_state, h->d_state, sizeof(DeltaState), cudaMemcpyDeviceToHost, h->stream));
+    int shard_err = 0;
+    if (h->sharded()) CK(cudaMemcpyAsync(&shard_err, h->sctx.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (shard_err) {
+        unsigned long long f[2 * MAX_SHARD + 2] = {0};
+        cudaMemcpy(f, h->d_flags, sizeof f, cudaMemcpyDeviceToHost);
+        char buf[512];
+        int o = snprintf(buf, sizeof buf, "sharded instance: a peer GPU did not reach the barrier (timeout); rank %d/%d epoch %llu, peers' (epoch,fail):",
+                         h->shard_rank, h->shard_world, f[2 * MAX_SHARD]);
+        for (int sl = 0; sl < 2; sl++)
+            for (int p = 0; p < h->shard_world && o < 480; p++)
+                o += snprintf(buf + o, sizeof buf - o, " s%d[%d]=(%llu,%llu)", sl, p, f[sl * MAX_SHARD + p] >> 1, f[sl * MAX_SHARD + p] & 1);
+        return h->fail(OPB_ERR_INTERNAL, buf);
+    }
     return OPB_OK;
 }
 
@@ -569,7 +739,7 @@ static int single_factor(opb_handle* h, double delta, int mode, int* ok) {
     launch_ctl_single(h->d_state, delta, mode, h->stream);
     enqueue_attempt(h);
     if (mode == OPB_MODE_LDLT)
-        launch_ldlt_inertia(h->B->dev, h->Lval.p, h->B->d_dpos.p, h->B->S.n, h->d_state, h->stream);
+        launch_ldlt_inertia(h->dev, h->Lval.p, h->B->d_dpos.p, h->B->S.n, h->d_state, h->stream);
     CK(cudaGetLastError());
     int rc = read_state(h); if (rc) return rc;
     h->ready = opb_handle::FACTORED;
@@ -623,7 +793,8 @@ int opb_direction_resident(opb_handle* h, int n_refine) {
         launch_schur_rhs(D, st);
         for (int it = 0; it < n_refine; it++) {
             launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, D.n, st);
-            launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode, st);
+            launch_solve(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode,
+                         h->shard_ctx(), B.d_colowner.p, st);
             launch_permute_out_add(h->xw.p, B.d_perm.p, h->dx.p, D.n, 1, st);
             // the reference also evaluates the residual after the last correction but only
             // prints it (schur.jl:177-179); it does not influence the direction
@@ -656,7 +827,8 @@ int opb_solve_resident(opb_handle* h, int nsolves) {
     for (int k = 0; k < nsolves; k++)
         run_captured(h, h->g_solve, h->mode, [&] {
             launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, B.S.n, h->stream);
-            launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode, h->stream);
+            launch_solve(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode,
+                         h->shard_ctx(), B.d_colowner.p, h->stream);
             launch_permute_out_add(h->xw.p, B.d_perm.p, h->b.p, B.S.n, 0, h->stream);
         });
     CK(cudaGetLastError());
@@ -698,10 +870,11 @@ int opb_ls_factor_csc(opb_handle* h, int64_t dim, const int64_t* cp, const int64
     if (!cp || !ri || !nz || dim <= 0 || (base != 0 && base != 1)) return h->fail(OPB_ERR_INVALID, "bad arguments");
     if (mode != OPB_MODE_CHOLESKY && mode != OPB_MODE_LDLT) return h->fail(OPB_ERR_INVALID, "bad mode");
     if (mode == OPB_MODE_CHOLESKY && m_neg != 0) return h->fail(OPB_ERR_INVALID, "Cholesky requires m == 0 (julia.jl:30)");
+    if (h->sharded()) return h->fail(OPB_ERR_INVALID, "opb_ls_factor_csc is not available on a sharded handle");
     int rc = need_device(h); if (rc) return rc;
     const int64_t nnz = cp[dim] - base;
     uint64_t h1 = pattern_hash(dim, cp, ri, nnz) + (uint64_t)base;
-    std::string key = "C|" + cache_key(h->device, h->opt, !h->user_perm.empty(), h1, 0);
+    std::string key = "C|" + cache_key(h, h1, 0);
     std::shared_ptr<Bundle> B = cache_get(key);
     if (B && (B->S.n != dim || B->schur)) B.reset();
     if (B) {
@@ -740,7 +913,8 @@ int opb_ls_solve(opb_handle* h, const double* rhs, double* sol) {
     cudaStream_t st = h->stream;
     CK(cudaMemcpyAsync(h->res.p, rhs, n * sizeof(double), cudaMemcpyHostToDevice, st));
     launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, n, st);
-    launch_solve(B.dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode, st);
+    launch_solve(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode,
+                         h->shard_ctx(), B.d_colowner.p, st);
     launch_permute_out_add(h->xw.p, B.d_perm.p, h->b.p, n, 0, st);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(sol, h->b.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -775,6 +949,11 @@ int opb_get_info(opb_handle* h, const char* key, double* out) {
     else if (k == "sum_rows") *out = (double)S.rowidx.size();
     else if (k == "x_total") *out = (double)B.x_total;
     else if (k == "n_trtri") *out = B.trtri.count;
+    else if (k == "shard_rank") *out = B.rank;
+    else if (k == "shard_world") *out = B.world;
+    else if (k == "shard_load") *out = B.world > 1 ? B.shard.load[B.rank] : S.flops;
+    else if (k == "shard_top_flops") *out = B.world > 1 ? B.shard.top_flops : 0.0;
+    else if (k == "shard_barriers") { int c = 0; for (const LevelPlan& L : B.plan) c += L.barrier_before; *out = c; }
     else return h->fail(OPB_ERR_INVALID, "unknown info key " + k);
     return OPB_OK;
 }
@@ -803,6 +982,8 @@ int64_t opb_get_symbolic(opb_handle* h, const char* name, int64_t* out, int64_t 
     if (k == "pairA") return copy_out(B.P.pairA, out, cap);
     if (k == "pairB") return copy_out(B.P.pairB, out, cap);
     if (k == "hmap") return copy_out(B.P.hmap, out, cap);
+    if (k == "owner") { if (B.world > 1) return copy_out(B.shard.owner, out, cap); return copy_out(std::vector<int>(S.nsuper, 0), out, cap); }
+    if (k == "top") { std::vector<int> t(S.nsuper, 0); if (B.world > 1) for (int q = 0; q < S.nsuper; q++) t[q] = B.shard.top[q]; return copy_out(t, out, cap); }
     return h->fail(OPB_ERR_INVALID, "unknown symbolic array " + k);
 }
 

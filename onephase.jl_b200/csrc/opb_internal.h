@@ -36,6 +36,8 @@ struct DeltaState {
     double kkt_err[6];
 };
 
+constexpr int MAX_SHARD = 8;          // GPUs one instance can be sharded over
+
 // leading dimension of a panel / inverse block with N rows (even: 16-byte aligned columns)
 __host__ __device__ inline int ld_of(int N) { return (N + 1) & ~1; }
 
@@ -53,6 +55,34 @@ struct DevSym {
     const int* child_list;
     const int* perm;   // perm[new] = old
     const int64_t* Xoff;  // per supernode: offset of inv(L11) (c x c, ld = ld_of(c)) in Xinv, or -1
+    // ---- one instance sharded over several GPUs; owner == nullptr on a single GPU
+    const int* owner;     // per supernode: rank that owns it
+    int rank, world;
+    double* cb_peer[MAX_SHARD];   // update-block buffer of every rank (peer-mapped; [rank] = own)
+    double* u_peer[MAX_SHARD];    // forward-solve update vectors of every rank
+    double* x_peer[MAX_SHARD];    // solution vector of every rank (top supernodes are pushed to all)
+};
+
+// update block / forward update vector of child `ch`: in the owner's HBM, read over NVLink when
+// the child belongs to another rank (the reduction of the subtree roots' update blocks onto the
+// separator front happens inside the consuming extend-add, not as a separate collective)
+__device__ __forceinline__ const double* child_cb(const DevSym& S, const double* CB, int ch) {
+    return (S.owner ? S.cb_peer[S.owner[ch]] : CB) + S.CBoff[ch];
+}
+__device__ __forceinline__ const double* child_u(const DevSym& S, const double* u, int ch) {
+    return (S.owner ? S.u_peer[S.owner[ch]] : u) + S.rowptr[ch];
+}
+
+// Cross-GPU barrier state of a sharded handle: every rank owns 2 x MAX_SHARD flag words that
+// its peers write over NVLink ((epoch << 1) | fail, slot = epoch & 1) and a local epoch counter.
+struct ShardCtx {
+    int rank, world;
+    unsigned long long* flags_local;            // [2][MAX_SHARD]
+    unsigned long long* flags_peer[MAX_SHARD];  // the same array on every rank
+    unsigned long long* epoch;                  // local barrier counter
+    int* error;                                 // local: set to 1 when a wait timed out
+    long long timeout_clocks;                   // a wait gives up after this many SM clocks
+    DeltaState* state;                          // local controller state (fail bit exchanged at every barrier)
 };
 
 template <class T>
@@ -99,6 +129,10 @@ struct LevelPlan {
     // big fronts are sorted by pivot-column count (descending); outer step t of the blocked
     // factorisation touches the first step_count[t] of them
     std::vector<int> step_count, step_maxN;
+    // sharded instance: a cross-GPU barrier precedes this level (a supernode of the level has a
+    // child on another rank); push_count = top supernodes of this rank on the level, whose solution
+    // is pushed to every peer in the backward sweep
+    int barrier_before = 0, push_count = 0, push_begin = 0, push_maxc = 0;
 };
 
 // ---- kernels_assembly.cu
@@ -124,7 +158,7 @@ void launch_ctl_single(DeltaState* st_d, double delta, int mode, cudaStream_t st
 cudaError_t factor_configure();
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
-                          int outer_block, cudaStream_t st);
+                          int outer_block, const ShardCtx* shard, cudaStream_t st);
 
 // ---- kernels_dense.cu  (Cholesky of big fronts on the FP64 tensor pipe, pivot-block inverses,
 //                         multi-CTA triangular solves for big supernodes)
@@ -147,12 +181,25 @@ void launch_solve_wide_bwd(const DevSym& S, const LevelPlan& L, const int* d_sch
 void launch_ldlt_inertia(const DevSym& S, const double* Lval, const int64_t* dpos, int n,
                          DeltaState* st_d, cudaStream_t st);
 
+// every translation unit: load its kernels now instead of at first launch
+cudaError_t preload_assembly();
+cudaError_t preload_vec();
+cudaError_t preload_solve();
+cudaError_t preload_factor();
+cudaError_t preload_dense();
+cudaError_t preload_shard();
+
+// ---- kernels_shard.cu  (cross-GPU barrier over peer-mapped flags, solution pushes)
+void launch_shard_barrier(const ShardCtx& C, cudaStream_t st);
+void launch_push_supernodes(const DevSym& S, const int* list, int count, int maxc, const double* x, cudaStream_t st);
+void launch_push_owned(const DevSym& S, const int* colowner, const double* x, cudaStream_t st);
+
 // ---- kernels_solve.cu
 cudaError_t solve_configure();
 // x (permuted order, length n) is overwritten with the solution; u = workspace (len rowidx)
 void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                   const double* Lval, const double* Xinv, double* x, double* xnew, double* u, int mode,
-                  cudaStream_t st);
+                  const ShardCtx* shard, const int* colowner, cudaStream_t st);
 void launch_permute_in(const double* b, const int* perm, double* x, int n, cudaStream_t st);
 void launch_permute_out_add(const double* x, const int* perm, double* dst, int n, int accumulate, cudaStream_t st);
 

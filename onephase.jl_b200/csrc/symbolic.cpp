@@ -816,4 +816,88 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
     return true;
 }
 
+void shard_map(const Symbolic& S, int world, ShardMap& out) {
+    const int NS = S.nsuper;
+    out = ShardMap();
+    out.world = std::max(1, world);
+    out.owner.assign(NS, 0);
+    out.top.assign(NS, 0);
+    out.level_barrier.assign(std::max(1, S.nlevels), 0);
+    out.load.assign(out.world, 0.0);
+    // factorisation flops of every supernode and of the subtree below it (children have smaller
+    // indices: the supernodes are numbered in postorder)
+    std::vector<double> w(NS), W(NS);
+    std::vector<int> fd(NS);             // first descendant: subtree(s) = [fd[s], s]
+    for (int s = 0; s < NS; s++) {
+        const double c = S.sfirst[s + 1] - S.sfirst[s], N = c + (double)(S.rowptr[s + 1] - S.rowptr[s]);
+        // sum_{j<c} (N-j)^2
+        w[s] = c * N * N - N * c * (c - 1) + (c - 1) * c * (2 * c - 1) / 6.0;
+        W[s] = w[s];
+        fd[s] = s;
+    }
+    for (int s = 0; s < NS; s++) {
+        const int p = S.sparent[s];
+        if (p >= 0) { W[p] += W[s]; fd[p] = std::min(fd[p], fd[s]); }
+    }
+    if (out.world > 1) {
+        double total_all = 0;
+        struct Task { std::vector<int> roots; int a, b; };
+        std::vector<Task> stack;
+        {
+            Task t; t.a = 0; t.b = out.world;
+            for (int s = 0; s < NS; s++) if (S.sparent[s] < 0) { t.roots.push_back(s); total_all += W[s]; }
+            stack.push_back(std::move(t));
+        }
+        int expansions = 0;
+        const int max_expansions = 64 * out.world;
+        while (!stack.empty()) {
+            Task T = std::move(stack.back());
+            stack.pop_back();
+            if (T.b - T.a == 1) {
+                for (int r : T.roots) for (int s = fd[r]; s <= r; s++) out.owner[s] = T.a;
+                continue;
+            }
+            const int mid = T.a + (T.b - T.a) / 2;
+            const double f1 = (double)(mid - T.a) / (T.b - T.a), f2 = 1.0 - f1;
+            std::vector<int> bin1, bin2;
+            for (;;) {
+                std::sort(T.roots.begin(), T.roots.end(), [&](int x, int y) { return W[x] != W[y] ? W[x] > W[y] : x < y; });
+                double total = 0, l1 = 0, l2 = 0;
+                for (int r : T.roots) total += W[r];
+                bin1.clear(); bin2.clear();
+                for (int r : T.roots) {
+                    if (l1 / f1 <= l2 / f2) { bin1.push_back(r); l1 += W[r]; } else { bin2.push_back(r); l2 += W[r]; }
+                }
+                const bool splittable = T.roots.size() >= 2;
+                const double imbalance = total > 0 ? std::max(l1 / f1, l2 / f2) / total : 1.0;
+                if (splittable && imbalance <= 1.10) break;
+                // expand the heaviest root that still has children
+                int pick = -1;
+                for (size_t k = 0; k < T.roots.size(); k++) {
+                    const int r = T.roots[k];
+                    if (S.child_ptr[r + 1] > S.child_ptr[r]) { pick = (int)k; break; }
+                }
+                if (pick < 0 || expansions >= max_expansions || W[T.roots[pick]] < 1e-3 * total_all) break;
+                const int hnode = T.roots[pick];
+                expansions++;
+                out.owner[hnode] = T.a;
+                out.top[hnode] = 1;
+                T.roots.erase(T.roots.begin() + pick);
+                for (int k = S.child_ptr[hnode]; k < S.child_ptr[hnode + 1]; k++) T.roots.push_back(S.child_list[k]);
+            }
+            Task t1, t2;
+            t1.a = T.a; t1.b = mid; t1.roots = std::move(bin1);
+            t2.a = mid; t2.b = T.b; t2.roots = std::move(bin2);
+            stack.push_back(std::move(t1));
+            stack.push_back(std::move(t2));
+        }
+    }
+    for (int s = 0; s < NS; s++) {
+        out.load[out.owner[s]] += w[s];
+        if (out.top[s]) out.top_flops += w[s];
+        const int p = S.sparent[s];
+        if (p >= 0 && out.owner[p] != out.owner[s]) out.level_barrier[S.level[p]] = 1;
+    }
+}
+
 }  // namespace opb

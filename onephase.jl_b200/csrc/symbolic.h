@@ -84,6 +84,21 @@ bool build_csc_pattern(int64_t n, const int64_t* Ap, const int64_t* Ai, int inde
 bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
              const SymOptions& opt, const int64_t* user_perm, Symbolic& S);
 
+// Mapping of the supernodal elimination tree onto `world` GPUs: proportional
+// ("subtree-to-subcube") mapping by factorisation flops.  A rank range that cannot be split
+// evenly over the current subtree roots expands its heaviest root: that supernode becomes a
+// `top` supernode (it has descendants on other ranks) owned by the first rank of the range, and
+// its children become roots.  Everything below the final roots is private to one rank.
+struct ShardMap {
+    int world = 1;
+    std::vector<int> owner;              // per supernode: rank that factorises and solves it
+    std::vector<char> top;               // per supernode: descendants live on more than one rank
+    std::vector<char> level_barrier;     // per level: some supernode of the level has a child on another rank
+    std::vector<double> load;            // per rank: flops of the supernodes it owns
+    double top_flops = 0;                // flops of the top supernodes
+};
+void shard_map(const Symbolic& S, int world, ShardMap& out);
+
 uint64_t pattern_hash(int64_t n, const int64_t* p, const int64_t* i, int64_t nnz);
 
 }  // namespace opb

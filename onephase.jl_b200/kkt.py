@@ -179,7 +179,11 @@ class Schur_B200_KKT_solver:
     """Drop-in for Schur_KKT_solver (schur.jl:3-31).  The matrix Q, its factor and
     the cached (J, H, y, s) of factor_it live in HBM behind one opb handle."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, shard=None):
+        """shard: None, or an object with `rank`, `world` and `exchange(bytes) -> list[bytes]`
+        (ThreadShard / DistShard below): ONE instance is then factorised and solved by `world`
+        GPUs, every rank calling the same methods with the same data."""
+        self.shard = shard
         self.ls_solver = None
         self.factor_it = None
         self.delta_x_vec = None
@@ -206,6 +210,8 @@ class Schur_B200_KKT_solver:
     def initialize(self, initial_it):
         if self._h is None:
             self._h = _lib.Handle(self.device)
+            if self.shard is not None and self.shard.world > 1:
+                self._h.shard_init(self.shard.rank, self.shard.world)
         self.dir = Class_point(np.zeros(dim(initial_it)), np.zeros(ncon(initial_it)), np.zeros(ncon(initial_it)))
 
     def finalize(self):
@@ -229,6 +235,7 @@ class Schur_B200_KKT_solver:
             if key != self._pattern_key:
                 # pattern changed (Class_cutest.jl:490-502 can drop numerical zeros): new symbolic analysis
                 self._h.set_structure(J.shape[1], J.shape[0], J.indptr, J.indices, H.indptr, H.indices, 0)
+                self._attach_peers()
                 self._pattern_key = key
             self._pattern_ident = ident
             self._pattern_refs = (J.indptr, J.indices, H.indptr, H.indices)   # keep the ids alive
@@ -236,6 +243,22 @@ class Schur_B200_KKT_solver:
         self.factor_it = it
         self.Q = None
         self.ready = "system_formed"
+
+    def _attach_peers(self):
+        """Sharded instance: after every symbolic analysis the ranks exchange the CUDA IPC
+        descriptors of their peer-visible buffers and map each other's memory."""
+        if self.shard is None or self.shard.world <= 1:
+            return
+        import hashlib
+        # every rank must have derived the same ordering and the same supernode-to-rank map
+        sig = hashlib.md5(self._h.symbolic("perm").tobytes() + self._h.symbolic("owner").tobytes()).digest()
+        blobs = self.shard.exchange(self._h.shard_export() + sig)
+        for p, b in enumerate(blobs):
+            if b[_lib.SHARD_BLOB_BYTES:] != sig:
+                raise RuntimeError("sharded instance: rank %d derived a different symbolic analysis" % p)
+            if p != self.shard.rank:
+                self._h.shard_attach(p, b[:_lib.SHARD_BLOB_BYTES])
+        self.shard.exchange(b"ok")            # nobody launches before every rank has attached
 
     def get_Q(self):
         """Lower triangle of Q with the current shift, as scipy CSC (for is_diag_dom)."""
@@ -332,13 +355,54 @@ def ipopt_strategy(it, kkt_solver, pars, timer=None):
     raise RuntimeError("max it")                         # delta_strategy.jl:113
 
 
-def pick_KKT_solver(pars):
+class DistShard:
+    """Rank bookkeeping of a sharded instance over torch.distributed (one process per GPU).
+    Only the IPC descriptors travel through the process group; the numeric data moves between
+    the GPUs inside the kernels (peer-mapped HBM over NVLink)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self._dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def exchange(self, blob):
+        out = [None] * self.world
+        self._dist.all_gather_object(out, blob, group=self.group)
+        return out
+
+
+class ThreadShard:
+    """The same bookkeeping for `world` host threads of ONE process, each driving its own handle
+    (used by the single-GPU tests: several virtual ranks on one device)."""
+
+    class _Hub:
+        def __init__(self, world):
+            import threading
+            self.world, self.slots, self.barrier = world, [None] * world, threading.Barrier(world)
+
+    def __init__(self, hub, rank):
+        self.hub, self.rank, self.world = hub, rank, hub.world
+
+    @classmethod
+    def make(cls, world):
+        hub = cls._Hub(world)
+        return [cls(hub, r) for r in range(world)]
+
+    def exchange(self, blob):
+        self.hub.slots[self.rank] = blob
+        self.hub.barrier.wait()
+        out = list(self.hub.slots)
+        self.hub.barrier.wait()
+        return out
+
+
+def pick_KKT_solver(pars, shard=None):
     """kkt_system_solver.jl:232-287 extended with the B200 symbols."""
     t, ls = pars.kkt.kkt_solver_type, pars.kkt.linear_solver_type
     if t == "schur_b200":
         if ls != "b200":
             raise ValueError("pick a valid solver!")
-        k = Schur_B200_KKT_solver(pars.device)
+        k = Schur_B200_KKT_solver(pars.device, shard)
         k.ls_solver = linear_solver_B200("definite", pars.kkt.linear_solver_safe_mode,
                                          pars.kkt.linear_solver_recycle, pars.device)
     else:
