@@ -939,62 +939,106 @@ wide_bwd_gather_kernel(DevSym S, const int* __restrict__ list, const double* __r
 }
 
 // xnew[k] = xs[k] - sum_{i >= b1} L[i,k] * f[i]  for the columns k of block blk, where f is the
-// final solution on the later pivot rows and the ancestors' values on the rows >= c
+// final solution on the later pivot rows and the ancestors' values on the rows >= c.
+// WPC warps share one column (interleaved 128-row chunks, partial sums combined in shared memory
+// in a fixed order): a warp per column of a few tall fronts leaves most SMs idle.  Fronts with
+// N >= TALL_N take the 4-warp variant, the others the 1-warp variant.
+constexpr int TALL_N = 8192;
+template <int WPC>
 __global__ void __launch_bounds__(WT)
 wide_bwd_upd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lval,
                     const double* __restrict__ x, double* __restrict__ xnew, const double* __restrict__ u, int blk) {
+    __shared__ double red[KG];
     const Front d = get_front(S, list[blockIdx.y]);
+    if ((d.N >= TALL_N) != (WPC > 1)) return;     // the other variant's front (fixed per front: reproducible)
     const int b0 = blk * XB;
     const int b1 = min(d.c, b0 + XB);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int k = b0 + blockIdx.x * KG + w;
-    if (k >= b1) return;
-    const double* col = Lval + d.loff + (size_t)k * d.ld;
-    const double* xs = x + d.first;
-    const double* us = u + S.rowptr[d.s];
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    // later pivot rows [b1, c)
-    int i = b1 + lane;
-    for (; i + 96 < d.c; i += 128) {
-        a0 += col[i] * xs[i]; a1 += col[i + 32] * xs[i + 32];
-        a2 += col[i + 64] * xs[i + 64]; a3 += col[i + 96] * xs[i + 96];
+    const int part = w % WPC;
+    const int k = b0 + blockIdx.x * (KG / WPC) + w / WPC;
+    const bool valid = k < b1;
+    double acc = 0.0;
+    if (valid) {
+        const double* col = Lval + d.loff + (size_t)k * d.ld;
+        const double* xs = x + d.first;
+        const double* us = u + S.rowptr[d.s];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        // later pivot rows [b1, c): groups of 128 rows dealt round-robin to the WPC warps
+        int base = b1 + 128 * part;
+        for (; base + 128 <= d.c; base += 128 * WPC) {
+            const int i = base + lane;
+            a0 += col[i] * xs[i]; a1 += col[i + 32] * xs[i + 32];
+            a2 += col[i + 64] * xs[i + 64]; a3 += col[i + 96] * xs[i + 96];
+        }
+        for (int i = base + lane; i < d.c && i < base + 128; i += 32) a0 += col[i] * xs[i];
+        // rows below the pivot block
+        const double* colr = col + d.c;
+        base = 128 * part;
+        for (; base + 128 <= d.r; base += 128 * WPC) {
+            const int t = base + lane;
+            a0 += colr[t] * us[t]; a1 += colr[t + 32] * us[t + 32];
+            a2 += colr[t + 64] * us[t + 64]; a3 += colr[t + 96] * us[t + 96];
+        }
+        for (int t = base + lane; t < d.r && t < base + 128; t += 32) a0 += colr[t] * us[t];
+        acc = (a0 + a1) + (a2 + a3);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     }
-    for (; i < d.c; i += 32) a0 += col[i] * xs[i];
-    // rows below the pivot block
-    const double* colr = col + d.c;
-    int t = lane;
-    for (; t + 96 < d.r; t += 128) {
-        a0 += colr[t] * us[t]; a1 += colr[t + 32] * us[t + 32];
-        a2 += colr[t + 64] * us[t + 64]; a3 += colr[t + 96] * us[t + 96];
+    if (WPC == 1) {
+        if (valid && lane == 0) xnew[d.first + k] = x[d.first + k] - acc;
+        return;
     }
-    for (; t < d.r; t += 32) a0 += colr[t] * us[t];
-    double acc = (a0 + a1) + (a2 + a3);
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) xnew[d.first + k] = xs[k] - acc;
+    if (lane == 0) red[w] = acc;
+    __syncthreads();
+    if (valid && part == 0 && lane == 0) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < WPC; q++) v += red[w + q];
+        xnew[d.first + k] = x[d.first + k] - v;
+    }
 }
 
 // xs[k] = sum_{i in [k, b1)} X[i,k] * xnew[i]  for the columns k of block blk
+template <int WPC>
 __global__ void __launch_bounds__(WT)
 wide_bwd_tri_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Xinv,
                     double* __restrict__ x, const double* __restrict__ xnew, int blk) {
+    __shared__ double red[KG];
     const Front d = get_front(S, list[blockIdx.y]);
+    if ((d.N >= TALL_N) != (WPC > 1)) return;     // the other variant's front (fixed per front: reproducible)
     const int b0 = blk * XB;
     const int b1 = min(d.c, b0 + XB);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int k = b0 + blockIdx.x * KG + w;
-    if (k >= b1) return;
-    const double* col = Xinv + d.xoff + (size_t)k * d.ldx;
-    const double* xn = xnew + d.first;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int i = (k & ~31) + lane;      // aligned start; entries above the diagonal are zero
-    for (; i + 96 < b1; i += 128) {
-        a0 += col[i] * xn[i]; a1 += col[i + 32] * xn[i + 32];
-        a2 += col[i + 64] * xn[i + 64]; a3 += col[i + 96] * xn[i + 96];
+    const int part = w % WPC;
+    const int k = b0 + blockIdx.x * (KG / WPC) + w / WPC;
+    const bool valid = k < b1;
+    double acc = 0.0;
+    if (valid) {
+        const double* col = Xinv + d.xoff + (size_t)k * d.ldx;
+        const double* xn = xnew + d.first;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const int i0 = (k & ~31);            // aligned start; entries above the diagonal are zero
+        int base = i0 + 128 * part;
+        for (; base + 128 <= b1; base += 128 * WPC) {
+            const int i = base + lane;
+            a0 += col[i] * xn[i]; a1 += col[i + 32] * xn[i + 32];
+            a2 += col[i + 64] * xn[i + 64]; a3 += col[i + 96] * xn[i + 96];
+        }
+        for (int i = base + lane; i < b1 && i < base + 128; i += 32) a0 += col[i] * xn[i];
+        acc = (a0 + a1) + (a2 + a3);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     }
-    for (; i < b1; i += 32) a0 += col[i] * xn[i];
-    double acc = (a0 + a1) + (a2 + a3);
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) x[d.first + k] = acc;
+    if (WPC == 1) {
+        if (valid && lane == 0) x[d.first + k] = acc;
+        return;
+    }
+    if (lane == 0) red[w] = acc;
+    __syncthreads();
+    if (valid && part == 0 && lane == 0) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < WPC; q++) v += red[w + q];
+        x[d.first + k] = v;
+    }
 }
 
 inline size_t diag_smem() { return (size_t)(LDD * WB + INVBUF + XS_BLOCKS * INVBUF) * sizeof(double); }
@@ -1119,10 +1163,19 @@ void launch_solve_wide_bwd(const DevSym& S, const LevelPlan& L, const int* d_sch
     const int nblk = (L.maxC[FC_BIG] + XB - 1) / XB;
     for (int blk = nblk - 1; blk >= 0; blk--) {
         const int cb = std::min(XB, L.maxC[FC_BIG] - blk * XB);
-        dim3 g1((cb + KG - 1) / KG, cnt);
-        wide_bwd_upd_kernel<<<g1, WT, 0, st>>>(S, list, Lval, x, xnew, u, blk);
-        wide_bwd_tri_kernel<<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
-        count_launch(2);
+        if (L.maxN[FC_BIG] >= TALL_N) {
+            constexpr int WPC = 4;
+            dim3 g1((cb + KG / WPC - 1) / (KG / WPC), cnt);
+            wide_bwd_upd_kernel<WPC><<<g1, WT, 0, st>>>(S, list, Lval, x, xnew, u, blk);
+            wide_bwd_tri_kernel<WPC><<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
+            count_launch(2);
+        }
+        if (L.minN[FC_BIG] < TALL_N) {
+            dim3 g1((cb + KG - 1) / KG, cnt);
+            wide_bwd_upd_kernel<1><<<g1, WT, 0, st>>>(S, list, Lval, x, xnew, u, blk);
+            wide_bwd_tri_kernel<1><<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
+            count_launch(2);
+        }
     }
 }
 
@@ -1139,8 +1192,10 @@ cudaError_t preload_dense() {
     e = cudaFuncGetAttributes(&a, mid_panel_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, trtri_merge_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_bwd_gather_kernel); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, wide_bwd_tri_kernel); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, wide_bwd_upd_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_bwd_tri_kernel<1>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_bwd_tri_kernel<4>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_bwd_upd_kernel<1>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_bwd_upd_kernel<4>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_fwd_gather_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_fwd_tri_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_fwd_upd_kernel); if (e != cudaSuccess) return e;

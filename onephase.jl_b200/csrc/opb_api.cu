@@ -93,6 +93,7 @@ static void build_plan(Bundle& B) {
             else fc = FC_BIG;
             cls[fc].push_back(s);
             L.maxN[fc] = std::max(L.maxN[fc], N);
+            L.minN[fc] = std::min(L.minN[fc], N);
             L.maxC[fc] = std::max(L.maxC[fc], c);
             L.maxPanel[fc] = std::max(L.maxPanel[fc], N * std::min(c, WB));
             if (fc >= FC_MID) {

@@ -122,6 +122,7 @@ constexpr int XB = 2048;              // pivot blocks are inverted in diagonal b
 // Per-level schedule built on the host from Symbolic.
 struct LevelPlan {
     int begin[NFC] = {0}, count[NFC] = {0}, maxN[NFC] = {0}, maxC[NFC] = {0}, maxPanel[NFC] = {0};
+    int minN[NFC] = {1 << 30, 1 << 30, 1 << 30, 1 << 30, 1 << 30, 1 << 30, 1 << 30};
     int all_begin = 0, all_count = 0;          // every supernode of the level
     int solo_count = 0;                        // classes T32 .. S152 (a prefix of the level)
     int wide_begin = 0, wide_count = 0;        // classes MID .. BIG (the rest)

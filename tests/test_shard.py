@@ -161,9 +161,10 @@ def test_virtual_ranks_delta_loop_failure_is_seen_by_every_rank():
     # indefinite Hessian: attempts fail on SOME rank (near the accepted delta only in the top
     # separator); every rank must take the same delta decisions (fail bit exchanged at the
     # barriers) and end with the same factor
-    rep = _case("chain", 2, "nh=300", "neg_curv=50.0")
-    assert rep["ref"][0][1] > 1 and rep["ref"][0][2] > 0
-    _case("chain", 3, "nh=300", "neg_curv=50.0", "--delta-prev", "1e-3")
+    # (offdiag_curv: negative curvature the diagonal test of the delta rule cannot see -> x8 retries)
+    rep = _case("chain", 2, "nh=300", "offdiag_curv=5.0")
+    assert rep["ref"][0][1] > 3 and rep["ref"][0][2] > 0
+    _case("chain", 3, "nh=300", "offdiag_curv=5.0", "--delta-prev", "1e-3")
 
 
 @pytest.mark.gpu
@@ -187,10 +188,10 @@ def _mp_worker(rank, world, port, out):
     try:
         pkg = g.package()
         report = []
-        for gen, kw, neg in (("chain", dict(nh=300), 0.0), ("chain", dict(nh=300), 50.0),
+        for gen, kw, neg in (("chain", dict(nh=300), 0.0), ("chain", dict(nh=300), 5.0),
                              ("sparse_qp", dict(n=20000, m_gen=10000), None), ("pde_control", dict(N=20), None)):
             prob = getattr(pkg.problems, gen)(seed=2, **kw) if neg is None else \
-                getattr(pkg.problems, gen)(seed=2, neg_curv=neg, **kw)
+                getattr(pkg.problems, gen)(seed=2, offdiag_curv=neg, **kw)
             pars = pkg.Class_parameters(device=rank)
 
             def solve(shard):
