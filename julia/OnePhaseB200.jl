@@ -111,10 +111,13 @@ mutable struct Schur_B200_KKT_solver <: abstract_schur_solver
     _pattern::UInt64
     _delta::Float64
     _diag_min::Float64
+    _shard_rank::Int                       # one instance over several GPUs (shard_init!); world 1 = off
+    _shard_world::Int
     function Schur_B200_KKT_solver()
         this = new()
         this.ready = :not_ready
         this._h = nothing; this._pattern = 0; this._delta = 0.0; this._diag_min = NaN
+        this._shard_rank = 0; this._shard_world = 1
         return this
     end
 end
@@ -203,3 +206,29 @@ end
 #     my_kkt_solver = Schur_B200_KKT_solver()
 #     linear_solver_type == :b200 || error("pick a valid solver!")
 #     my_kkt_solver.ls_solver = linear_solver_B200(:definite, safe, recycle)
+
+# ---------------------------------------------------------------------------------------------
+# One instance over several GPUs (include/onephase_b200.h, opb_shard_*): one Julia process per GPU,
+# every process making the same calls with the same data.  `allgather(blob)::Vector{Vector{UInt8}}`
+# is any transport the host program has (MPI.Allgather, Distributed.jl, a file): only these 320
+# bytes per rank travel through it, the numeric data moves between the GPUs inside the kernels.
+#   shard_init!(kkt_solver, rank, world)        before the first form_system!
+#   shard_attach!(kkt_solver, allgather)        after every opb_set_structure (form_system! calls it)
+function shard_init!(kkt_solver::Schur_B200_KKT_solver, rank::Integer, world::Integer)
+    opb_check(kkt_solver._h, ccall((:opb_shard_init, LIBOPB), Cint, (Ptr{Cvoid}, Cint, Cint),
+                                   kkt_solver._h.ptr, rank, world))
+    kkt_solver._shard_rank = rank; kkt_solver._shard_world = world
+end
+
+function shard_attach!(kkt_solver::Schur_B200_KKT_solver, allgather::Function)
+    blob = Vector{UInt8}(undef, 320)
+    opb_check(kkt_solver._h, ccall((:opb_shard_export, LIBOPB), Cint, (Ptr{Cvoid}, Ptr{UInt8}),
+                                   kkt_solver._h.ptr, blob))
+    blobs = allgather(blob)
+    for p in 0:(kkt_solver._shard_world - 1)
+        p == kkt_solver._shard_rank && continue
+        opb_check(kkt_solver._h, ccall((:opb_shard_attach, LIBOPB), Cint, (Ptr{Cvoid}, Cint, Ptr{UInt8}),
+                                       kkt_solver._h.ptr, p, blobs[p + 1]))
+    end
+    allgather(UInt8[1])          # nobody launches before every rank has attached
+end

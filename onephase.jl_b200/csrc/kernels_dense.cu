@@ -616,10 +616,10 @@ chol_trsm_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
 
 // right-looking update of PANEL columns [cbeg, min(cend, c)) with the finished columns
 // [k0, k0+klen):  L[i,k] -= sum_p L[i,p] L[k,p]   (i >= k).
-// Two-level blocking: after every WB-wide block only the columns up to the end of the enclosing
-// outer block are updated (klen = WB); the columns beyond it get ONE rank-`outer` update when the
-// outer block is complete (klen = outer), so the bulk of the panel flops runs with a long K loop
-// and the panel is read-modify-written c/outer instead of c/WB times.
+// Called in a recursive (binary) schedule, see launch_wide_chol_level: inside an outer block the
+// last 2^j finished blocks update the next 2^j blocks (klen = 128 * 2^j), and a complete outer
+// block updates all remaining columns at once (klen = outer), so the bulk of the panel flops runs
+// with a long K loop and the panel is read-modify-written c/outer instead of c/WB times.
 // cbeg and k0 are multiples of WB.  (The update block of the front is formed once, at the end,
 // by front_cb_kernel.)
 __global__ void __launch_bounds__(GEMM_THREADS)
@@ -1062,7 +1062,8 @@ cudaError_t dense_configure() {
 }
 
 void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
-                            double* CB, double* Xinv, DeltaState* st_d, int outer_block, cudaStream_t st) {
+                            double* CB, double* Xinv, DeltaState* st_d, int outer_block, const SideStream* side,
+                            cudaStream_t st) {
     if (!L.wide_count) return;
     // medium fronts: panel in shared memory
     for (int fc = FC_MID; fc <= FC_MIDL; fc++) {
@@ -1076,22 +1077,25 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
         dim3 gea((L.maxN[FC_BIG] + EAP_RB - 1) / EAP_RB, L.count[FC_BIG]);
         big_extend_add_panel_kernel<<<gea, 256, 0, st>>>(S, list, Lval, CB, st_d);
         count_launch();
-        const int sub = std::max(1, outer_block / WB);          // WB blocks per outer block
+        int sub = 1;                                            // WB blocks per outer block (power of two)
+        while (sub * 2 * WB <= outer_block) sub *= 2;
         const int nsteps = (int)L.step_count.size();
-        auto update = [&](int k0, int klen, int cbeg, int cend) {
+        auto update = [&](cudaStream_t sx, int k0, int klen, int cbeg, int cend) -> bool {
             // fronts with panel columns beyond cbeg: a prefix of the list (sorted by c descending)
             const int tb = cbeg / WB;
-            if (tb >= nsteps || L.step_count[tb] <= 0) return;
+            if (cend <= cbeg || tb >= nsteps || L.step_count[tb] <= 0) return false;
             const int cnt2 = L.step_count[tb];
             const int nrow = (L.step_maxN[tb] - cbeg + BM - 1) / BM;
             const int ncol = (std::min(cend, L.maxC[FC_BIG]) - cbeg + BN - 1) / BN;
             long long tiles = 0;
             for (int J = 0; J < ncol && J < nrow; J++) tiles += nrow - J;
-            if (tiles <= 0) return;
+            if (tiles <= 0) return false;
             dim3 gu((unsigned)tiles, cnt2);
-            chol_panel_update_kernel<<<gu, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, list, Lval, k0, klen, cbeg, cend, st_d);
+            chol_panel_update_kernel<<<gu, GEMM_THREADS, sizeof(GemmSmem), sx>>>(S, list, Lval, k0, klen, cbeg, cend, st_d);
             count_launch();
+            return true;
         };
+        bool pending_join = false;       // an update is still running on the side stream
         for (int t = 0; t < nsteps; t++) {
             const int cnt = L.step_count[t];
             if (cnt <= 0) break;
@@ -1104,10 +1108,35 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
             dim3 gt(nrow, cnt);
             chol_trsm_kernel<<<gt, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, list, Lval, Xinv, t, st_d);
             count_launch();
-            const int ob_end = (t / sub + 1) * sub * WB;        // first column after the enclosing outer block
-            if ((t + 1) * WB < ob_end) update(t * WB, WB, (t + 1) * WB, ob_end);
-            else update((t / sub) * sub * WB, sub * WB, ob_end, 1 << 30);
+            // Recursive (binary) schedule of the right-looking updates: with tb blocks finished and
+            // 2^j the largest power of two dividing tb, the last 2^j blocks update the next 2^j
+            // blocks (K = 128 * 2^j); when 2^j reaches the outer block they update ALL remaining
+            // columns instead.  Every block column has received exactly the blocks before it when
+            // its turn comes, half of the flops inside an outer block run at K = outer/2, a
+            // quarter at outer/4, ..., and the panel is read-modify-written c/outer times.
+            const int tb = t + 1;
+            const int wblk = tb & -tb;
+            int k0, klen, cend;
+            const int cbeg = tb * WB;
+            if (wblk >= sub) { k0 = (tb - sub) * WB; klen = sub * WB; cend = 1 << 30; }
+            else { k0 = (tb - wblk) * WB; klen = wblk * WB; cend = (tb + wblk) * WB; }
+            // the previous step's side update wrote the columns this step updates
+            if (pending_join) { cudaStreamWaitEvent(st, side->join, 0); pending_join = false; }
+            const bool has_rest = cend > cbeg + WB && tb + 1 < nsteps && L.step_count[tb + 1] > 0;
+            if (side && has_rest) {
+                // look-ahead: block column tb (all the next diagonal block and TRSM need) on the main
+                // stream, the columns beyond it on the side stream, concurrently with those kernels
+                cudaEventRecord(side->fork, st);
+                cudaStreamWaitEvent(side->stream, side->fork, 0);
+                update(side->stream, k0, klen, cbeg + WB, cend);
+                cudaEventRecord(side->join, side->stream);      // always rejoin (stream capture demands it)
+                pending_join = true;
+                update(st, k0, klen, cbeg, cbeg + WB);
+            } else {
+                update(st, k0, klen, cbeg, cend);
+            }
         }
+        if (pending_join) cudaStreamWaitEvent(st, side->join, 0);
     }
     // update blocks of all medium and big fronts, written once
     {

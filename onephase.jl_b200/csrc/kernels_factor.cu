@@ -361,7 +361,7 @@ cudaError_t factor_configure() {
 
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
-                          int outer_block, const ShardCtx* shard, cudaStream_t st) {
+                          int outer_block, const ShardCtx* shard, const SideStream* side, cudaStream_t st) {
     for (const LevelPlan& L : plan) {
         // sharded instance: the update blocks of children on other ranks must be complete
         if (shard && L.barrier_before) launch_shard_barrier(*shard, st);
@@ -379,7 +379,7 @@ void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, c
         if (!L.wide_count) continue;
         if (mode == 0) {
             // Cholesky: panels in shared memory / blocked on the FP64 tensor pipe (kernels_dense.cu)
-            launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, outer_block, st);
+            launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, outer_block, side, st);
             continue;
         }
         // LDL' fallback: scalar blocked path over every front that does not fit in shared memory

@@ -210,6 +210,9 @@ struct opb_handle {
         peer_ok[p] = false; peer_blob[p].clear();
     }
 
+    SideStream side;                     // look-ahead stream of the blocked panel factorisation
+    bool lookahead = true;
+
     int fail(int code, const std::string& msg) { err = msg; return code; }
     int cuda_fail(cudaError_t e, const char* where) {
         err = std::string(where) + ": " + cudaGetErrorString(e);
@@ -280,6 +283,10 @@ int opb_create(opb_handle** out, int device_id, unsigned flags) {
         if (e != cudaSuccess) return h->cuda_fail(e, "dense_configure (is this an sm_100a device?)");
         e = h->red.alloc(8);
         if (e != cudaSuccess) return h->cuda_fail(e, "cudaMalloc(red)");
+        e = cudaStreamCreateWithFlags(&h->side.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.join, cudaEventDisableTiming);
+        if (e != cudaSuccess) return h->cuda_fail(e, "side stream");
         for (auto pre : {preload_assembly, preload_vec, preload_solve, preload_factor, preload_dense, preload_shard}) {
             e = pre();
             if (e != cudaSuccess) return h->cuda_fail(e, "kernel preload (is this an sm_100a device?)");
@@ -301,6 +308,9 @@ int opb_destroy(opb_handle* h) {
         h->red.release();
         h->drop_graphs();
         for (int p = 0; p < MAX_SHARD; p++) h->close_peer(p);
+        if (h->side.stream) { cudaStreamSynchronize(h->side.stream); cudaStreamDestroy(h->side.stream); }
+        if (h->side.fork) cudaEventDestroy(h->side.fork);
+        if (h->side.join) cudaEventDestroy(h->side.join);
         if (h->d_flags) cudaFree(h->d_flags);
         if (h->d_state_raw) cudaFree(h->d_state_raw);
         if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -332,6 +342,7 @@ int opb_set_option(opb_handle* h, const char* key, double v) {
     else if (k == "attempts_per_sync") h->attempts_per_sync = std::max(1, (int)v);
     else if (k == "outer_block") { h->outer_block = std::max(WB, ((int)v / WB) * WB); h->drop_graphs(); }
     else if (k == "barrier_timeout_s") { h->barrier_timeout_s = v; h->sctx.timeout_clocks = (long long)(v * 2.0e9); h->drop_graphs(); }
+    else if (k == "lookahead") { h->lookahead = v != 0; h->drop_graphs(); }
     else if (k == "graphs") { h->use_graphs = v != 0; h->drop_graphs(); }
     else return h->fail(OPB_ERR_INVALID, "unknown option " + k);
     return OPB_OK;
@@ -621,7 +632,7 @@ static void enqueue_attempt_raw(opb_handle* h) {
     launch_scatter_fronts(h->Mval.p, B.d_amap.p, B.d_dpos.p, h->sdiag.p, h->Lval.p, B.S.nnzL,
                           B.Mp[B.S.n], B.S.n, h->d_state, 1, st);
     launch_factor_levels(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->Xinv.p, h->d_state, h->mode,
-                         h->outer_block, h->shard_ctx(), st);
+                         h->outer_block, h->shard_ctx(), h->lookahead ? &h->side : nullptr, st);
     if (h->mode == OPB_MODE_CHOLESKY && B.trtri.count)
         launch_trtri(h->dev, B.trtri, B.d_sched.p, h->Lval.p, h->Xinv.p, h->Twork.p, h->d_state, st);
     // sharded: every rank learns about a failed pivot anywhere before the delta rule is applied

@@ -116,7 +116,7 @@ constexpr int MID_PANEL = 12000;      // doubles
 constexpr int MIDL_PANEL = 26000;     // doubles
 constexpr int NB = 32;                // block-column width of the LDL' big-front path
 constexpr int WB = 128;               // block width of the Cholesky big-front path (DMMA)
-constexpr int OUTER_BLOCK = 1024;     // default outer block of the two-level panel update (multiple of WB)
+constexpr int OUTER_BLOCK = 2048;     // default outer block of the panel update (WB times a power of two)
 constexpr int XB = 2048;              // pivot blocks are inverted in diagonal blocks of this many columns
 
 // Per-level schedule built on the host from Symbolic.
@@ -155,11 +155,19 @@ void launch_ctl_init(DeltaState* st_d, double delta_prev, double delta_zero, dou
                      int mode, cudaStream_t st);
 void launch_ctl_single(DeltaState* st_d, double delta, int mode, cudaStream_t st);
 
+// Second stream of a handle: the part of a panel update that does not touch the next block
+// column runs there, concurrently with the (latency-bound) diagonal-block and TRSM kernels of
+// the next step.  Fork / join through the two events (also while the main stream is captured).
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+
 // ---- kernels_factor.cu
 cudaError_t factor_configure();
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
-                          int outer_block, const ShardCtx* shard, cudaStream_t st);
+                          int outer_block, const ShardCtx* shard, const SideStream* side, cudaStream_t st);
 
 // ---- kernels_dense.cu  (Cholesky of big fronts on the FP64 tensor pipe, pivot-block inverses,
 //                         multi-CTA triangular solves for big supernodes)
@@ -172,7 +180,8 @@ struct TrtriPlan {
 cudaError_t dense_configure();
 // medium + big fronts of one level (Cholesky)
 void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
-                            double* CB, double* Xinv, DeltaState* st_d, int outer_block, cudaStream_t st);
+                            double* CB, double* Xinv, DeltaState* st_d, int outer_block, const SideStream* side,
+                            cudaStream_t st);
 void launch_trtri(const DevSym& S, const TrtriPlan& T, const int* d_sched, const double* Lval,
                   double* Xinv, double* Twork, const DeltaState* st_d, cudaStream_t st);
 void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
