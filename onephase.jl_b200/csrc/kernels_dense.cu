@@ -799,11 +799,13 @@ trtri_merge_kernel(DevSym S, const int* __restrict__ list, const double* __restr
 // ---------------------------------------------------------------------------
 constexpr int WT = 512;
 constexpr int SLAB = 32;      // rows per CTA in the row-oriented products
+constexpr int TALL_N = 8192;  // fronts with at least this many rows take the finer-grained solve variants
 constexpr int KG = WT / 32;   // k-groups (warps)
 
 // children's update vectors into this supernode's right-hand side; a CTA owns a range of
-// destination rows, children are applied in ascending order (deterministic, no atomics)
-constexpr int GR = 2048;      // destination rows per CTA
+// destination rows, a thread one destination: it sums that destination's sources in ascending
+// child order (gather lists built at symbolic time: deterministic, no atomics, no searches)
+constexpr int GR = 512;       // destination rows per CTA (one per thread)
 __global__ void __launch_bounds__(WT)
 wide_fwd_gather_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ x, double* __restrict__ u) {
     const int s = list[blockIdx.y];
@@ -816,27 +818,10 @@ wide_fwd_gather_kernel(DevSym S, const int* __restrict__ list, double* __restric
     const int row1 = min(c + r, row0 + GR);
     double* xs = x + first;
     double* us = u + rp;
-    const int tid = threadIdx.x;
-    for (int i = max(row0, c) + tid; i < row1; i += WT) us[i - c] = 0.0;
-    __syncthreads();
-    for (int k = S.child_ptr[s]; k < S.child_ptr[s + 1]; k++) {
-        const int ch = S.child_list[k];
-        const int64_t rpc = S.rowptr[ch];
-        const int rc = (int)(S.rowptr[ch + 1] - rpc);
-        const int* __restrict__ relc = S.rel + rpc;
-        const double* uc = child_u(S, u, ch);
-        int lo = 0, hi = rc;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < row0) lo = mid + 1; else hi = mid; }
-        const int t0 = lo;
-        hi = rc;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < row1) lo = mid + 1; else hi = mid; }
-        const int t1 = lo;
-        for (int t = t0 + tid; t < t1; t += WT) {
-            const int dst = relc[t];
-            const double v = uc[t];
-            if (dst < c) xs[dst] += v; else us[dst - c] += v;
-        }
-        __syncthreads();
+    const int64_t gb = rp + first;
+    for (int i = row0 + threadIdx.x; i < row1; i += WT) {
+        const double acc = gather_dest(S, u, gb + i);
+        if (i < c) xs[i] += acc; else us[i - c] = acc;
     }
 }
 
@@ -845,39 +830,46 @@ wide_fwd_gather_kernel(DevSym S, const int* __restrict__ list, double* __restric
 // The solves walk those blocks: per block one triangular product with its inverse and one
 // rectangular product with the columns of L below / right of it.
 
-// xnew[i] = sum_{k in [b0, i]} X[i,k] * xs[k]   for the pivot rows i of block blk
+// xnew[i] = sum_{k in [b0, i]} X[i,k] * xs[k]   for the pivot rows i of block blk.
+// A CTA owns RS consecutive rows; its 512 threads split the k range 512/RS ways (a lane group of
+// RS lanes reads RS consecutive rows of one column: full 32-byte sectors for RS >= 4).  Fronts
+// with N >= TALL_N take RS = 8 (four times the CTAs, a quarter of the serial work per CTA: a level
+// with one tall front would otherwise run on 64 CTAs), the others RS = 32.
+template <int RS>
 __global__ void __launch_bounds__(WT)
 wide_fwd_tri_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Xinv,
                     const double* __restrict__ x, double* __restrict__ xnew, int blk) {
-    __shared__ double red[KG][SLAB];
+    constexpr int KS = WT / RS;              // k-groups per CTA
+    __shared__ double red[KS][RS];
     const Front d = get_front(S, list[blockIdx.y]);
+    if ((d.N >= TALL_N) != (RS < 32)) return;     // the other variant's front
     const int b0 = blk * XB;
     const int b1 = min(d.c, b0 + XB);
-    const int i0 = b0 + blockIdx.x * SLAB;
+    const int i0 = b0 + blockIdx.x * RS;
     if (i0 >= b1) return;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int i = i0 + lane;
+    const int r = threadIdx.x % RS, w = threadIdx.x / RS;
+    const int i = i0 + r;
     const double* X = Xinv + d.xoff;
     const double* xs = x + d.first;
-    const int kend = min(b1, i0 + SLAB);
+    const int kend = min(b1, i0 + RS);
     double acc = 0.0;
     if (i < b1) {
         int k = b0 + w;
-        for (; k + 7 * KG < kend; k += 8 * KG) {
+        for (; k + 7 * KS < kend; k += 8 * KS) {
             double v[8];
 #pragma unroll
-            for (int t = 0; t < 8; t++) v[t] = X[i + (size_t)(k + t * KG) * d.ldx];
+            for (int t = 0; t < 8; t++) v[t] = X[i + (size_t)(k + t * KS) * d.ldx];
 #pragma unroll
-            for (int t = 0; t < 8; t++) acc += v[t] * xs[k + t * KG];
+            for (int t = 0; t < 8; t++) acc += v[t] * xs[k + t * KS];
         }
-        for (; k < kend; k += KG) acc += X[i + (size_t)k * d.ldx] * xs[k];   // upper part of X is zero
+        for (; k < kend; k += KS) acc += X[i + (size_t)k * d.ldx] * xs[k];   // upper part of X is zero
     }
-    red[w][lane] = acc;
+    red[w][r] = acc;
     __syncthreads();
     if (w == 0 && i < b1) {
         double v = 0.0;
-#pragma unroll
-        for (int g = 0; g < KG; g++) v += red[g][lane];
+#pragma unroll 8
+        for (int g = 0; g < KS; g++) v += red[g][r];
         xnew[d.first + i] = v;
     }
 }
@@ -943,7 +935,6 @@ wide_bwd_gather_kernel(DevSym S, const int* __restrict__ list, const double* __r
 // WPC warps share one column (interleaved 128-row chunks, partial sums combined in shared memory
 // in a fixed order): a warp per column of a few tall fronts leaves most SMs idle.  Fronts with
 // N >= TALL_N take the 4-warp variant, the others the 1-warp variant.
-constexpr int TALL_N = 8192;
 template <int WPC>
 __global__ void __launch_bounds__(WT)
 wide_bwd_upd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lval,
@@ -1173,11 +1164,19 @@ void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sch
     const int nblk = (L.maxC[FC_BIG] + XB - 1) / XB;
     for (int blk = 0; blk < nblk; blk++) {
         const int cb = std::min(XB, L.maxC[FC_BIG] - blk * XB);
-        dim3 g1((cb + SLAB - 1) / SLAB, cnt);
-        wide_fwd_tri_kernel<<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
+        if (L.maxN[FC_BIG] >= TALL_N) {
+            dim3 g1((cb + 7) / 8, cnt);
+            wide_fwd_tri_kernel<8><<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
+            count_launch();
+        }
+        if (L.minN[FC_BIG] < TALL_N) {
+            dim3 g1((cb + SLAB - 1) / SLAB, cnt);
+            wide_fwd_tri_kernel<SLAB><<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
+            count_launch();
+        }
         dim3 g2((L.maxN[FC_BIG] - blk * XB + SLAB - 1) / SLAB, cnt);
         wide_fwd_upd_kernel<<<g2, WT, 0, st>>>(S, list, Lval, x, xnew, u, blk);
-        count_launch(2);
+        count_launch();
     }
 }
 
@@ -1226,7 +1225,8 @@ cudaError_t preload_dense() {
     e = cudaFuncGetAttributes(&a, wide_bwd_upd_kernel<1>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_bwd_upd_kernel<4>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_fwd_gather_kernel); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, wide_fwd_tri_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_fwd_tri_kernel<8>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_fwd_tri_kernel<SLAB>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_fwd_upd_kernel); if (e != cudaSuccess) return e;
     return cudaSuccess;
 }

@@ -45,21 +45,15 @@ fwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
     double* xs = x + first;
     double* us = u + rp;
     const int tid = threadIdx.x;
-    for (int t = tid; t < r; t += ST) us[t] = 0.0;
-    __syncthreads();
-    for (int k = S.child_ptr[s]; k < S.child_ptr[s + 1]; k++) {
-        const int ch = S.child_list[k];
-        const int64_t rpc = S.rowptr[ch];
-        const int rc = (int)(S.rowptr[ch + 1] - rpc);
-        const int* __restrict__ relc = S.rel + rpc;
-        const double* uc = child_u(S, u, ch);
-        for (int t = tid; t < rc; t += ST) {
-            const int dst = relc[t];
-            const double v = uc[t];
-            if (dst < c) xs[dst] += v; else us[dst - c] += v;
+    // children's update vectors: every destination sums its sources (ascending child order)
+    {
+        const int64_t gb = rp + first;
+        for (int dd = tid; dd < N; dd += ST) {
+            const double acc = gather_dest(S, u, gb + dd);
+            if (dd < c) xs[dd] += acc; else us[dd - c] = acc;
         }
-        __syncthreads();
     }
+    __syncthreads();
     for (int j0 = 0; j0 < c; j0 += SB) {
         const int b = min(SB, c - j0);
         stage_diag(panel, ld, j0, b, Dd, rdiag, mode);
@@ -146,6 +140,70 @@ bwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
     }
 }
 
+// Tiny supernodes (class T32: c + r <= 32, the bulk of the lowest levels): one WARP per
+// supernode, lane = row of the front.  The solution / update entries live in registers, the
+// substitution runs on shuffles; eight supernodes per CTA.
+constexpr int TW = 8;      // warps (supernodes) per CTA
+
+__global__ void __launch_bounds__(TW * 32)
+fwd_tiny_kernel(DevSym S, const int* __restrict__ list, int count, const double* __restrict__ Lval,
+                double* __restrict__ x, double* __restrict__ u, int mode) {
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * TW + (threadIdx.x >> 5);
+    if (idx >= count) return;
+    const int s = list[idx];
+    const int first = S.sfirst[s];
+    const int c = S.sfirst[s + 1] - first;
+    const int64_t rp = S.rowptr[s];
+    const int r = (int)(S.rowptr[s + 1] - rp);
+    const int N = c + r, ld = ld_of(N);
+    const double* __restrict__ panel = Lval + S.Loff[s];
+    double v = 0.0;
+    if (lane < N) {
+        v = gather_dest(S, u, rp + first + lane);
+        if (lane < c) v += x[first + lane];
+    }
+    for (int q = 0; q < c; q++) {
+        const double lq = (lane >= q && lane < N) ? panel[lane + (size_t)q * ld] : 0.0;   // L[lane, q]
+        double val = __shfl_sync(0xffffffffu, v, q);
+        if (mode == 0) val = val / __shfl_sync(0xffffffffu, lq, q);
+        if (lane == q) v = val;
+        else if (lane > q) v -= lq * val;
+    }
+    if (lane < c) x[first + lane] = v;
+    else if (lane < N) u[rp + lane - c] = v;
+}
+
+__global__ void __launch_bounds__(TW * 32)
+bwd_tiny_kernel(DevSym S, const int* __restrict__ list, int count, const double* __restrict__ Lval,
+                double* __restrict__ x, int mode) {
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * TW + (threadIdx.x >> 5);
+    if (idx >= count) return;
+    const int s = list[idx];
+    const int first = S.sfirst[s];
+    const int c = S.sfirst[s + 1] - first;
+    const int64_t rp = S.rowptr[s];
+    const int r = (int)(S.rowptr[s + 1] - rp);
+    const int N = c + r, ld = ld_of(N);
+    const double* __restrict__ panel = Lval + S.Loff[s];
+    double v = 0.0;
+    if (lane < c) {
+        v = x[first + lane];
+        if (mode == 1) v = v / panel[lane + (size_t)lane * ld];
+    } else if (lane < N) {
+        v = x[S.rowidx[rp + lane - c]];          // the ancestors' entries are final
+    }
+    for (int q = c - 1; q >= 0; q--) {
+        const double lq = (lane >= q && lane < N) ? panel[lane + (size_t)q * ld] : 0.0;   // L[lane, q]
+        double dot = (lane > q) ? lq * v : 0.0;
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        const double dq = __shfl_sync(0xffffffffu, lq, q);
+        if (lane == q) v = (mode == 0) ? (v - dot) / dq : (v - dot);
+    }
+    if (lane < c) x[first + lane] = v;
+}
+
 __global__ void permute_in_kernel(const double* __restrict__ b, const int* __restrict__ perm,
                                   double* __restrict__ x, int n) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -180,14 +238,24 @@ void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int
     for (size_t l = 0; l < plan.size(); l++) {
         const LevelPlan& L = plan[l];
         if (shard && L.barrier_before) launch_shard_barrier(*shard, st);
-        const int solo = wide ? L.all_count - L.count[FC_BIG] : L.all_count;
-        if (solo) { fwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.all_begin, Lval, x, u, mode); count_launch(); }
+        const int tiny = L.count[FC_T32];
+        const int solo = (wide ? L.all_count - L.count[FC_BIG] : L.all_count) - tiny;
+        if (tiny) {
+            fwd_tiny_kernel<<<(tiny + TW - 1) / TW, TW * 32, 0, st>>>(S, d_sched + L.begin[FC_T32], tiny, Lval, x, u, mode);
+            count_launch();
+        }
+        if (solo) { fwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.begin[FC_S64], Lval, x, u, mode); count_launch(); }
         if (wide) launch_solve_wide_fwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
     }
     for (size_t l = plan.size(); l-- > 0;) {
         const LevelPlan& L = plan[l];
-        const int solo = wide ? L.all_count - L.count[FC_BIG] : L.all_count;
-        if (solo) { bwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.all_begin, Lval, x, u, mode); count_launch(); }
+        const int tiny = L.count[FC_T32];
+        const int solo = (wide ? L.all_count - L.count[FC_BIG] : L.all_count) - tiny;
+        if (tiny) {
+            bwd_tiny_kernel<<<(tiny + TW - 1) / TW, TW * 32, 0, st>>>(S, d_sched + L.begin[FC_T32], tiny, Lval, x, mode);
+            count_launch();
+        }
+        if (solo) { bwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.begin[FC_S64], Lval, x, u, mode); count_launch(); }
         if (wide) launch_solve_wide_bwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
         if (shard) {
             launch_push_supernodes(S, d_sched + L.push_begin, L.push_count, L.push_maxc, x, st);
@@ -215,6 +283,8 @@ cudaError_t preload_solve() {
     cudaFuncAttributes a;
     cudaError_t e;
     e = cudaFuncGetAttributes(&a, fwd_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, fwd_tiny_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, bwd_tiny_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, bwd_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, permute_in_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, permute_out_kernel); if (e != cudaSuccess) return e;

@@ -41,7 +41,8 @@ struct Bundle {
     size_t device_bytes = 0;
     // device copies
     DBuf<int> d_sfirst, d_rowidx, d_rel, d_sparent, d_child_ptr, d_child_list, d_perm, d_sched;
-    DBuf<int64_t> d_rowptr, d_Loff, d_CBoff, d_amap, d_dpos, d_Mp, d_src, d_Xoff;
+    DBuf<int64_t> d_rowptr, d_Loff, d_CBoff, d_amap, d_dpos, d_Mp, d_src, d_Xoff, d_gptr, d_gsrc;
+    DBuf<int> d_gch;
     DBuf<int64_t> d_pair_ptr, d_Jp, d_Rp, d_Sp;
     DBuf<int> d_pairA, d_pairB, d_hmap, d_Jrow, d_Rcol, d_Rpos, d_Scol, d_Spos;
     DevSym dev{};
@@ -53,7 +54,7 @@ struct Bundle {
         d_Mp.release(); d_src.release(); d_Xoff.release(); d_pair_ptr.release(); d_Jp.release(); d_Rp.release(); d_Sp.release();
         d_pairA.release(); d_pairB.release(); d_hmap.release(); d_Jrow.release(); d_Rcol.release();
         d_Rpos.release(); d_Scol.release(); d_Spos.release();
-        d_owner.release(); d_colowner.release();
+        d_owner.release(); d_colowner.release(); d_gptr.release(); d_gsrc.release(); d_gch.release();
     }
 };
 
@@ -452,6 +453,7 @@ static int upload_bundle(opb_handle* h, Bundle& B) {
     CK(B.d_child_list.upload(S.child_list, st)); CK(B.d_perm.upload(S.perm, st));
     CK(B.d_sched.upload(B.sched, st));
     CK(B.d_Xoff.upload(B.Xoff, st));
+    CK(B.d_gptr.upload(S.gptr, st)); CK(B.d_gsrc.upload(S.gsrc, st)); CK(B.d_gch.upload(S.gch, st));
     if (B.world > 1) { CK(B.d_owner.upload(B.shard.owner, st)); CK(B.d_colowner.upload(B.colowner, st)); }
     {
         // diagonal entries carry a flag so the scatter kernel adds delta to them
@@ -478,6 +480,7 @@ static int upload_bundle(opb_handle* h, Bundle& B) {
     B.dev.rel = B.d_rel.p; B.dev.Loff = B.d_Loff.p; B.dev.CBoff = B.d_CBoff.p;
     B.dev.sparent = B.d_sparent.p; B.dev.child_ptr = B.d_child_ptr.p; B.dev.child_list = B.d_child_list.p;
     B.dev.perm = B.d_perm.p; B.dev.Xoff = B.d_Xoff.p;
+    B.dev.gptr = B.d_gptr.p; B.dev.gsrc = B.d_gsrc.p; B.dev.gch = B.d_gch.p;
     B.dev.owner = B.world > 1 ? B.d_owner.p : nullptr;
     B.dev.rank = B.rank; B.dev.world = B.world;
     return OPB_OK;
@@ -994,6 +997,9 @@ int64_t opb_get_symbolic(opb_handle* h, const char* name, int64_t* out, int64_t 
     if (k == "pairA") return copy_out(B.P.pairA, out, cap);
     if (k == "pairB") return copy_out(B.P.pairB, out, cap);
     if (k == "hmap") return copy_out(B.P.hmap, out, cap);
+    if (k == "gptr") return copy_out(S.gptr, out, cap);
+    if (k == "gsrc") return copy_out(S.gsrc, out, cap);
+    if (k == "gch") return copy_out(S.gch, out, cap);
     if (k == "owner") { if (B.world > 1) return copy_out(B.shard.owner, out, cap); return copy_out(std::vector<int>(S.nsuper, 0), out, cap); }
     if (k == "top") { std::vector<int> t(S.nsuper, 0); if (B.world > 1) for (int q = 0; q < S.nsuper; q++) t[q] = B.shard.top[q]; return copy_out(t, out, cap); }
     return h->fail(OPB_ERR_INVALID, "unknown symbolic array " + k);

@@ -55,6 +55,9 @@ struct DevSym {
     const int* child_list;
     const int* perm;   // perm[new] = old
     const int64_t* Xoff;  // per supernode: offset of inv(L11) (c x c, ld = ld_of(c)) in Xinv, or -1
+    const int64_t* gptr;  // forward-solve gather lists (symbolic.h)
+    const int64_t* gsrc;
+    const int* gch;
     // ---- one instance sharded over several GPUs; owner == nullptr on a single GPU
     const int* owner;     // per supernode: rank that owns it
     int rank, world;
@@ -71,6 +74,14 @@ __device__ __forceinline__ const double* child_cb(const DevSym& S, const double*
 }
 __device__ __forceinline__ const double* child_u(const DevSym& S, const double* u, int ch) {
     return (S.owner ? S.u_peer[S.owner[ch]] : u) + S.rowptr[ch];
+}
+// sum of the children's update-vector entries that land on destination g (ascending child order)
+__device__ __forceinline__ double gather_dest(const DevSym& S, const double* u, int64_t g) {
+    double acc = 0.0;
+    const int64_t e1 = S.gptr[g + 1];
+    for (int64_t e = S.gptr[g]; e < e1; e++)
+        acc += (S.owner ? S.u_peer[S.owner[S.gch[e]]] : u)[S.gsrc[e]];
+    return acc;
 }
 
 // Cross-GPU barrier state of a sharded handle: every rank owns 2 x MAX_SHARD flag words that

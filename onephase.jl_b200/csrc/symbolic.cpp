@@ -789,6 +789,32 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
             S.rel[t] = pc + (int)(q - S.rowptr[p]);
         }
     }
+    // ---- forward-solve gather lists (the transpose of `rel`): per destination of every front the
+    // update-vector entries of its children, ascending child order
+    {
+        const int64_t G = (int64_t)S.rowidx.size() + n;
+        S.gptr.assign(G + 1, 0);
+        for (int s = 0; s < NS; s++) {
+            const int p = S.sparent[s];
+            if (p < 0) continue;
+            const int64_t gb = S.rowptr[p] + S.sfirst[p];
+            for (int64_t t = S.rowptr[s]; t < S.rowptr[s + 1]; t++) S.gptr[gb + S.rel[t] + 1]++;
+        }
+        for (int64_t g = 0; g < G; g++) S.gptr[g + 1] += S.gptr[g];
+        S.gsrc.assign(S.gptr[G], 0);
+        S.gch.assign(S.gptr[G], 0);
+        std::vector<int64_t> nxt(S.gptr.begin(), S.gptr.end() - 1);
+        for (int s = 0; s < NS; s++) {          // ascending s = ascending child order inside every parent
+            const int p = S.sparent[s];
+            if (p < 0) continue;
+            const int64_t gb = S.rowptr[p] + S.sfirst[p];
+            for (int64_t t = S.rowptr[s]; t < S.rowptr[s + 1]; t++) {
+                const int64_t e = nxt[gb + S.rel[t]]++;
+                S.gsrc[e] = t;
+                S.gch[e] = s;
+            }
+        }
+    }
     // ---- map M_L entries into the L panels
     S.amap.assign(Mp[n], -1);
     S.dpos.assign(n, -1);

@@ -58,6 +58,11 @@ struct Symbolic {
     int nlevels = 0;
     std::vector<int> level_ptr, level_list;  // supernodes grouped by level
     std::vector<int> child_ptr, child_list;  // children of each supernode (ascending)
+    // forward-solve gather lists: destination d (0 <= d < c+r) of supernode s sums the entries
+    // gsrc[gptr[g] .. gptr[g+1]) of the update-vector storage, g = rowptr[s] + sfirst[s] + d, in
+    // ascending child order (gch = the child each entry belongs to)
+    std::vector<int64_t> gptr, gsrc;
+    std::vector<int> gch;
     std::vector<int64_t> amap;           // per M_L entry: destination offset in L storage
     std::vector<int64_t> dpos;           // per original variable: offset of its diagonal in L
     std::vector<int> col2super;          // permuted column -> supernode

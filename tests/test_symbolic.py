@@ -156,3 +156,35 @@ def test_user_permutation(pkg, orc):
         hb = pkg.Handle(-1)
         hb.set_permutation(np.zeros(prob.n, np.int64))
         hb.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
+
+
+def test_forward_gather_lists_are_the_transpose_of_rel(pkg):
+    """gptr/gsrc/gch (forward-solve gather lists) against the child-by-child scatter through `rel`."""
+    prob = pkg.problems.sparse_qp(3000, 1500, seed=4)
+    h = pkg.Handle(-1)
+    h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
+    sfirst, sparent, rowptr, rel = (h.symbolic(k) for k in ("sfirst", "sparent", "rowptr", "rel"))
+    gptr, gsrc, gch = h.symbolic("gptr"), h.symbolic("gsrc"), h.symbolic("gch")
+    ns = len(sparent)
+    assert len(gptr) == rowptr[-1] + prob.n + 1 and gptr[0] == 0
+    rng = np.random.default_rng(0)
+    u = rng.standard_normal(rowptr[-1])
+    # reference: scatter every child's update vector into its parent, children ascending
+    want = np.zeros(len(gptr) - 1)
+    nsrc = 0
+    for s in range(ns):
+        p = sparent[s]
+        if p < 0:
+            continue
+        gb = rowptr[p] + sfirst[p]
+        for t in range(rowptr[s], rowptr[s + 1]):
+            want[gb + rel[t]] += u[t]
+            nsrc += 1
+    assert gptr[-1] == nsrc == len(gsrc) == len(gch)
+    got = np.array([u[gsrc[gptr[g]:gptr[g + 1]]].sum() for g in range(len(gptr) - 1)])
+    assert np.allclose(got, want, rtol=0, atol=1e-12)
+    for g in range(len(gptr) - 1):                       # ascending child order inside a destination
+        ch = gch[gptr[g]:gptr[g + 1]]
+        assert np.all(np.diff(ch) > 0)
+    # every entry belongs to the child it claims
+    assert np.all((gsrc >= rowptr[gch]) & (gsrc < rowptr[gch + 1]))
