@@ -140,43 +140,24 @@ bwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
     }
 }
 
-// Tiny supernodes (class T32: c + r <= 32, the bulk of the lowest levels): one WARP per
-// supernode, lane = row of the front.  The solution / update entries live in registers, the
-// substitution runs on shuffles; eight supernodes per CTA.
+// Tiny supernodes (class T32: c + r <= 32, the bulk of the lowest level): one WARP per supernode,
+// lane l owns the rows l, l + 32, ... (R per lane; R = 1 is what runs) of the front.  The solution /
+// update entries live in registers, the substitution runs on shuffles, every panel entry is read
+// once; eight supernodes per CTA.
 constexpr int TW = 8;      // warps (supernodes) per CTA
 
-__global__ void __launch_bounds__(TW * 32)
-fwd_tiny_kernel(DevSym S, const int* __restrict__ list, int count, const double* __restrict__ Lval,
-                double* __restrict__ x, double* __restrict__ u, int mode) {
-    const int lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * TW + (threadIdx.x >> 5);
-    if (idx >= count) return;
-    const int s = list[idx];
-    const int first = S.sfirst[s];
-    const int c = S.sfirst[s + 1] - first;
-    const int64_t rp = S.rowptr[s];
-    const int r = (int)(S.rowptr[s + 1] - rp);
-    const int N = c + r, ld = ld_of(N);
-    const double* __restrict__ panel = Lval + S.Loff[s];
-    double v = 0.0;
-    if (lane < N) {
-        v = gather_dest(S, u, rp + first + lane);
-        if (lane < c) v += x[first + lane];
-    }
-    for (int q = 0; q < c; q++) {
-        const double lq = (lane >= q && lane < N) ? panel[lane + (size_t)q * ld] : 0.0;   // L[lane, q]
-        double val = __shfl_sync(0xffffffffu, v, q);
-        if (mode == 0) val = val / __shfl_sync(0xffffffffu, lq, q);
-        if (lane == q) v = val;
-        else if (lane > q) v -= lq * val;
-    }
-    if (lane < c) x[first + lane] = v;
-    else if (lane < N) u[rp + lane - c] = v;
+template <int R>
+__device__ __forceinline__ double pick(const double (&v)[R], int j) {
+    double r = v[0];
+#pragma unroll
+    for (int t = 1; t < R; t++) if (j == t) r = v[t];
+    return r;
 }
 
+template <int R>
 __global__ void __launch_bounds__(TW * 32)
-bwd_tiny_kernel(DevSym S, const int* __restrict__ list, int count, const double* __restrict__ Lval,
-                double* __restrict__ x, int mode) {
+fwd_small_kernel(DevSym S, const int* __restrict__ list, int count, const double* __restrict__ Lval,
+                 double* __restrict__ x, double* __restrict__ u, int mode) {
     const int lane = threadIdx.x & 31;
     const int idx = blockIdx.x * TW + (threadIdx.x >> 5);
     if (idx >= count) return;
@@ -187,21 +168,92 @@ bwd_tiny_kernel(DevSym S, const int* __restrict__ list, int count, const double*
     const int r = (int)(S.rowptr[s + 1] - rp);
     const int N = c + r, ld = ld_of(N);
     const double* __restrict__ panel = Lval + S.Loff[s];
-    double v = 0.0;
-    if (lane < c) {
-        v = x[first + lane];
-        if (mode == 1) v = v / panel[lane + (size_t)lane * ld];
-    } else if (lane < N) {
-        v = x[S.rowidx[rp + lane - c]];          // the ancestors' entries are final
+    double v[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const int row = lane + 32 * j;
+        v[j] = 0.0;
+        if (row < N) {
+            v[j] = gather_dest(S, u, rp + first + row);
+            if (row < c) v[j] += x[first + row];
+        }
+    }
+    for (int q = 0; q < c; q++) {
+        const double* __restrict__ col = panel + (size_t)q * ld;
+        double lq[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) { const int row = lane + 32 * j; lq[j] = (row > q && row < N) ? col[row] : 0.0; }
+        double val = __shfl_sync(0xffffffffu, pick<R>(v, q >> 5), q & 31);
+        if (mode == 0) val = val / col[q];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const int row = lane + 32 * j;
+            if (row == q) v[j] = val; else v[j] -= lq[j] * val;     // lq = 0 above the diagonal
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const int row = lane + 32 * j;
+        if (row < c) x[first + row] = v[j];
+        else if (row < N) u[rp + row - c] = v[j];
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(TW * 32)
+bwd_small_kernel(DevSym S, const int* __restrict__ list, int count, const double* __restrict__ Lval,
+                 double* __restrict__ x, int mode) {
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * TW + (threadIdx.x >> 5);
+    if (idx >= count) return;
+    const int s = list[idx];
+    const int first = S.sfirst[s];
+    const int c = S.sfirst[s + 1] - first;
+    const int64_t rp = S.rowptr[s];
+    const int r = (int)(S.rowptr[s + 1] - rp);
+    const int N = c + r, ld = ld_of(N);
+    const double* __restrict__ panel = Lval + S.Loff[s];
+    double v[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const int row = lane + 32 * j;
+        v[j] = 0.0;
+        if (row < c) {
+            v[j] = x[first + row];
+            if (mode == 1) v[j] = v[j] / panel[row + (size_t)row * ld];
+        } else if (row < N) {
+            v[j] = x[S.rowidx[rp + row - c]];          // the ancestors' entries are final
+        }
     }
     for (int q = c - 1; q >= 0; q--) {
-        const double lq = (lane >= q && lane < N) ? panel[lane + (size_t)q * ld] : 0.0;   // L[lane, q]
-        double dot = (lane > q) ? lq * v : 0.0;
+        const double* __restrict__ col = panel + (size_t)q * ld;
+        double dot = 0.0;
+#pragma unroll
+        for (int j = 0; j < R; j++) { const int row = lane + 32 * j; if (row > q && row < N) dot += col[row] * v[j]; }
         for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        const double dq = __shfl_sync(0xffffffffu, lq, q);
-        if (lane == q) v = (mode == 0) ? (v - dot) / dq : (v - dot);
+        const double dq = (mode == 0) ? col[q] : 1.0;
+#pragma unroll
+        for (int j = 0; j < R; j++) if (lane + 32 * j == q) v[j] = (v[j] - dot) / dq;
     }
-    if (lane < c) x[first + lane] = v;
+#pragma unroll
+    for (int j = 0; j < R; j++) { const int row = lane + 32 * j; if (row < c) x[first + row] = v[j]; }
+}
+
+template <int R>
+void launch_small(bool forward, const DevSym& S, const int* list, int count, const double* Lval, double* x,
+                  double* u, int mode, cudaStream_t st) {
+    if (!count) return;
+    const unsigned g = (unsigned)((count + TW - 1) / TW);
+    if (forward) fwd_small_kernel<R><<<g, TW * 32, 0, st>>>(S, list, count, Lval, x, u, mode);
+    else bwd_small_kernel<R><<<g, TW * 32, 0, st>>>(S, list, count, Lval, x, mode);
+    count_launch();
+}
+// Only the tiny class runs a warp per supernode: for the wider classes (R = 2..5 rows per lane) the
+// serial substitution of a single warp over up to ~100 columns was measured slower than the
+// CTA-per-supernode kernels with their 32-column blocks (C3: 2.28 vs 1.69 ms per solve pair).
+void launch_small_classes(bool forward, const DevSym& S, const LevelPlan& L, const int* d_sched,
+                          const double* Lval, double* x, double* u, int mode, cudaStream_t st) {
+    launch_small<1>(forward, S, d_sched + L.begin[FC_T32], L.count[FC_T32], Lval, x, u, mode, st);
 }
 
 __global__ void permute_in_kernel(const double* __restrict__ b, const int* __restrict__ perm,
@@ -238,23 +290,16 @@ void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int
     for (size_t l = 0; l < plan.size(); l++) {
         const LevelPlan& L = plan[l];
         if (shard && L.barrier_before) launch_shard_barrier(*shard, st);
-        const int tiny = L.count[FC_T32];
-        const int solo = (wide ? L.all_count - L.count[FC_BIG] : L.all_count) - tiny;
-        if (tiny) {
-            fwd_tiny_kernel<<<(tiny + TW - 1) / TW, TW * 32, 0, st>>>(S, d_sched + L.begin[FC_T32], tiny, Lval, x, u, mode);
-            count_launch();
-        }
+        // warp per supernode for the tiny class, CTA per supernode above
+        const int solo = (wide ? L.all_count - L.count[FC_BIG] : L.all_count) - L.count[FC_T32];
+        launch_small_classes(true, S, L, d_sched, Lval, x, u, mode, st);
         if (solo) { fwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.begin[FC_S64], Lval, x, u, mode); count_launch(); }
         if (wide) launch_solve_wide_fwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
     }
     for (size_t l = plan.size(); l-- > 0;) {
         const LevelPlan& L = plan[l];
-        const int tiny = L.count[FC_T32];
-        const int solo = (wide ? L.all_count - L.count[FC_BIG] : L.all_count) - tiny;
-        if (tiny) {
-            bwd_tiny_kernel<<<(tiny + TW - 1) / TW, TW * 32, 0, st>>>(S, d_sched + L.begin[FC_T32], tiny, Lval, x, mode);
-            count_launch();
-        }
+        const int solo = (wide ? L.all_count - L.count[FC_BIG] : L.all_count) - L.count[FC_T32];
+        launch_small_classes(false, S, L, d_sched, Lval, x, u, mode, st);
         if (solo) { bwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.begin[FC_S64], Lval, x, u, mode); count_launch(); }
         if (wide) launch_solve_wide_bwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
         if (shard) {
@@ -283,8 +328,8 @@ cudaError_t preload_solve() {
     cudaFuncAttributes a;
     cudaError_t e;
     e = cudaFuncGetAttributes(&a, fwd_kernel); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, fwd_tiny_kernel); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, bwd_tiny_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, fwd_small_kernel<1>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, bwd_small_kernel<1>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, bwd_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, permute_in_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, permute_out_kernel); if (e != cudaSuccess) return e;
