@@ -173,9 +173,11 @@ class Handle:
         self.check(self.L.opb_shard_attach(self.h, int(peer), blob))
 
     # --- numeric
-    def form(self, Jx, Hx, y, s, want_diag=True):
+    def form(self, Jx, Hx, y, s, want_diag=True, out=None):
         Jx, Hx, y, s = f64(Jx), f64(Hx), f64(y), f64(s)
-        sd = np.empty(self.n) if want_diag else None
+        if out is not None:
+            assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (self.n,)
+        sd = out if out is not None else (np.empty(self.n) if want_diag else None)
         dmin = ctypes.c_double()
         self.check(self.L.opb_form(self.h, pf(Jx), pf(Hx), pf(y), pf(s), pf(sd),
                                    ctypes.cast(ctypes.byref(dmin), c_f64p)))
@@ -206,9 +208,17 @@ class Handle:
         self.check(self.L.opb_factor(self.h, float(delta), ctypes.byref(ok)))
         return ok.value
 
-    def direction(self, dual_r, primal_r, comp_r, n_refine=3):
+    def direction(self, dual_r, primal_r, comp_r, n_refine=3, out=None):
+        """out = (dx, dy, ds): caller-owned float64 arrays written in place (the reference fills
+        kkt_solver.dir.x/y/s in place, schur.jl:89-128); fresh arrays when omitted."""
         a, b, c = f64(dual_r), f64(primal_r), f64(comp_r)
-        dx = np.empty(self.n); dy = np.empty(self.m); ds = np.empty(self.m); err = np.empty(6)
+        if out is not None:
+            dx, dy, ds = out
+            for v, k in ((dx, self.n), (dy, self.m), (ds, self.m)):
+                assert v.dtype == np.float64 and v.flags.c_contiguous and v.shape == (k,)
+        else:
+            dx = np.empty(self.n); dy = np.empty(self.m); ds = np.empty(self.m)
+        err = np.empty(6)
         self.check(self.L.opb_direction(self.h, pf(a), pf(b), pf(c), n_refine, pf(dx), pf(dy), pf(ds), pf(err)))
         return dx, dy, ds, err
 

@@ -116,6 +116,8 @@ def set_delta(it, d):
 
 
 def _csc(A):
+    if sp.isspmatrix_csc(A) and A.has_sorted_indices:
+        return A              # the usual case: no new object, the sortedness flag stays cached on A
     A = sp.csc_matrix(A)
     if not A.has_sorted_indices:
         A = A.copy(); A.sort_indices()
@@ -239,7 +241,10 @@ class Schur_B200_KKT_solver:
                 self._pattern_key = key
             self._pattern_ident = ident
             self._pattern_refs = (J.indptr, J.indices, H.indptr, H.indices)   # keep the ids alive
-        self.schur_diag, self._diag_min = self._h.form(J.data, H.data, it.y, it.s)
+        # schur_diag is refilled in place (same array object across iterations, like the reference's
+        # kkt_solver.schur_diag field) unless the dimension changed
+        reuse = self.schur_diag if (self.schur_diag is not None and self.schur_diag.shape == (J.shape[1],)) else None
+        self.schur_diag, self._diag_min = self._h.form(J.data, H.data, it.y, it.s, out=reuse)
         self.factor_it = it
         self.Q = None
         self.ready = "system_formed"
@@ -320,7 +325,13 @@ class Schur_B200_KKT_solver:
 
     def compute_direction_implementation(self, timer=None):
         n_ref = self.pars.kkt.ItRefine_Num if self.pars is not None else 3
-        dx, dy, ds, err = self._h.direction(self.rhs.dual_r, self.rhs.primal_r, self.rhs.comp_r, n_ref)
+        # kkt_solver.dir.x/y/s are filled in place, as in the reference (schur.jl:115-123)
+        n, m = self._h.n, self._h.m
+        d = self.dir
+        ok = all(isinstance(v, np.ndarray) and v.dtype == np.float64 and v.flags.c_contiguous and v.shape == (k,)
+                 for v, k in ((d.x, n), (d.y, m), (d.s, m)))
+        out = (d.x, d.y, d.s) if ok else None
+        dx, dy, ds, err = self._h.direction(self.rhs.dual_r, self.rhs.primal_r, self.rhs.comp_r, n_ref, out=out)
         self.dir.x, self.dir.y, self.dir.s = dx, dy, ds
         self.kkt_err_norm = Class_kkt_error(*[float(v) for v in err])
         self.rhs_norm = float(err[4])
