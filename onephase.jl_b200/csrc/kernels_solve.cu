@@ -18,9 +18,10 @@ constexpr int SB = 32;         // column block
 constexpr int DLD = SB + 1;
 
 // stage the b x b diagonal block at (j0, j0) of a panel in shared memory, plus 1/diag
+template <int NT>
 __device__ __forceinline__ void stage_diag(const double* __restrict__ panel, int ld, int j0, int b,
                                            double* Dd, double* rdiag, int mode) {
-    for (int e = threadIdx.x; e < SB * SB; e += ST) {
+    for (int e = threadIdx.x; e < SB * SB; e += NT) {
         const int i = e & (SB - 1), j = e >> 5;
         if (i < b && j < b && i >= j) Dd[i + j * DLD] = panel[(j0 + i) + (size_t)(j0 + j) * ld];
     }
@@ -29,7 +30,9 @@ __device__ __forceinline__ void stage_diag(const double* __restrict__ panel, int
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(ST)
+// NT threads per supernode (256 is what runs, see launch_cta_classes)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 fwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lval,
            double* __restrict__ x, double* __restrict__ u, int mode) {
     __shared__ double yb[SB];
@@ -48,7 +51,7 @@ fwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
     // children's update vectors: every destination sums its sources (ascending child order)
     {
         const int64_t gb = rp + first;
-        for (int dd = tid; dd < N; dd += ST) {
+        for (int dd = tid; dd < N; dd += NT) {
             const double acc = gather_dest(S, u, gb + dd);
             if (dd < c) xs[dd] += acc; else us[dd - c] = acc;
         }
@@ -56,7 +59,7 @@ fwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
     __syncthreads();
     for (int j0 = 0; j0 < c; j0 += SB) {
         const int b = min(SB, c - j0);
-        stage_diag(panel, ld, j0, b, Dd, rdiag, mode);
+        stage_diag<NT>(panel, ld, j0, b, Dd, rdiag, mode);
         if (tid < 32) {
             const int lane = tid;
             double xv = (lane < b) ? xs[j0 + lane] : 0.0;
@@ -68,7 +71,7 @@ fwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
             if (lane < b) { xs[j0 + lane] = xv; yb[lane] = xv; }
         }
         __syncthreads();
-        for (int i = j0 + b + tid; i < N; i += ST) {
+        for (int i = j0 + b + tid; i < N; i += NT) {
             const double* pr = panel + i + (size_t)j0 * ld;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int q = 0;
@@ -86,7 +89,8 @@ fwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
     }
 }
 
-__global__ void __launch_bounds__(ST)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 bwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lval,
            double* __restrict__ x, double* __restrict__ u, int mode) {
     __shared__ double yb[SB];
@@ -103,15 +107,15 @@ bwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
     double* us = u + rp;
     const int* __restrict__ rows = S.rowidx + rp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int t = tid; t < r; t += ST) us[t] = x[rows[t]];
+    for (int t = tid; t < r; t += NT) us[t] = x[rows[t]];
     if (mode == 1)
-        for (int j = tid; j < c; j += ST) xs[j] = xs[j] / panel[j + (size_t)j * ld];
+        for (int j = tid; j < c; j += NT) xs[j] = xs[j] / panel[j + (size_t)j * ld];
     __syncthreads();
     const int nblk = (c + SB - 1) / SB;
     for (int blk = nblk - 1; blk >= 0; blk--) {
         const int j0 = blk * SB;
         const int b = min(SB, c - j0);
-        for (int q = warp; q < b; q += ST / 32) {
+        for (int q = warp; q < b; q += NT / 32) {
             const double* col = panel + (size_t)(j0 + q) * ld;
             double a0 = 0.0, a1 = 0.0;
             int i = j0 + b + lane;
@@ -126,7 +130,7 @@ bwd_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lv
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) yb[q] = xs[j0 + q] - acc;
         }
-        stage_diag(panel, ld, j0, b, Dd, rdiag, mode);     // ends with a barrier: yb is complete too
+        stage_diag<NT>(panel, ld, j0, b, Dd, rdiag, mode);     // ends with a barrier: yb is complete too
         if (tid < 32) {
             double xv = (lane < b) ? yb[lane] : 0.0;
             for (int q = b - 1; q >= 0; q--) {
@@ -256,6 +260,23 @@ void launch_small_classes(bool forward, const DevSym& S, const LevelPlan& L, con
     launch_small<1>(forward, S, d_sched + L.begin[FC_T32], L.count[FC_T32], Lval, x, u, mode, st);
 }
 
+template <int NT>
+void launch_cta(bool forward, const DevSym& S, const int* list, int count, const double* Lval, double* x,
+                double* u, int mode, cudaStream_t st) {
+    if (count <= 0) return;
+    if (forward) fwd_kernel<NT><<<count, NT, 0, st>>>(S, list, Lval, x, u, mode);
+    else bwd_kernel<NT><<<count, NT, 0, st>>>(S, list, Lval, x, u, mode);
+    count_launch();
+}
+// CTA-per-supernode classes of a level (`solo` supernodes starting at the S64 class): ONE launch
+// with 256 threads.  Per-class thread counts (64 / 128 / 256 in three launches) were measured
+// slower: the extra launches per level cost more than the higher residency gains (C3: 2.02 vs
+// 1.67 ms per solve pair).
+void launch_cta_classes(bool forward, const DevSym& S, const LevelPlan& L, const int* d_sched, int solo,
+                        const double* Lval, double* x, double* u, int mode, cudaStream_t st) {
+    launch_cta<ST>(forward, S, d_sched + L.begin[FC_S64], solo, Lval, x, u, mode, st);
+}
+
 __global__ void permute_in_kernel(const double* __restrict__ b, const int* __restrict__ perm,
                                   double* __restrict__ x, int n) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,14 +314,14 @@ void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int
         // warp per supernode for the tiny class, CTA per supernode above
         const int solo = (wide ? L.all_count - L.count[FC_BIG] : L.all_count) - L.count[FC_T32];
         launch_small_classes(true, S, L, d_sched, Lval, x, u, mode, st);
-        if (solo) { fwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.begin[FC_S64], Lval, x, u, mode); count_launch(); }
+        launch_cta_classes(true, S, L, d_sched, solo, Lval, x, u, mode, st);
         if (wide) launch_solve_wide_fwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
     }
     for (size_t l = plan.size(); l-- > 0;) {
         const LevelPlan& L = plan[l];
         const int solo = (wide ? L.all_count - L.count[FC_BIG] : L.all_count) - L.count[FC_T32];
         launch_small_classes(false, S, L, d_sched, Lval, x, u, mode, st);
-        if (solo) { bwd_kernel<<<solo, ST, 0, st>>>(S, d_sched + L.begin[FC_S64], Lval, x, u, mode); count_launch(); }
+        launch_cta_classes(false, S, L, d_sched, solo, Lval, x, u, mode, st);
         if (wide) launch_solve_wide_bwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
         if (shard) {
             launch_push_supernodes(S, d_sched + L.push_begin, L.push_count, L.push_maxc, x, st);
@@ -327,10 +348,10 @@ void launch_permute_out_add(const double* x, const int* perm, double* dst, int n
 cudaError_t preload_solve() {
     cudaFuncAttributes a;
     cudaError_t e;
-    e = cudaFuncGetAttributes(&a, fwd_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, fwd_kernel<ST>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, fwd_small_kernel<1>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, bwd_small_kernel<1>); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, bwd_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, bwd_kernel<ST>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, permute_in_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, permute_out_kernel); if (e != cudaSuccess) return e;
     return cudaSuccess;

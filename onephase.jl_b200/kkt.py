@@ -320,7 +320,8 @@ class Schur_B200_KKT_solver:
             raise RuntimeError("kkt solver not ready to compute direction!")
         self.compute_direction_implementation(timer)
         for v in (self.dir.x, self.dir.y, self.dir.s):      # check_for_nan, IPM_tools.jl:32-49
-            if np.isnan(v).any():
+            # a NaN anywhere makes the sum NaN: one pass without a temporary in the usual case
+            if np.isnan(np.sum(v)) and np.isnan(v).any():
                 raise FloatingPointError("NaN in direction")
 
     def compute_direction_implementation(self, timer=None):
@@ -355,8 +356,14 @@ def ipopt_strategy(it, kkt_solver, pars, timer=None):
     st, num_fac, delta = kkt_solver._h.factor_delta_loop(get_delta(it), d.zero, d.min, d.max, d.start,
                                                          d.inc, d.dec, 500)
     n = dim(it)
-    kkt_solver.delta_x_vec = delta * np.ones(n)
-    kkt_solver.delta_s_vec = np.zeros(ncon(it))
+    # delta_x_vec = delta * ones(n), delta_s_vec = zeros(m) (delta_strategy.jl via update_delta!):
+    # refilled in place when the sizes are unchanged
+    dxv, dsv = kkt_solver.delta_x_vec, kkt_solver.delta_s_vec
+    if isinstance(dxv, np.ndarray) and dxv.shape == (n,) and isinstance(dsv, np.ndarray) and dsv.shape == (ncon(it),):
+        dxv.fill(delta); dsv.fill(0.0)
+    else:
+        kkt_solver.delta_x_vec = np.full(n, delta)
+        kkt_solver.delta_s_vec = np.zeros(ncon(it))
     kkt_solver._delta = delta
     kkt_solver.ready = "factored"
     if st == 1:
