@@ -37,7 +37,7 @@ WORKLOADS = {
     "c3_sparse_qp_n200k": ("sparse_qp", dict(n=200_000, m_gen=100_000), dict(n=50_000, m_gen=25_000)),
     "c2_chain_n100k": ("chain", dict(nh=25_000), dict(nh=25_000)),
     "c4_elec_n1200": ("elec", dict(n_p=400), dict(n_p=400)),
-    "c5_pde_100": ("pde_control", dict(N=100), dict(N=28)),
+    "c5_pde_100": ("pde_control", dict(N=100), dict(N=32)),
     "c5_pde_60": ("pde_control", dict(N=60), dict(N=24)),
     "c5_pde_40": ("pde_control", dict(N=40), dict(N=24)),
     "c3_small": ("sparse_qp", dict(n=20_000, m_gen=10_000), dict(n=20_000, m_gen=10_000)),

@@ -12,6 +12,7 @@
 #include "symbolic.h"
 
 #include <algorithm>
+#include <map>
 #include <cstring>
 #include <numeric>
 
@@ -758,11 +759,10 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
     for (int s = 0; s < NS; s++) {
         int64_t c = S.sfirst[s + 1] - S.sfirst[s], r = S.rowptr[s + 1] - S.rowptr[s];
         S.Loff[s + 1] = S.Loff[s] + panel_ld(c + r) * c;
-        S.CBoff[s + 1] = S.CBoff[s] + r * r;
         S.max_front = std::max<int64_t>(S.max_front, c + r);
         if (S.sparent[s] >= 0) S.level[S.sparent[s]] = std::max(S.level[S.sparent[s]], S.level[s] + 1);
     }
-    S.nnzL = S.Loff[NS]; S.cb_total = S.CBoff[NS];
+    S.nnzL = S.Loff[NS];
     S.nlevels = 0;
     for (int s = 0; s < NS; s++) S.nlevels = std::max(S.nlevels, S.level[s] + 1);
     S.level_ptr.assign(S.nlevels + 1, 0);
@@ -772,6 +772,59 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
     {
         std::vector<int> nxt(S.level_ptr.begin(), S.level_ptr.end() - 1);
         for (int s = 0; s < NS; s++) S.level_list[nxt[S.level[s]]++] = s;
+    }
+    // ---- storage of the update blocks.  Block s (r x r) is written while level(s) is processed and
+    // read while level(parent(s)) is processed, so it is live on the level interval
+    // [level(s), level(parent)].  Offsets are handed out level by level from a first-fit free list:
+    // before level l starts, every block whose parent sits below l is returned.  (A prefix-sum
+    // layout needs sum r^2 = 90 GB for the 100^3 PDE instance; the live set is a fraction of it.)
+    {
+        std::vector<std::vector<int>> dies(S.nlevels + 1);     // dies[l]: blocks free again when level l starts
+        for (int s = 0; s < NS; s++) {
+            const int p = S.sparent[s];
+            if (p >= 0) dies[S.level[p] + 1].push_back(s);
+        }
+        std::map<int64_t, int64_t> free_list;                   // offset -> size, coalesced
+        int64_t top = 0;
+        S.cb_total = 0;
+        auto release = [&](int64_t off, int64_t sz) {
+            if (sz <= 0) return;
+            auto it = free_list.emplace(off, sz).first;
+            auto nx = std::next(it);
+            if (nx != free_list.end() && it->first + it->second == nx->first) { it->second += nx->second; free_list.erase(nx); }
+            if (it != free_list.begin()) {
+                auto pv = std::prev(it);
+                if (pv->first + pv->second == it->first) { pv->second += it->second; free_list.erase(it); it = pv; }
+            }
+            if (it->first + it->second == top) { top = it->first; free_list.erase(it); }   // shrink the arena
+        };
+        std::vector<int64_t> bsize(NS, 0);
+        for (int l = 0; l < S.nlevels; l++) {
+            for (int s : dies[l]) release(S.CBoff[s], bsize[s]);
+            // biggest blocks first: they find (or create) their place before the small ones fragment it
+            std::vector<int> order(S.level_list.begin() + S.level_ptr[l], S.level_list.begin() + S.level_ptr[l + 1]);
+            auto rows_of = [&](int s) { return (int64_t)(S.rowptr[s + 1] - S.rowptr[s]); };
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rows_of(a) > rows_of(b); });
+            for (int s : order) {
+                const int64_t r = rows_of(s);
+                const int64_t sz = (r * r + 1) & ~(int64_t)1;
+                bsize[s] = (S.sparent[s] >= 0) ? sz : 0;
+                if (S.sparent[s] < 0 || sz == 0) { S.CBoff[s] = 0; bsize[s] = 0; continue; }
+                int64_t off = -1;
+                for (auto it = free_list.begin(); it != free_list.end(); ++it)
+                    if (it->second >= sz) {
+                        off = it->first;
+                        const int64_t rest = it->second - sz;
+                        free_list.erase(it);
+                        if (rest > 0) free_list.emplace(off + sz, rest);
+                        break;
+                    }
+                if (off < 0) { off = top; top += sz; }
+                S.CBoff[s] = off;
+                S.cb_total = std::max(S.cb_total, off + sz);
+            }
+        }
+        S.CBoff[NS] = S.cb_total;
     }
     // ---- relative indices of each update block inside the parent's front
     S.rel.assign(S.rowidx.size(), -1);

@@ -98,7 +98,7 @@ def test_structure_invariants(pkg):
             assert S.sparent[s] == -1
     # panels tile the L storage exactly, maps are injective
     c = np.diff(S.sfirst); r = np.diff(S.rowptr)
-    assert np.array_equal(np.diff(S.Loff), ((c + r + 1) & ~1) * c) and np.array_equal(np.diff(S.CBoff), r * r)
+    assert np.array_equal(np.diff(S.Loff), ((c + r + 1) & ~1) * c)
     assert len(np.unique(S.amap)) == len(S.amap) and S.amap.min() >= 0 and S.amap.max() < S.Loff[-1]
     h.close()
 
@@ -188,3 +188,33 @@ def test_forward_gather_lists_are_the_transpose_of_rel(pkg):
         assert np.all(np.diff(ch) > 0)
     # every entry belongs to the child it claims
     assert np.all((gsrc >= rowptr[gch]) & (gsrc < rowptr[gch + 1]))
+
+
+@pytest.mark.parametrize("gen,kw", [("sparse_qp", dict(n=4000, m_gen=2000)), ("pde_control", dict(N=12)),
+                                    ("chain", dict(nh=300)), ("elec", dict(n_p=10))])
+def test_update_block_storage_reuses_memory_without_overlap(pkg, gen, kw):
+    """CBoff comes from a level-lifetime allocator: block s is live on the levels
+    [level(s), level(parent(s))]; two blocks that are live on a common level must not overlap, and
+    the arena must not be larger than the prefix-sum layout."""
+    prob = getattr(pkg.problems, gen)(seed=3, **kw)
+    h = pkg.Handle(-1)
+    h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
+    sparent, rowptr, level, cboff = (h.symbolic(k) for k in ("sparent", "rowptr", "level", "CBoff"))
+    ns = len(sparent)
+    r = np.diff(rowptr)
+    total = int(h.info("cb_total"))
+    assert cboff[ns] == total and total <= int((r * r + 1).sum())
+    nlev = int(level.max()) + 1
+    live = [[] for _ in range(nlev)]
+    for s in range(ns):
+        p = sparent[s]
+        if p < 0 or r[s] == 0:
+            continue
+        assert cboff[s] >= 0 and cboff[s] + r[s] * r[s] <= total
+        for l in range(level[s], level[p] + 1):
+            live[l].append((int(cboff[s]), int(cboff[s] + r[s] * r[s])))
+    for l in range(nlev):
+        iv = sorted(live[l])
+        for (a0, a1), (b0, b1) in zip(iv, iv[1:]):
+            assert a1 <= b0, "update blocks live on level %d overlap" % l
+    h.close()
