@@ -127,7 +127,7 @@ constexpr int MID_PANEL = 12000;      // doubles
 constexpr int MIDL_PANEL = 26000;     // doubles
 constexpr int NB = 32;                // block-column width of the LDL' big-front path
 constexpr int WB = 128;               // block width of the Cholesky big-front path (DMMA)
-constexpr int OUTER_BLOCK = 2048;     // default outer block of the panel update (WB times a power of two)
+constexpr int OUTER_BLOCK = 4096;     // default outer block of the panel update (WB times a power of two)
 constexpr int XB = 2048;              // pivot blocks are inverted in diagonal blocks of this many columns
 
 // Per-level schedule built on the host from Symbolic.
