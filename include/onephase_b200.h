@@ -57,9 +57,14 @@ const char* opb_last_error(const opb_handle* h);
  * framework's current stream) instead of the handle's own stream. */
 int opb_set_stream(opb_handle* h, void* cuda_stream);
 
-/* Options (before opb_set_structure): "ordering" (4 auto = fewer flops of 0 and 3 [default],
- * 0 level-structure nested dissection + minimum-degree leaves, 1 natural, 3 METIS_NodeND),
- * "nd_leaf", "metis_max_n", "relax" (0/1), "relax_small", "attempts_per_sync", "graphs" (0/1). */
+/* Options.  Symbolic (before opb_set_structure): "ordering" (4 auto = fewer flops of 0 and 3
+ * [default], 0 level-structure nested dissection + minimum-degree leaves, 1 natural,
+ * 3 METIS_NodeND), "nd_leaf", "metis_max_n", "relax" (0/1), "relax_small".
+ * Numeric (any time): "attempts_per_sync" (delta-loop attempts enqueued per host
+ * synchronisation, default 2), "graphs" (0/1: replay the launch sequences from CUDA graphs),
+ * "outer_block" (columns of the outer block of the panel updates, 128 * 2^k, default 4096),
+ * "lookahead" (0/1: side-stream look-ahead in the blocked panel factorisation),
+ * "barrier_timeout_s" (sharded instance: seconds a rank waits for its peers, default 20). */
 int opb_set_option(opb_handle* h, const char* key, double value);
 /* Optional fill-reducing permutation supplied by the caller (0-based, perm[new] = old). */
 int opb_set_permutation(opb_handle* h, int64_t n, const int64_t* perm);

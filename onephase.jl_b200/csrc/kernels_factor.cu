@@ -362,9 +362,15 @@ cudaError_t factor_configure() {
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
                           int outer_block, const ShardCtx* shard, const SideStream* side, cudaStream_t st) {
+    bool prev_cross = false;
     for (const LevelPlan& L : plan) {
-        // sharded instance: the update blocks of children on other ranks must be complete
-        if (shard && L.barrier_before) launch_shard_barrier(*shard, st);
+        // Sharded instance: before a level with children on other ranks those children's update
+        // blocks must be complete; AFTER such a level nobody may go on before every rank has
+        // finished reading them, because the update-block arena reuses their memory from the
+        // next level on (symbolic.cpp, level-lifetime allocator).  The barrier that ends the
+        // attempt covers the last level.
+        if (shard && (L.barrier_before || prev_cross)) launch_shard_barrier(*shard, st);
+        prev_cross = L.barrier_before != 0;
         if (L.count[FC_T32]) {
             front_small_kernel<64><<<L.count[FC_T32], 64, small_smem(L.maxN[FC_T32]), st>>>(
                 S, d_sched + L.begin[FC_T32], Lval, CB, st_d);

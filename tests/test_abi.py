@@ -84,3 +84,18 @@ def test_host_mirror_state_machine(pkg):
     pars.kkt.linear_solver_type = "julia"
     with pytest.raises(ValueError, match="pick a valid solver"):
         pkg.pick_KKT_solver(pars)
+
+
+def test_options_are_validated(pkg):
+    """opb_set_option (include/onephase_b200.h): known keys are accepted on a host-only handle,
+    unknown keys are an error, outer_block is rounded to a multiple of the 128-column block."""
+    h = pkg.Handle(-1)
+    for key, v in (("ordering", 0), ("nd_leaf", 64), ("relax", 1), ("attempts_per_sync", 3), ("graphs", 0),
+                   ("outer_block", 1000), ("lookahead", 0), ("barrier_timeout_s", 2.5), ("metis_max_n", 1000)):
+        h.set_option(key, v)
+    with pytest.raises(pkg.OPBError):
+        h.set_option("no_such_option", 1)
+    prob = pkg.problems.chain(nh=30, seed=1)
+    h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
+    assert h.info("n") == prob.n
+    h.close()
