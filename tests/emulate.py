@@ -15,6 +15,8 @@ class Sym:
         self.amap = g("amap"); self.dpos = g("dpos"); self.Mp = g("Mp"); self.Mi = g("Mi")
         self.nsuper = len(self.sfirst) - 1
         self.nnzL = int(h.info("nnzL"))
+        self.cb_total = int(h.info("cb_total"))
+        self.gptr = g("gptr"); self.gsrc = g("gsrc")
 
 
 def assemble_M(h, Jx, Hx, y, s):
@@ -56,49 +58,63 @@ def factor(S, Mval, delta, mode="chol"):
     L = np.zeros(S.nnzL)
     L[S.amap] = Mval
     L[S.dpos] += delta
-    CB = {}
+    # update blocks live in ONE arena at CBoff (level-lifetime allocator, symbolic.cpp).  The device
+    # runs the supernodes of a level concurrently, so per level every front first READS its
+    # children's blocks and only then are the level's own blocks WRITTEN.
+    CB = np.full(max(S.cb_total, 1), np.nan)
     children = [[] for _ in range(S.nsuper)]
     for s in range(S.nsuper):
         if S.sparent[s] >= 0:
             children[S.sparent[s]].append(s)
-    order = np.argsort(S.level, kind="stable")
-    for s in order:
-        f = S.sfirst[s]; c = S.sfirst[s + 1] - f
-        r = S.rowptr[s + 1] - S.rowptr[s]; N = c + r
-        F = np.zeros((N, N))
-        ld = (N + 1) & ~1     # panel leading dimension (symbolic.h: panel_ld)
-        F[:, :c] = L[S.Loff[s]:S.Loff[s] + ld * c].reshape(c, ld).T[:N]
-        for ch in children[s]:
-            rel = S.rel[S.rowptr[ch]:S.rowptr[ch + 1]]
-            cb = CB.pop(ch)
-            idx = np.ix_(rel, rel)
-            F[idx] += np.tril(cb)
-        for j in range(c):
-            d = F[j, j]
-            if mode == "chol":
-                if not (d > 0):
-                    return False, L
-                ljj = np.sqrt(d)
-                F[j + 1:, j] /= ljj
-                F[j, j] = ljj
-                col = F[j + 1:, j]
-                F[j + 1:, j + 1:] -= np.tril(np.outer(col, col))
-            else:
-                if d == 0 or d != d:
-                    return False, L
-                w = F[j + 1:, j].copy()
-                F[j + 1:, j] = w / d
-                F[j + 1:, j + 1:] -= np.tril(np.outer(F[j + 1:, j], w))
-        P = np.zeros((ld, c)); P[:N] = F[:, :c]
-        L[S.Loff[s]:S.Loff[s] + ld * c] = P.T.reshape(-1)
-        CB[s] = F[c:, c:].copy()
+    nlev = int(S.level.max()) + 1 if S.nsuper else 0
+    by_level = [np.nonzero(S.level == l)[0] for l in range(nlev)]
+    for lev in by_level:
+        produced = []
+        for s in lev:
+            f = S.sfirst[s]; c = S.sfirst[s + 1] - f
+            r = S.rowptr[s + 1] - S.rowptr[s]; N = c + r
+            F = np.zeros((N, N))
+            ld = (N + 1) & ~1     # panel leading dimension (symbolic.h: panel_ld)
+            F[:, :c] = L[S.Loff[s]:S.Loff[s] + ld * c].reshape(c, ld).T[:N]
+            for ch in children[s]:
+                rel = S.rel[S.rowptr[ch]:S.rowptr[ch + 1]]
+                rc = len(rel)
+                cb = CB[S.CBoff[ch]:S.CBoff[ch] + rc * rc].reshape(rc, rc).T     # column-major, ld = rc
+                assert not np.isnan(np.tril(cb)).any(), "child update block was overwritten or never written"
+                idx = np.ix_(rel, rel)
+                F[idx] += np.tril(cb)
+            for j in range(c):
+                d = F[j, j]
+                if mode == "chol":
+                    if not (d > 0):
+                        return False, L
+                    ljj = np.sqrt(d)
+                    F[j + 1:, j] /= ljj
+                    F[j, j] = ljj
+                    col = F[j + 1:, j]
+                    F[j + 1:, j + 1:] -= np.tril(np.outer(col, col))
+                else:
+                    if d == 0 or d != d:
+                        return False, L
+                    w = F[j + 1:, j].copy()
+                    F[j + 1:, j] = w / d
+                    F[j + 1:, j + 1:] -= np.tril(np.outer(F[j + 1:, j], w))
+            P = np.zeros((ld, c)); P[:N] = F[:, :c]
+            L[S.Loff[s]:S.Loff[s] + ld * c] = P.T.reshape(-1)
+            if S.sparent[s] >= 0 and r > 0:
+                produced.append((s, F[c:, c:].copy()))
+        for s, blk in produced:
+            r = blk.shape[0]
+            CB[S.CBoff[s]:S.CBoff[s] + r * r] = blk.T.reshape(-1)
+        # a reused region now holds another block's values: the comparison of the resulting factor
+        # with the oracle (tests/test_symbolic.py) catches any clobbering of a live block
     return True, L
 
 
 def solve(S, L, b, mode="chol"):
     n = S.n
     x = b[S.perm].astype(float).copy()
-    u = {}
+    uflat = np.zeros(S.rowptr[-1])
     children = [[] for _ in range(S.nsuper)]
     for s in range(S.nsuper):
         if S.sparent[s] >= 0:
@@ -111,22 +127,18 @@ def solve(S, L, b, mode="chol"):
         ld = (N + 1) & ~1
         P = L[S.Loff[s]:S.Loff[s] + ld * c].reshape(c, ld).T[:N]
         panels[s] = P
-        us = np.zeros(r)
-        for ch in children[s]:
-            rel = S.rel[S.rowptr[ch]:S.rowptr[ch + 1]]
-            uc = u.pop(ch)
-            for t, dst in enumerate(rel):
-                if dst < c:
-                    x[f + dst] += uc[t]
-                else:
-                    us[dst - c] += uc[t]
+        # children's update vectors through the gather lists (gptr/gsrc), as fwd_kernel does
+        gb = S.rowptr[s] + f
+        acc = np.array([uflat[S.gsrc[S.gptr[gb + d]:S.gptr[gb + d + 1]]].sum() for d in range(N)])
+        x[f:f + c] += acc[:c]
+        us = acc[c:].copy()
         L11 = np.tril(P[:c, :c])
         if mode != "chol":
             L11 = np.tril(L11, -1) + np.eye(c)
         yv = np.linalg.solve(L11, x[f:f + c]) if c else x[f:f + c]
         x[f:f + c] = yv
         us -= P[c:, :c] @ yv
-        u[s] = us
+        uflat[S.rowptr[s]:S.rowptr[s + 1]] = us
     for s in order[::-1]:
         f = S.sfirst[s]; c = S.sfirst[s + 1] - f
         r = S.rowptr[s + 1] - S.rowptr[s]
