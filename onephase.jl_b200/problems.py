@@ -278,11 +278,13 @@ def grid_nd_perm(N, leaf=4):
 # ---------------------------------------------------------------------------
 # IPM-like sequence: same pattern, drifting (y, s), occasionally indefinite H
 # ---------------------------------------------------------------------------
-def ipm_sequence(prob: KKTProblem, steps=6, seed=0, indefinite_every=3, shift=5.0):
+def ipm_sequence(prob: KKTProblem, steps=6, seed=0, indefinite_every=3, shift=5.0, offdiag=0.0):
     """Yield KKTProblems sharing prob's sparsity pattern, mimicking outer
     iterations: s*y is driven towards a shrinking mu, J's values drift, and every
     `indefinite_every`-th iterate gets `shift` subtracted from H's stored diagonal
-    so the delta loop (delta_strategy.jl:37-114) has work to do.  delta_prev is
+    so the delta loop (delta_strategy.jl:37-114) has work to do; `offdiag` is added to H's stored
+    off-diagonal entries on those iterates instead (negative curvature the diagonal test of the
+    delta rule cannot see: the probe at delta = 0 fails and the x8 retries run).  delta_prev is
     left at 0; the caller threads the accepted delta through like one_phase.jl:205-206."""
     rng = np.random.default_rng(seed)
     y = prob.y.copy(); s = prob.s.copy()
@@ -291,6 +293,7 @@ def ipm_sequence(prob: KKTProblem, steps=6, seed=0, indefinite_every=3, shift=5.
     # positions of the stored diagonal entries of H (lower CSC: first entry of a column if row == col)
     cols = np.repeat(np.arange(prob.n), np.diff(H0.indptr))
     dpos = np.nonzero(H0.indices == cols)[0]
+    opos = np.nonzero(H0.indices != cols)[0]
     for t in range(steps):
         mu *= 0.3
         s = np.sqrt(s * (mu / y)) * np.exp(0.3 * rng.standard_normal(s.shape[0]))
@@ -299,6 +302,7 @@ def ipm_sequence(prob: KKTProblem, steps=6, seed=0, indefinite_every=3, shift=5.
         if indefinite_every and (t % indefinite_every) == indefinite_every - 1:
             H.data = H.data.copy()
             H.data[dpos] -= shift
+            H.data[opos] += offdiag
         J = prob.J.copy()
         J.data = prob.J.data * (1.0 + 0.01 * rng.standard_normal(J.nnz))
         yield KKTProblem("%s_it%d" % (prob.name, t), J, H, y.copy(), s.copy(),

@@ -158,3 +158,39 @@ def test_full_size_elec_dense(pkg):
 
 def test_mid_size_pde(pkg):
     _full_size_properties(pkg, pkg.problems.pde_control(40), expect_fac=1)
+
+
+def test_ipm_like_iterate_sequence(pkg, orc):
+    """Six outer iterations on ONE solver object: same sparsity pattern (one symbolic analysis),
+    drifting (J, y, s), every third iterate with an indefinite Hessian, the accepted delta threaded
+    through as delta_prev like one_phase.jl:205-206.  The (status, #fac, delta) sequence must equal
+    the oracle's and every direction must agree to 1e-10."""
+    base = pkg.problems.chain(nh=500, seed=1)
+    pars = pkg.Class_parameters()
+    k = pkg.pick_KKT_solver(pars)
+    k.initialize(pkg.Class_iterate(base.J, base.H, base.y, base.s))
+    delta_prev, perm, seq = 0.0, None, []
+    for t, prob in enumerate(pkg.problems.ipm_sequence(base, steps=6, seed=3, shift=0.0, offdiag=5.0)):
+        it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=delta_prev)
+        k.form_system(it)
+        if perm is None:
+            perm = k._h.symbolic("perm")
+        else:
+            assert np.array_equal(perm, k._h.symbolic("perm"))      # the analysis was reused
+        st, nf, delta = pkg.ipopt_strategy(it, k, pars)
+        Q, sd = orc.form_system(prob.J, prob.H, prob.y, prob.s)
+        QL = sp.tril(Q, format="csc"); QL.sort_indices()
+        F = orc.Factor(QL, perm)
+        st_o, nf_o, delta_o, tried = F.delta_loop(QL.data, sd, delta_prev)
+        assert (st, nf, delta) == (st_o, nf_o, delta_o), (t, (st, nf, delta), (st_o, nf_o, delta_o), tried)
+        seq.append(nf)
+        if st == "success":
+            r = prob.rhs[0]
+            k.kkt_associate_rhs(it, pkg.System_rhs(*r))
+            k.compute_direction()
+            dxo, dyo, dso, erro = F.direction(prob.J, prob.H, prob.y, prob.s, delta, *r)
+            for a, b in ((k.dir.x, dxo), (k.dir.y, dyo), (k.dir.s, dso)):
+                assert np.linalg.norm(a - b) <= REL_TOL * max(np.linalg.norm(b), 1e-300), t
+        delta_prev = delta
+    assert max(seq) > 1, "the sequence never exercised the delta loop: %r" % seq
+    k.finalize()
