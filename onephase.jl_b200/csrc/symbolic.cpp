@@ -12,6 +12,8 @@
 #include "symbolic.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <map>
 #include <cstring>
 #include <numeric>
@@ -235,7 +237,7 @@ void build_graph(int n, const std::vector<int64_t>& Mp, const std::vector<int>& 
 
 // Exact minimum degree on a small vertex set using bitset adjacency (elimination
 // graph model).  verts: global ids; reg[v]==rid marks membership.
-void md_small(const Graph& G, const std::vector<int>& verts, const std::vector<int>& reg, int rid,
+void md_small(const Graph& G, const std::vector<int>& verts, const int* reg, int rid,
               std::vector<int>& local, int* out) {
     const int k = (int)verts.size();
     if (k <= 2) { for (int t = 0; t < k; t++) out[t] = verts[t]; return; }
@@ -247,7 +249,7 @@ void md_small(const Graph& G, const std::vector<int>& verts, const std::vector<i
         int v = verts[t];
         for (int64_t p = G.xadj[v]; p < G.xadj[v + 1]; p++) {
             int u = G.adj[p];
-            if (reg[u] != rid) continue;
+            if (__atomic_load_n(&reg[u], __ATOMIC_RELAXED) != rid) continue;
             int lu = local[u];
             A[(size_t)t * W + (lu >> 6)] |= 1ull << (lu & 63);
         }
@@ -284,16 +286,23 @@ void md_small(const Graph& G, const std::vector<int>& verts, const std::vector<i
     }
 }
 
+// The two halves of a dissection are independent, so the upper levels of the recursion run on
+// several host threads.  Per-vertex arrays (reg, lvl, local) are shared: a task only writes the
+// entries of its own vertices; it may READ reg[] of a neighbour that a sibling task is relabelling,
+// but only to compare it with its own (unique) region id, so any value it sees gives the same
+// answer -- those accesses are relaxed atomics.  The result does not depend on the schedule.
 struct NDWork {
     const Graph* G;
-    std::vector<int> reg;      // region id of each vertex
-    std::vector<int> lvl;      // BFS level scratch
-    std::vector<int> queue;
-    std::vector<int> local;
-    int next_rid = 1;
+    int* reg;                  // region id of each vertex (shared)
+    int* lvl;                  // BFS level scratch (shared, own vertices only)
+    std::vector<int>* local_v; // md_small scratch, indexed by vertex (shared, own vertices only)
+    std::atomic<int>* next_rid;
+    std::vector<int> queue;    // per task
     int leaf;
-    int* perm;                 // output, new -> old
+    int* perm;                 // output, new -> old (disjoint ranges per task)
 };
+inline int reg_of(const NDWork& W, int v) { return __atomic_load_n(&W.reg[v], __ATOMIC_RELAXED); }
+inline void set_reg(NDWork& W, int v, int r) { __atomic_store_n(&W.reg[v], r, __ATOMIC_RELAXED); }
 
 // BFS inside region rid from root; fills W.queue (order) and W.lvl; returns #levels.
 int bfs(NDWork& W, int root, int rid, std::vector<int>& lptr) {
@@ -310,7 +319,7 @@ int bfs(NDWork& W, int root, int rid, std::vector<int>& lptr) {
         head++;
         for (int64_t p = G.xadj[v]; p < G.xadj[v + 1]; p++) {
             int u = G.adj[p];
-            if (W.reg[u] != rid || W.lvl[u] >= 0) continue;
+            if (reg_of(W, u) != rid || W.lvl[u] >= 0) continue;
             W.lvl[u] = cur + 1;
             W.queue.push_back(u);
         }
@@ -321,19 +330,22 @@ int bfs(NDWork& W, int root, int rid, std::vector<int>& lptr) {
 
 void order_fallback(NDWork& W, std::vector<int>& verts, int rid, int offset) {
     if ((int)verts.size() <= 2048) {
-        md_small(*W.G, verts, W.reg, rid, W.local, W.perm + offset);
+        md_small(*W.G, verts, W.reg, rid, *W.local_v, W.perm + offset);
     } else {
         std::sort(verts.begin(), verts.end());
         for (size_t t = 0; t < verts.size(); t++) W.perm[offset + t] = verts[t];
     }
 }
 
+constexpr int ND_PAR_DEPTH = 3;        // recursion levels that fork a host thread (up to 8 tasks)
+constexpr int ND_PAR_MIN = 20000;      // ... when both halves have at least this many vertices
+
 void nd_rec(NDWork& W, std::vector<int>& verts, int offset, int depth) {
     const Graph& G = *W.G;
     const int k = (int)verts.size();
     if (k == 0) return;
-    const int rid = W.next_rid++;
-    for (int v : verts) { W.reg[v] = rid; W.lvl[v] = -1; }
+    const int rid = W.next_rid->fetch_add(1);
+    for (int v : verts) { set_reg(W, v, rid); W.lvl[v] = -1; }
     if (k <= W.leaf || depth > 200) { order_fallback(W, verts, rid, offset); return; }
     // connected components
     std::vector<int> lptr;
@@ -363,9 +375,9 @@ void nd_rec(NDWork& W, std::vector<int>& verts, int offset, int depth) {
             while (pos < dust.size()) {
                 size_t end = std::min(dust.size(), pos + (size_t)std::max(W.leaf, 64));
                 std::vector<int> chunk(dust.begin() + pos, dust.begin() + end);
-                const int r2 = W.next_rid++;
-                for (int v : chunk) W.reg[v] = r2;
-                md_small(G, chunk, W.reg, r2, W.local, W.perm + off);
+                const int r2 = W.next_rid->fetch_add(1);
+                for (int v : chunk) set_reg(W, v, r2);
+                md_small(G, chunk, W.reg, r2, *W.local_v, W.perm + off);
                 off += (int)chunk.size();
                 pos = end;
             }
@@ -420,7 +432,7 @@ void nd_rec(NDWork& W, std::vector<int>& verts, int offset, int depth) {
         bool touches = false;
         for (int64_t p = G.xadj[v]; p < G.xadj[v + 1] && !touches; p++) {
             int u = G.adj[p];
-            if (W.reg[u] == rid && W.lvl[u] == best + 1) touches = true;
+            if (reg_of(W, u) == rid && W.lvl[u] == best + 1) touches = true;
         }
         if (touches) sep.push_back(v); else left.push_back(v);
     }
@@ -428,17 +440,25 @@ void nd_rec(NDWork& W, std::vector<int>& verts, int offset, int depth) {
     const int nl = (int)left.size(), nr = (int)right.size();
     // separator last
     std::sort(sep.begin(), sep.end());
-    for (size_t t = 0; t < sep.size(); t++) { W.perm[offset + nl + nr + t] = sep[t]; W.reg[sep[t]] = 0; }
-    nd_rec(W, left, offset, depth + 1);
-    nd_rec(W, right, offset + nl, depth + 1);
+    for (size_t t = 0; t < sep.size(); t++) { W.perm[offset + nl + nr + t] = sep[t]; set_reg(W, sep[t], 0); }
+    if (depth < ND_PAR_DEPTH && nl >= ND_PAR_MIN && nr >= ND_PAR_MIN) {
+        NDWork W2 = W;                 // shares the per-vertex arrays, own queue
+        W2.queue.clear();
+        std::thread th([&W2, &left, offset, depth] { nd_rec(W2, left, offset, depth + 1); });
+        nd_rec(W, right, offset + nl, depth + 1);
+        th.join();
+    } else {
+        nd_rec(W, left, offset, depth + 1);
+        nd_rec(W, right, offset + nl, depth + 1);
+    }
 }
 
 void nd_order(const Graph& G, int leaf, std::vector<int>& perm) {
+    std::vector<int> reg(G.n, 0), lvl(G.n, -1), local(G.n, 0);
+    std::atomic<int> next_rid{1};
     NDWork W;
     W.G = &G;
-    W.reg.assign(G.n, 0);
-    W.lvl.assign(G.n, -1);
-    W.local.assign(G.n, 0);
+    W.reg = reg.data(); W.lvl = lvl.data(); W.local_v = &local; W.next_rid = &next_rid;
     W.leaf = std::max(leaf, 4);
     perm.resize(G.n);
     W.perm = perm.data();
