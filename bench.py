@@ -431,14 +431,38 @@ def main():
             roofline = {"bound": "hbm", "kernel": "direction (3 x triangular solves + residuals)",
                         "achieved": dir_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dir_gbs / hbm_peak,
                         "traffic": None, "peak_source": hbm_src}
-        traffic = None
+        tr = {}
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")))
-            traffic = tr.get(args.workload, {}).get("factor_bytes_per_attempt" if roofline["bound"] == "tensor"
-                                                    else "direction_bytes")
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json"))).get(args.workload, {})
         except Exception:
             pass
-        roofline["traffic"] = traffic
+        roofline["traffic"] = tr.get("factor_bytes_per_attempt" if roofline["bound"] == "tensor" else "direction_bytes")
+        # the dominant KERNEL of a factorisation-bound step: CUDA events around its launches in one
+        # extra attempt (opb_profile_factor: plain launches, no look-ahead, so the timed kernels do
+        # not overlap anything); achieved = algorithmic flops it serves / its summed launch time
+        kernel_rooflines = {}
+        if roofline["bound"] == "tensor" and not sharded:
+            try:
+                pf = h.profile_factor(delta_res)
+                for kname, fl, ms, tkey in (("front_cb_kernel", pf["cb_flops"], pf["cb_ms"], "front_cb_bytes_per_attempt"),
+                                            ("chol_panel_update_kernel", pf["update_flops"], pf["update_ms"],
+                                             "panel_update_bytes_per_attempt")):
+                    if ms > 0:
+                        tf = fl / (ms * 1e-3) / 1e12
+                        kernel_rooflines[kname] = {"bound": "tensor", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                                                   "frac": tf / fp64_peak, "traffic": tr.get(tkey),
+                                                   "flops_per_attempt": fl, "ms_per_attempt": ms}
+                kernel_rooflines["attempt_ms_plain_launches"] = pf["total_ms"]
+                dom = max(("front_cb_kernel", "chol_panel_update_kernel"),
+                          key=lambda kk: kernel_rooflines.get(kk, {}).get("ms_per_attempt", 0.0))
+                if dom in kernel_rooflines:
+                    phase_roofline = roofline
+                    roofline = dict(kernel_rooflines[dom])
+                    roofline["kernel"] = dom + " (all its launches of one factorisation attempt; per-attempt sums)"
+                    roofline["peak_source"] = phase_roofline["peak_source"]
+                    roofline["share_of_step"] = roofline["ms_per_attempt"] * max(nf_res, 1) / tot
+            except Exception as e:      # the phase-level roofline stays
+                kernel_rooflines = {"error": str(e)[:200]}
         extra_rooflines = {
             "assembly": {"bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak},
             "factor": {"bound": "tensor", "achieved": fac_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fac_tflops / fp64_peak},
@@ -542,6 +566,7 @@ def main():
             "phases_ms": phases,
             "roofline": roofline,
             "rooflines_by_phase": extra_rooflines,
+            "rooflines_by_kernel": kernel_rooflines,
             "cpu_baseline": cpu,
             "other_workloads_kernels_only": others,
             "lib_launches_total": pkg.launch_count() - lib0,

@@ -127,6 +127,12 @@ int opb_delta_loop_resident(opb_handle* h, double delta_prev, double delta_zero,
                             double delta_max, double delta_start, double inc, double dec, int max_it);
 int opb_direction_resident(opb_handle* h, int n_refine);
 int opb_solve_resident(opb_handle* h, int nsolves);   /* triangular solves only, on the residual vector */
+/* One factorisation attempt at shift `delta` (like opb_factor) with CUDA events around every
+ * launch of the two FP64 tensor-pipe kernels: time of the whole attempt, summed time of the
+ * update-block kernel and of the panel-update kernel, and the algorithmic flops those kernels
+ * serve (for bench.py's per-kernel roofline).  Plain launches, no look-ahead stream. */
+int opb_profile_factor(opb_handle* h, double delta, double* total_ms, double* cb_ms, double* update_ms,
+                       double* cb_flops, double* update_flops, int* inertia_ok);
 /* blocks until the stream is idle and reads the controller state */
 int opb_sync_state(opb_handle* h, double* delta_out, int* num_fac_out, int* status_out, double* kkt_err_out);
 

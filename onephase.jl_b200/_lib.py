@@ -30,7 +30,7 @@ EXPORTS = [
     "opb_upload_values", "opb_upload_rhs", "opb_form_resident", "opb_delta_loop_resident",
     "opb_direction_resident", "opb_solve_resident", "opb_sync_state", "opb_get_info",
     "opb_get_symbolic", "opb_get_L_values", "opb_launch_count", "opb_version",
-    "opb_shard_init", "opb_shard_export", "opb_shard_attach",
+    "opb_shard_init", "opb_shard_export", "opb_shard_attach", "opb_profile_factor",
 ]
 SHARD_BLOB_BYTES = 320
 
@@ -89,6 +89,7 @@ def load():
     L.opb_shard_init.argtypes = [vp, ci, ci]
     L.opb_shard_export.argtypes = [vp, ctypes.c_char_p]
     L.opb_shard_attach.argtypes = [vp, ci, ctypes.c_char_p]
+    L.opb_profile_factor.argtypes = [vp, f64, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, c_intp]
     L.opb_launch_count.restype = ctypes.c_longlong
     L.opb_version.restype = ctypes.c_char_p
     _lib = L
@@ -261,6 +262,17 @@ class Handle:
 
     def solve_resident(self, nsolves=1):
         self.check(self.L.opb_solve_resident(self.h, nsolves))
+
+    def profile_factor(self, delta):
+        """One attempt with per-kernel CUDA-event timing (opb_profile_factor)."""
+        v = [ctypes.c_double() for _ in range(5)]
+        ok = ctypes.c_int()
+        self.check(self.L.opb_profile_factor(self.h, float(delta),
+                                             *[ctypes.cast(ctypes.byref(x), c_f64p) for x in v], ctypes.byref(ok)))
+        keys = ("total_ms", "cb_ms", "update_ms", "cb_flops", "update_flops")
+        out = {k: x.value for k, x in zip(keys, v)}
+        out["inertia_ok"] = ok.value
+        return out
 
     def sync_state(self):
         d = ctypes.c_double(); nf = ctypes.c_int(); st = ctypes.c_int(); err = np.empty(6)

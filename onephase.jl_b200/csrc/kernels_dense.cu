@@ -1057,7 +1057,7 @@ cudaError_t dense_configure() {
 
 void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
                             double* CB, double* Xinv, DeltaState* st_d, int outer_block, const SideStream* side,
-                            cudaStream_t st) {
+                            KernelTimer* timer, cudaStream_t st) {
     if (!L.wide_count) return;
     // medium fronts: panel in shared memory
     for (int fc = FC_MID; fc <= FC_MIDL; fc++) {
@@ -1085,7 +1085,9 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
             for (int J = 0; J < ncol && J < nrow; J++) tiles += nrow - J;
             if (tiles <= 0) return false;
             dim3 gu((unsigned)tiles, cnt2);
+            if (timer) cudaEventRecord(timer->next(1), sx);
             chol_panel_update_kernel<<<gu, GEMM_THREADS, sizeof(GemmSmem), sx>>>(S, list, Lval, k0, klen, cbeg, cend, st_d);
+            if (timer) cudaEventRecord(timer->next(1), sx);
             count_launch();
             return true;
         };
@@ -1136,7 +1138,9 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
     {
         const long long nt = (L.wide_maxR + 1 + BM - 1) / BM + 1;
         dim3 g((unsigned)(nt * (nt + 1) / 2), L.wide_count);
+        if (timer) cudaEventRecord(timer->next(0), st);
         front_cb_kernel<<<g, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, d_sched + L.wide_begin, Lval, CB, st_d);
+        if (timer) cudaEventRecord(timer->next(0), st);
         count_launch();
     }
 }

@@ -361,7 +361,8 @@ cudaError_t factor_configure() {
 
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
-                          int outer_block, const ShardCtx* shard, const SideStream* side, cudaStream_t st) {
+                          int outer_block, const ShardCtx* shard, const SideStream* side, KernelTimer* timer,
+                          cudaStream_t st) {
     bool prev_cross = false;
     for (const LevelPlan& L : plan) {
         // Sharded instance: before a level with children on other ranks those children's update
@@ -385,7 +386,7 @@ void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, c
         if (!L.wide_count) continue;
         if (mode == 0) {
             // Cholesky: panels in shared memory / blocked on the FP64 tensor pipe (kernels_dense.cu)
-            launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, outer_block, side, st);
+            launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, outer_block, side, timer, st);
             continue;
         }
         // LDL' fallback: scalar blocked path over every front that does not fit in shared memory

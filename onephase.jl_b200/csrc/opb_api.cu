@@ -213,6 +213,7 @@ struct opb_handle {
 
     SideStream side;                     // look-ahead stream of the blocked panel factorisation
     bool lookahead = true;
+    KernelTimer ktimer;                  // opb_profile_factor
 
     int fail(int code, const std::string& msg) { err = msg; return code; }
     int cuda_fail(cudaError_t e, const char* where) {
@@ -309,6 +310,7 @@ int opb_destroy(opb_handle* h) {
         h->red.release();
         h->drop_graphs();
         for (int p = 0; p < MAX_SHARD; p++) h->close_peer(p);
+        h->ktimer.release();
         if (h->side.stream) { cudaStreamSynchronize(h->side.stream); cudaStreamDestroy(h->side.stream); }
         if (h->side.fork) cudaEventDestroy(h->side.fork);
         if (h->side.join) cudaEventDestroy(h->side.join);
@@ -628,14 +630,14 @@ static int stage_form(opb_handle* h) {
     return OPB_OK;
 }
 
-static void enqueue_attempt_raw(opb_handle* h) {
+static void enqueue_attempt_raw(opb_handle* h, KernelTimer* timer = nullptr) {
     Bundle& B = *h->B;
     cudaStream_t st = h->stream;
     launch_ctl_begin(h->d_state, st);
     launch_scatter_fronts(h->Mval.p, B.d_amap.p, B.d_dpos.p, h->sdiag.p, h->Lval.p, B.S.nnzL,
                           B.Mp[B.S.n], B.S.n, h->d_state, 1, st);
     launch_factor_levels(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->Xinv.p, h->d_state, h->mode,
-                         h->outer_block, h->shard_ctx(), h->lookahead ? &h->side : nullptr, st);
+                         h->outer_block, h->shard_ctx(), (h->lookahead && !timer) ? &h->side : nullptr, timer, st);
     if (h->mode == OPB_MODE_CHOLESKY && B.trtri.count)
         launch_trtri(h->dev, B.trtri, B.d_sched.p, h->Lval.p, h->Xinv.p, h->Twork.p, h->d_state, st);
     // sharded: every rank learns about a failed pivot anywhere before the delta rule is applied
@@ -766,6 +768,49 @@ int opb_factor(opb_handle* h, double delta, int* inertia_ok) {
     int rc = need_device(h); if (rc) return rc;
     if (!h->B || h->ready == opb_handle::NOT_READY) return h->fail(OPB_ERR_STATE, "kkt solver not ready to factor (form_system first)");
     return single_factor(h, delta, OPB_MODE_CHOLESKY, inertia_ok);
+}
+
+int opb_profile_factor(opb_handle* h, double delta, double* total_ms, double* cb_ms, double* update_ms,
+                       double* cb_flops, double* update_flops, int* inertia_ok) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || h->ready == opb_handle::NOT_READY) return h->fail(OPB_ERR_STATE, "kkt solver not ready to factor (form_system first)");
+    if (h->sharded()) return h->fail(OPB_ERR_INVALID, "opb_profile_factor is not available on a sharded handle");
+    h->mode = OPB_MODE_CHOLESKY;
+    cudaStream_t st = h->stream;
+    KernelTimer& T = h->ktimer;
+    T.used = 0;
+    cudaEvent_t e0 = T.next(2), e1 = T.next(2);            // the whole attempt
+    launch_ctl_single(h->d_state, delta, OPB_MODE_CHOLESKY, st);
+    CK(cudaEventRecord(e0, st));
+    enqueue_attempt_raw(h, &T);                              // plain launches, no look-ahead: the timed kernels do not overlap
+    CK(cudaEventRecord(e1, st));
+    CK(cudaGetLastError());
+    rc = read_state(h); if (rc) return rc;
+    h->ready = opb_handle::FACTORED;
+    if (inertia_ok) *inertia_ok = (h->h_state.status == 1) ? 1 : 0;
+    float ms = 0.f;
+    double sum[2] = {0.0, 0.0};
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (total_ms) *total_ms = ms;
+    for (size_t p = 1; 2 * p + 1 < T.used; p++) {
+        CK(cudaEventElapsedTime(&ms, T.ev[2 * p], T.ev[2 * p + 1]));
+        if (T.kind[p] == 0 || T.kind[p] == 1) sum[T.kind[p]] += ms;
+    }
+    if (cb_ms) *cb_ms = sum[0];
+    if (update_ms) *update_ms = sum[1];
+    // algorithmic flops of the two kernels over the fronts they serve (MID, MIDL and BIG classes):
+    // update block r^2 c (lower half, multiply-add), panel updates N c^2 - 2 c^3 / 3 (BIG only)
+    double fcb = 0.0, fup = 0.0;
+    const Symbolic& S = h->B->S;
+    for (int s = 0; s < S.nsuper; s++) {
+        const double c = S.sfirst[s + 1] - S.sfirst[s], r = (double)(S.rowptr[s + 1] - S.rowptr[s]), N = c + r;
+        if (N <= SMALL_N) continue;
+        fcb += r * r * c;
+        if (!(c <= WB && N * c <= MIDL_PANEL)) fup += N * c * c - 2.0 * c * c * c / 3.0;
+    }
+    if (cb_flops) *cb_flops = fcb;
+    if (update_flops) *update_flops = fup;
+    return OPB_OK;
 }
 
 int opb_upload_rhs(opb_handle* h, const double* dual_r, const double* primal_r, const double* comp_r) {

@@ -174,11 +174,26 @@ struct SideStream {
     cudaEvent_t fork = nullptr, join = nullptr;
 };
 
+// Optional per-kernel timing of one factorisation attempt (opb_profile_factor): CUDA events
+// around every launch of the two tensor-pipe kernels, on the launching stream.
+struct KernelTimer {
+    std::vector<cudaEvent_t> ev;       // pairs (begin, end)
+    std::vector<int> kind;             // per pair: 0 = front_cb_kernel, 1 = chol_panel_update_kernel
+    size_t used = 0;
+    cudaEvent_t next(int k) {
+        if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+        if ((used & 1) == 0) { if (kind.size() <= used / 2) kind.push_back(k); else kind[used / 2] = k; }
+        return ev[used++];
+    }
+    void release() { for (cudaEvent_t e : ev) cudaEventDestroy(e); ev.clear(); kind.clear(); used = 0; }
+};
+
 // ---- kernels_factor.cu
 cudaError_t factor_configure();
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
-                          int outer_block, const ShardCtx* shard, const SideStream* side, cudaStream_t st);
+                          int outer_block, const ShardCtx* shard, const SideStream* side, KernelTimer* timer,
+                          cudaStream_t st);
 
 // ---- kernels_dense.cu  (Cholesky of big fronts on the FP64 tensor pipe, pivot-block inverses,
 //                         multi-CTA triangular solves for big supernodes)
@@ -192,7 +207,7 @@ cudaError_t dense_configure();
 // medium + big fronts of one level (Cholesky)
 void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
                             double* CB, double* Xinv, DeltaState* st_d, int outer_block, const SideStream* side,
-                            cudaStream_t st);
+                            KernelTimer* timer, cudaStream_t st);
 void launch_trtri(const DevSym& S, const TrtriPlan& T, const int* d_sched, const double* Lval,
                   double* Xinv, double* Twork, const DeltaState* st_d, cudaStream_t st);
 void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
