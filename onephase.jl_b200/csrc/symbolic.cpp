@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <system_error>
 #include <thread>
 #include <map>
 #include <cstring>
@@ -444,9 +445,16 @@ void nd_rec(NDWork& W, std::vector<int>& verts, int offset, int depth) {
     if (depth < ND_PAR_DEPTH && nl >= ND_PAR_MIN && nr >= ND_PAR_MIN) {
         NDWork W2 = W;                 // shares the per-vertex arrays, own queue
         W2.queue.clear();
-        std::thread th([&W2, &left, offset, depth] { nd_rec(W2, left, offset, depth + 1); });
+        std::thread th;
+        bool forked = true;
+        try {
+            th = std::thread([&W2, &left, offset, depth] { nd_rec(W2, left, offset, depth + 1); });
+        } catch (const std::system_error&) {
+            forked = false;            // no thread to be had: same work, serially
+        }
+        if (!forked) nd_rec(W, left, offset, depth + 1);
         nd_rec(W, right, offset + nl, depth + 1);
-        th.join();
+        if (forked) th.join();
     } else {
         nd_rec(W, left, offset, depth + 1);
         nd_rec(W, right, offset + nl, depth + 1);
