@@ -338,6 +338,7 @@ int opb_set_option(opb_handle* h, const char* key, double v) {
     if (!h || !key) return OPB_ERR_INVALID;
     std::string k(key);
     if (k == "nd_leaf") h->opt.nd_leaf = (int)v;
+    else if (k == "nd_balance") h->opt.nd_balance = v;
     else if (k == "ordering") h->opt.ordering = (int)v;
     else if (k == "relax") h->opt.relax_enable = (int)v;
     else if (k == "metis_max_n") h->opt.metis_max_n = (int)v;
@@ -524,8 +525,8 @@ static int alloc_numeric(opb_handle* h) {
 static std::string cache_key(const opb_handle* h, uint64_t h1, uint64_t h2) {
     const SymOptions& o = h->opt;
     char buf[200];
-    snprintf(buf, sizeof buf, "%d|%d|%d|%d|%d|%d|%d/%d|%016llx|%016llx", h->device, o.nd_leaf, o.ordering, o.metis_max_n,
-             o.relax_enable, h->user_perm.empty() ? 0 : 1, h->shard_rank, h->shard_world,
+    snprintf(buf, sizeof buf, "%d|%d|%.4f|%d|%d|%d|%d|%d/%d|%016llx|%016llx", h->device, o.nd_leaf, o.nd_balance, o.ordering,
+             o.metis_max_n, o.relax_enable, h->user_perm.empty() ? 0 : 1, h->shard_rank, h->shard_world,
              (unsigned long long)h1, (unsigned long long)h2);
     return buf;
 }

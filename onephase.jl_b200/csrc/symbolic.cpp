@@ -300,6 +300,7 @@ struct NDWork {
     std::atomic<int>* next_rid;
     std::vector<int> queue;    // per task
     int leaf;
+    double balance;            // a separator level must leave at least this fraction on either side
     int* perm;                 // output, new -> old (disjoint ranges per task)
 };
 inline int reg_of(const NDWork& W, int v) { return __atomic_load_n(&W.reg[v], __ATOMIC_RELAXED); }
@@ -412,7 +413,7 @@ void nd_rec(NDWork& W, std::vector<int>& verts, int offset, int depth) {
     int best = -1; int64_t bestsz = INT64_MAX;
     for (int l = 1; l + 1 < nlev; l++) {
         int left = lptr[l], sz = lptr[l + 1] - lptr[l], right = k - lptr[l + 1];
-        if (left < 0.3 * k || right < 0.3 * k) continue;
+        if (left < W.balance * k || right < W.balance * k) continue;
         if (sz < bestsz) { bestsz = sz; best = l; }
     }
     if (best < 0) {
@@ -461,13 +462,14 @@ void nd_rec(NDWork& W, std::vector<int>& verts, int offset, int depth) {
     }
 }
 
-void nd_order(const Graph& G, int leaf, std::vector<int>& perm) {
+void nd_order(const Graph& G, int leaf, double balance, std::vector<int>& perm) {
     std::vector<int> reg(G.n, 0), lvl(G.n, -1), local(G.n, 0);
     std::atomic<int> next_rid{1};
     NDWork W;
     W.G = &G;
     W.reg = reg.data(); W.lvl = lvl.data(); W.local_v = &local; W.next_rid = &next_rid;
     W.leaf = std::max(leaf, 4);
+    W.balance = std::min(0.45, std::max(0.05, balance));
     perm.resize(G.n);
     W.perm = perm.data();
     std::vector<int> all(G.n);
@@ -623,7 +625,7 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
     auto own_order = [&](std::vector<int>& out) {
         Graph G;
         build_graph(n, Mp, Mi, G);
-        nd_order(G, opt.nd_leaf, out);
+        nd_order(G, opt.nd_leaf, opt.nd_balance, out);
     };
     // factorisation flops (sum of squared column counts) of a candidate ordering
     auto flops_of = [&](const std::vector<int>& pm) {

@@ -90,7 +90,7 @@ def test_options_are_validated(pkg):
     """opb_set_option (include/onephase_b200.h): known keys are accepted on a host-only handle,
     unknown keys are an error, outer_block is rounded to a multiple of the 128-column block."""
     h = pkg.Handle(-1)
-    for key, v in (("ordering", 0), ("nd_leaf", 64), ("relax", 1), ("attempts_per_sync", 3), ("graphs", 0),
+    for key, v in (("ordering", 0), ("nd_leaf", 64), ("nd_balance", 0.35), ("relax", 1), ("attempts_per_sync", 3), ("graphs", 0),
                    ("outer_block", 1000), ("lookahead", 0), ("barrier_timeout_s", 2.5), ("metis_max_n", 1000)):
         h.set_option(key, v)
     with pytest.raises(pkg.OPBError):
