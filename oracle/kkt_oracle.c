@@ -531,3 +531,70 @@ void orc_direction(const orc_factor *F, i64 n, i64 m,
     free(S); free(sym_p); free(ym); free(tm); free(b); free(res); free(sol);
     free(jr); free(hr); free(tn);
 }
+
+/* ---------------------------------------------------------------------------
+ * Helper of oracle/supernodal.py (the multifrontal CPU baseline): extend-add of a child's
+ * update block (rc x rc, column-major, lower part) into its parent's front, split into the
+ * pivot-column panel P (N x c, leading dimension ldp) and the parent's own update block U
+ * (r x r, leading dimension r).  rel[t] = position of child row t inside the parent front.
+ * Plain index arithmetic: the dense algebra of that baseline runs in BLAS. */
+void orc_extend_add(double *P, i64 ldp, i64 c, double *U, i64 r, const i64 *rel, i64 rc, const double *cb) {
+    for (i64 u = 0; u < rc; u++) {
+        const i64 pj = rel[u];
+        const double *col = cb + u * rc;
+        if (pj < c) {
+            double *dst = P + pj * ldp;
+            for (i64 t = u; t < rc; t++) dst[rel[t]] += col[t];
+        } else {
+            double *dst = U + (pj - c) * r - c;
+            for (i64 t = u; t < rc; t++) dst[rel[t]] += col[t];
+        }
+    }
+}
+
+/* Supernodal triangular solves x <- (L L')^-1 x (x in the permuted order) for oracle/supernodal.py.
+ * Panels: supernode s has c = sfirst[s+1]-sfirst[s] pivot columns and r = rowptr[s+1]-rowptr[s]
+ * rows below them (global indices rowidx), stored column-major at L + Loff[s] with leading
+ * dimension ld = (c+r+1) & ~1.  u (length rowptr[ns]) is scratch for the update vectors;
+ * children of s are child_list[child_ptr[s] .. child_ptr[s+1]) in ascending order, rel maps a
+ * child's rows to positions of the parent front.  Column-oriented forward, row-oriented backward:
+ * every entry of L is read once per sweep (CHOLMOD's supernodal solve does the same with BLAS-2). */
+void orc_snode_solve(i64 ns, const i64 *sfirst, const i64 *rowptr, const i64 *rowidx, const i64 *rel,
+                     const i64 *Loff, const i64 *child_ptr, const i64 *child_list, const double *L,
+                     double *x, double *u) {
+    for (i64 s = 0; s < ns; s++) {
+        const i64 f = sfirst[s], c = sfirst[s + 1] - f, rp = rowptr[s], r = rowptr[s + 1] - rp;
+        const i64 N = c + r, ld = (N + 1) & ~(i64)1;
+        const double *P = L + Loff[s];
+        double *xs = x + f, *us = u + rp;
+        for (i64 t = 0; t < r; t++) us[t] = 0.0;
+        for (i64 k = child_ptr[s]; k < child_ptr[s + 1]; k++) {
+            const i64 ch = child_list[k], rpc = rowptr[ch], rc = rowptr[ch + 1] - rpc;
+            for (i64 t = 0; t < rc; t++) {
+                const i64 dst = rel[rpc + t];
+                if (dst < c) xs[dst] += u[rpc + t]; else us[dst - c] += u[rpc + t];
+            }
+        }
+        for (i64 j = 0; j < c; j++) {
+            const double *col = P + j * ld;
+            const double xj = xs[j] / col[j];
+            xs[j] = xj;
+            for (i64 i = j + 1; i < c; i++) xs[i] -= col[i] * xj;
+            for (i64 i = c; i < N; i++) us[i - c] -= col[i] * xj;
+        }
+    }
+    for (i64 s = ns - 1; s >= 0; s--) {
+        const i64 f = sfirst[s], c = sfirst[s + 1] - f, rp = rowptr[s], r = rowptr[s + 1] - rp;
+        const i64 N = c + r, ld = (N + 1) & ~(i64)1;
+        const double *P = L + Loff[s];
+        double *xs = x + f, *us = u + rp;
+        for (i64 t = 0; t < r; t++) us[t] = x[rowidx[rp + t]];
+        for (i64 j = c - 1; j >= 0; j--) {
+            const double *col = P + j * ld;
+            double acc = xs[j];
+            for (i64 i = j + 1; i < c; i++) acc -= col[i] * xs[i];
+            for (i64 i = c; i < N; i++) acc -= col[i] * us[i - c];
+            xs[j] = acc / col[j];
+        }
+    }
+}

@@ -60,6 +60,9 @@ def lib():
                                     _i64p, _i64p, _f64p, _i64p, _i64p, _f64p,
                                     _f64p, _f64p, ctypes.c_double, _f64p, _f64p, _f64p,
                                     ctypes.c_int, _f64p, _f64p, _f64p, _f64p]
+        L.orc_extend_add.argtypes = [_f64p, ctypes.c_int64, ctypes.c_int64, _f64p, ctypes.c_int64,
+                                     _i64p, ctypes.c_int64, _f64p]
+        L.orc_snode_solve.argtypes = [ctypes.c_int64] + [_i64p] * 7 + [_f64p, _f64p, _f64p]
         _LIB = L
     return _LIB
 

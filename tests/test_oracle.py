@@ -242,3 +242,36 @@ def test_golden_fixtures(pkg, orc):
         out = run_case(pkg, orc, CASES[name])
         for key in g.files:
             assert np.array_equal(np.asarray(out[key]), g[key], equal_nan=True), (name, key)
+
+
+@pytest.mark.parametrize("gen,kw,delta_prev", [("chain", dict(nh=120, offdiag_curv=5.0), 0.0),
+                                               ("chain", dict(nh=60, neg_curv=30.0), 1e-3),
+                                               ("sparse_qp", dict(n=2500, m_gen=1200), 0.0),
+                                               ("pde_control", dict(N=9), 0.0), ("elec", dict(n_p=15), 0.0)])
+def test_supernodal_cpu_baseline_matches_the_scalar_oracle(pkg, orc, gen, kw, delta_prev):
+    """oracle/supernodal.py (multifrontal + BLAS-3: the CPU baseline bench.py times with all host
+    cores) against oracle/kkt_oracle.c: identical (status, #fac, delta) sequence, solves and
+    directions within 1e-10."""
+    from oracle import supernodal
+    prob = getattr(pkg.problems, gen)(seed=4, **kw)
+    h = pkg.Handle(-1)
+    h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
+    Q, sd = orc.form_system(prob.J, prob.H, prob.y, prob.s)
+    QL = sp.tril(Q, format="csc"); QL.sort_indices()
+    F0 = orc.Factor(QL, h.symbolic("perm"))
+    F1 = supernodal.SupernodalFactor(QL, h)
+    st0, nf0, d0, tried0 = F0.delta_loop(QL.data, sd, delta_prev)
+    st1, nf1, d1, tried1 = F1.delta_loop(QL.data, sd, delta_prev)
+    assert (st0, nf0, d0) == (st1, nf1, d1), ((st0, nf0, d0), (st1, nf1, d1))
+    assert np.array_equal(tried0, tried1)
+    b = np.random.default_rng(0).standard_normal(prob.n)
+    x0, x1 = F0.solve(b), F1.solve(b)
+    assert np.linalg.norm(x0 - x1) <= 1e-9 * np.linalg.norm(x0)
+    for r in prob.rhs:
+        a = F0.direction(prob.J, prob.H, prob.y, prob.s, d0, *r)
+        c = F1.direction(prob.J, prob.H, prob.y, prob.s, d1, *r)
+        for u, v in zip(a[:3], c[:3]):
+            assert np.linalg.norm(u - v) <= 1e-10 * max(np.linalg.norm(u), 1e-300)
+        assert c[3][4] == pytest.approx(a[3][4], rel=1e-14)          # rhs norm
+        assert c[3][5] <= 10 * max(a[3][5], 1e-16)                   # N err
+    h.close()
