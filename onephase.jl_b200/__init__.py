@@ -12,4 +12,4 @@ The directory name contains a dot, so load it with __graft_entry__.package()
 from . import _lib, kkt, problems  # noqa: F401
 from ._lib import Handle, OPBError, build, launch_count  # noqa: F401
 from .kkt import (Class_iterate, Class_parameters, DistShard, Schur_B200_KKT_solver, System_rhs,  # noqa: F401
-                  ThreadShard, ipopt_strategy, linear_solver_B200, pick_KKT_solver)
+                  ThreadShard, ipopt_strategy, linear_solver_B200, pick_KKT_solver, respond_to_failed_step)

@@ -414,6 +414,28 @@ class ThreadShard:
         return out
 
 
+def respond_to_failed_step(it, kkt_solver, pars, old_delta, grad_lag_inf=None, response="lag_delta_inc"):
+    """The failure-driven delta increase of the outer loop (IPM/one_phase.jl:231-242): after a
+    failed line search the caller raises delta and refactorises ONCE (the inertia flag is ignored
+    there, `tot_num_fac += 1`).  `grad_lag_inf` = norm(eval_grad_lag(iter, mu), Inf), which lives
+    outside the path (the NLP); `old_delta` = get_delta(iter) before this outer iteration.
+    Returns (new_delta, inertia)."""
+    d = pars.delta
+    floor = max(d.start, old_delta * d.dec)
+    if response == "lag_delta_inc":
+        if grad_lag_inf is None:
+            raise ValueError("response_to_failure = :lag_delta_inc needs norm(grad L, Inf)")
+        dx_inf = float(np.abs(kkt_solver.dir.x).max())
+        new_delta = max(grad_lag_inf / dx_inf, get_delta(it) * d.inc, floor)
+    elif response == "default":
+        new_delta = max(get_delta(it) * d.inc, floor)
+    else:
+        raise ValueError("pars.test.response_to_failure parameter incorrectly set")      # one_phase.jl:238
+    set_delta(it, new_delta)
+    inertia = kkt_solver.factor(new_delta)       # factor!(kkt_solver, get_delta(iter), timer), one_phase.jl:241
+    return new_delta, inertia
+
+
 def pick_KKT_solver(pars, shard=None):
     """kkt_system_solver.jl:232-287 extended with the B200 symbols."""
     t, ls = pars.kkt.kkt_solver_type, pars.kkt.linear_solver_type

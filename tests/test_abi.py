@@ -99,3 +99,28 @@ def test_options_are_validated(pkg):
     h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
     assert h.info("n") == prob.n
     h.close()
+
+
+def test_failure_driven_delta_increase_rule(pkg):
+    """respond_to_failed_step = one_phase.jl:231-242: delta <- max(|grad L|/|dx|, 8 delta,
+    max(delta.start, delta_old/pi)) (or without the first term for :default), then ONE factor!."""
+    class FakeSolver:
+        def __init__(self):
+            self.dir = type("P", (), {"x": np.array([0.5, -2.0, 1.0])})()
+            self.calls = []
+
+        def factor(self, delta):
+            self.calls.append(delta)
+            return 1
+    pars = pkg.Class_parameters()
+    prob = pkg.problems.toy("toy_lp1")
+    it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=1e-3)
+    k = FakeSolver()
+    new, inertia = pkg.respond_to_failed_step(it, k, pars, old_delta=1e-4, grad_lag_inf=10.0)
+    assert new == max(10.0 / 2.0, 8e-3, max(1e-6, 1e-4 / np.pi)) == 5.0 and it.delta == 5.0
+    assert k.calls == [5.0] and inertia == 1
+    it.delta = 1e-3
+    new, _ = pkg.respond_to_failed_step(it, k, pars, old_delta=1.0, response="default")
+    assert new == max(8e-3, 1.0 / np.pi)
+    with pytest.raises(ValueError):
+        pkg.respond_to_failed_step(it, k, pars, old_delta=0.0, response="nonsense")
