@@ -1,0 +1,36 @@
+"""bench.py's reference arm (the CPU restatement timed on the host cores) runs without a GPU:
+check that it prints ONE JSON line with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_the_contract_line():
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c3_small",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "impl"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["higher_is_better"] is False and d["unit"] == "ms/iter"
+    assert d["config"]["workload"] == "c3_small" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "supernodal" in cb["sample"]
+
+
+def test_workload_table_is_consistent():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.DEFAULT_WORKLOAD in bench.WORKLOADS
+    import __graft_entry__ as g
+    pkg = g.package()
+    for name, (gen, kw, kws) in bench.WORKLOADS.items():
+        assert hasattr(pkg.problems, gen), name
+        assert set(kws) <= set(kw) | {"N", "n", "m_gen", "nh", "n_p"}
