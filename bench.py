@@ -10,8 +10,14 @@ One "step" = one outer IPM iteration's linear algebra on one synthetic instance
   e2e   : the same step through the reference-facing plugin API (host numpy
           buffers in, host buffers out: H2D of J/H values, y, s, rhs; D2H of
           schur_diag, dx, dy, ds, N err) -- the headline against --impl reference
-  --impl reference : the CPU restatement of the reference path (oracle/) on the
-          box's host cores, on a bounded sample of the same workload.
+  --impl reference : the CPU restatement of the reference path (oracle/snode.c +
+          oracle/supernodal.py: own METIS ordering, own symbolic analysis redone every step
+          like `linear_solver_recycle = false`, multifrontal Cholesky on the host BLAS with all
+          cores) on the SAME workload at FULL size, for as many steps as the time budget
+          allows (at least one).  That process never imports the product package.
+
+The same line carries the other BASELINE.json shapes (C2 chain, C3 sparse QP, C4 elec) with
+their own value / e2e / per-phase rooflines / full-size CPU baseline (`workloads`).
 
 Multi-GPU (torchrun): the path shards by instance -- one independent solve per GPU,
 no data-path collective ("replicas", scaling = weak).  value = wall ms / (N * K).  The same
@@ -33,23 +39,28 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as graft  # noqa: E402
 
 WORKLOADS = {
-    # name: (generator, kwargs, cpu-sample kwargs)
-    "c3_sparse_qp_n200k": ("sparse_qp", dict(n=200_000, m_gen=100_000), dict(n=50_000, m_gen=25_000)),
+    # name: (generator in tests/problems.py, kwargs, kwargs of the bounded CPU sample of the b200 arm's cpu_baseline leg)
+    "c3_sparse_qp_n200k": ("sparse_qp", dict(n=200_000, m_gen=100_000), dict(n=200_000, m_gen=100_000)),
     "c2_chain_n100k": ("chain", dict(nh=25_000), dict(nh=25_000)),
     "c4_elec_n1200": ("elec", dict(n_p=400), dict(n_p=400)),
     "c5_pde_100": ("pde_control", dict(N=100), dict(N=56)),
-    "c5_pde_60": ("pde_control", dict(N=60), dict(N=24)),
-    "c5_pde_40": ("pde_control", dict(N=40), dict(N=24)),
+    "c5_pde_60": ("pde_control", dict(N=60), dict(N=40)),
+    "c5_pde_40": ("pde_control", dict(N=40), dict(N=40)),
     "c3_small": ("sparse_qp", dict(n=20_000, m_gen=10_000), dict(n=20_000, m_gen=10_000)),
 }
 DEFAULT_WORKLOAD = "c5_pde_100"
+OTHER_WORKLOADS = ("c2_chain_n100k", "c3_sparse_qp_n200k", "c4_elec_n1200")
 N_DIRECTIONS = 2
 N_REFINE = 3
+REFERENCE_BUDGET_S = 200.0       # --impl reference: timed steps stop once this much wall time is spent
 
 
-def make_problem(pkg, workload, seed, sample=False):
+def make_problem(workload, seed, sample=False, override=None):
     gen, kw, kws = WORKLOADS[workload]
-    return getattr(pkg.problems, gen)(seed=seed, **(kws if sample else kw))
+    args = dict(kws if sample else kw)
+    if override:
+        args.update(override)
+    return getattr(graft.problems(), gen)(seed=seed, **args)
 
 
 class ClockSampler(threading.Thread):
@@ -133,65 +144,258 @@ def measure_fp64_peak(torch, dev):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def cpu_iteration(orc, pkg, prob, hs):
-    """One step of the CPU baseline: oracle/supernodal.py, the multifrontal restatement of the
-    reference path with BLAS-3 dense kernels on all host cores (the performance class of the
-    CHOLMOD supernodal factorisation behind julia.jl:34); assembly by oracle/kkt_oracle.c.  `hs` is a
-    host-only handle holding the symbolic analysis; its cost is added per step by the caller
-    (the reference analyses on every call: linear_solver_recycle=false)."""
+# ---------------------------------------------------------------------------
+# CPU side (oracle/ only -- nothing of the product is used here)
+# ---------------------------------------------------------------------------
+CPU_NOTE = ("oracle/snode.c + supernodal.py: own METIS_NodeND ordering + elimination tree / column counts / relaxed "
+            "supernodes redone every step (the reference analyses on every ls_factor!: recycle=false), multifrontal "
+            "Cholesky with dpotrf/dtrsm/dsyrk fronts and dtrsv/dgemv solves on scipy's OpenBLAS, scipy sparse "
+            "products, assembly by oracle/kkt_oracle.c")
+
+
+def cpu_iteration(prob, threads=None):
+    """One step of the CPU baseline (form_system! -> ipopt_strategy! -> 2 x compute_direction!)."""
     import scipy.sparse as sp
+    from oracle import oracle as orc
     from oracle import supernodal
+    with supernodal.blas_threads(threads):
+        t0 = time.perf_counter()
+        Q, sd = orc.form_system(prob.J, prob.H, prob.y, prob.s)
+        QL = sp.tril(Q, format="csc"); QL.sort_indices()
+        t1 = time.perf_counter()
+        F = supernodal.SupernodalFactor(QL, ordering="metis")
+        t2 = time.perf_counter()
+        st, nf, delta, _ = F.delta_loop(QL.data, sd, prob.delta_prev)
+        t3 = time.perf_counter()
+        err = None
+        for r in prob.rhs[:N_DIRECTIONS]:
+            err = F.direction(prob.J, prob.H, prob.y, prob.s, delta, *r, n_refine=N_REFINE)[3]
+        t4 = time.perf_counter()
+    return dict(form_ms=(t1 - t0) * 1e3, analysis_ms=(t2 - t1) * 1e3, factor_ms=(t3 - t2) * 1e3,
+                direction_ms=(t4 - t3) * 1e3, total_ms=(t4 - t0) * 1e3, num_fac=nf, delta=delta,
+                N_err=float(err[5]) if err is not None else None, flops=F.info("flops"),
+                nnz_L=int(F.info("nnzL_true")), factor_gflops=F.info("flops") * nf / max(t3 - t2, 1e-9) / 1e9)
+
+
+def cpu_memory_estimate_bytes(workload_args, gen):
+    """Host memory the full-size CPU step needs (factor + update-block stack + matrices): 36 GB peak
+    measured for pde N = 100 (METIS fill: nnz(L) = 3.6e9 with the relaxation zeros), ~ N^4 scaling."""
+    if gen != "pde_control":
+        return 4e9
+    return 36e9 * (workload_args["N"] / 100.0) ** 4 + 4e9
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    assert "onephase_jl_b200" not in sys.modules
+    gen, kw, _ = WORKLOADS[args.workload]
+    name, override, same_config = args.workload, None, True
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64e9
+    if gen == "pde_control" and cpu_memory_estimate_bytes(kw, gen) > 0.85 * avail:
+        for N in (80, 64, 56, 40):
+            if N < kw["N"] and cpu_memory_estimate_bytes(dict(N=N), gen) <= 0.85 * avail:
+                override = dict(N=N); name = "c5_pde_%d_sample" % N; same_config = False
+                break
+    prob = make_problem(args.workload, seed=0, override=override)
+    cores = os.cpu_count() or 1
+    budget = float(os.environ.get("OPB_REFERENCE_BUDGET_S", REFERENCE_BUDGET_S))
+    t_start = time.perf_counter()
+    times, runs, warm_done = [], [], 0
+    # The first step always runs.  It is a warm-up step only when the whole schedule (W + K steps at
+    # that cost) fits the budget; otherwise it is too expensive to discard and counts as the first
+    # timed step, and further steps run while the budget lasts.
     t0 = time.perf_counter()
-    Q, sd = orc.form_system(prob.J, prob.H, prob.y, prob.s)
-    QL = sp.tril(Q, format="csc"); QL.sort_indices()
-    t1 = time.perf_counter()
-    F = supernodal.SupernodalFactor(QL, hs)
-    st, nf, delta, _ = F.delta_loop(QL.data, sd, prob.delta_prev)
-    t2 = time.perf_counter()
-    for r in prob.rhs[:N_DIRECTIONS]:
-        F.direction(prob.J, prob.H, prob.y, prob.s, delta, *r, n_refine=N_REFINE)
-    t3 = time.perf_counter()
-    return dict(form_ms=(t1 - t0) * 1e3, factor_ms=(t2 - t1) * 1e3, direction_ms=(t3 - t2) * 1e3,
-                total_ms=(t3 - t0) * 1e3, num_fac=nf)
+    r = cpu_iteration(prob, cores)
+    first_s = time.perf_counter() - t0
+    if args.warmup >= 1 and first_s * (args.warmup + args.steps) <= budget:
+        warm_done = 1
+        while warm_done < args.warmup:
+            cpu_iteration(prob, cores); warm_done += 1
+    else:
+        times.append(r["total_ms"]); runs.append(r)
+    while len(times) < args.steps and (not times or time.perf_counter() - t_start + 1.1 * first_s <= budget):
+        r = cpu_iteration(prob, cores)
+        times.append(r["total_ms"]); runs.append(r)
+    ms = float(np.mean(times))
+    last = runs[-1]
+    sample = ("%s(%s), full size, %d timed step(s) of %d requested within a %.0f s budget: %s"
+              % (gen, override or kw, len(times), args.steps, budget, CPU_NOTE))
+    out = {"metric": "kkt_factor_solve_ms_per_iter", "value": ms, "unit": "ms/iter", "n_gpus": args.gpus,
+           "steps": len(times), "warmup": warm_done, "steps_requested": args.steps, "warmup_requested": args.warmup,
+           "ms_per_step": ms, "higher_is_better": False,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+           "same_config": same_config,
+           "config": {"workload": name, "generator": gen, "generator_args": override or kw,
+                      "n": int(prob.n), "m": int(prob.m), "nnz_J": int(prob.J.nnz),
+                      "directions_per_iter": N_DIRECTIONS, "refine": N_REFINE, "num_fac": last["num_fac"],
+                      "delta": last["delta"], "N_err": last["N_err"], "factor_flops": last["flops"], "nnz_L": last["nnz_L"],
+                      "instances": 1, "parallelism": "one instance on the host cores (BLAS threads = %d)" % cores},
+           "cpu_baseline": {"value": ms, "unit": "ms/iter", "cores": cores, "kind": "port", "sample": sample,
+                            "breakdown_ms": {k: last[k] for k in ("form_ms", "analysis_ms", "factor_ms", "direction_ms")},
+                            "factor_gflops": last["factor_gflops"]},
+           "e2e": {"value": ms, "unit": "ms/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
 
 
-CPU_SAMPLE_NOTE = ("oracle/supernodal.py: multifrontal Cholesky with LAPACK/BLAS-3 fronts (dpotrf, dtrsm, dsyrk on all host "
-                   "cores), C supernodal solves, scipy products; symbolic analysis redone per call like the reference "
-                   "(recycle=false)")
+# ---------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------
+def pin_problem(torch, prob):
+    """The e2e leg copies its inputs from PINNED host memory every step (a Julia Vector{Float64} is
+    pageable: `e2e_pageable` times the same step from ordinary numpy buffers)."""
+    import scipy.sparse as sp
+
+    def pinned(a):
+        t = torch.empty(a.shape[0], dtype=torch.float64, pin_memory=True)
+        v = t.numpy(); v[:] = a
+        return v
+    prob.J = sp.csc_matrix((pinned(prob.J.data), prob.J.indices, prob.J.indptr), shape=prob.J.shape)
+    prob.H = sp.csc_matrix((pinned(prob.H.data), prob.H.indices, prob.H.indptr), shape=prob.H.shape)
+    prob.y = pinned(prob.y); prob.s = pinned(prob.s)
+    prob.rhs = [tuple(pinned(v) for v in r) for r in prob.rhs]
+    return prob
+
+
+class Instance:
+    """One KKT instance bound to a solver object (the plugin API) on the current torch stream."""
+
+    def __init__(self, pkg, torch, prob, local, opts=(), shard=None):
+        self.pkg, self.torch, self.prob = pkg, torch, prob
+        self.pars = pkg.Class_parameters(device=local)
+        self.it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=prob.delta_prev)
+        self.k = pkg.pick_KKT_solver(self.pars, shard=shard)
+        self.k.initialize(self.it)
+        self.k._h.set_stream(torch.cuda.current_stream().cuda_stream)
+        for kv in opts:
+            key, val = kv.split("=")
+            self.k._h.set_option(key, float(val))
+        t0 = time.perf_counter()
+        self.k.form_system(self.it)              # symbolic analysis happens here, once
+        self.t_symbolic = time.perf_counter() - t0
+        self.h = self.k._h
+        self.rhs = [pkg.System_rhs(*r) for r in prob.rhs[:N_DIRECTIONS]]
+        d = self.pars.delta
+        self.dl_args = (prob.delta_prev, d.zero, d.min, d.max, d.start, d.inc, d.dec, 500)
+
+    def e2e_step(self):
+        k, it = self.k, self.it
+        k.form_system(it)
+        st, nf, delta = self.pkg.ipopt_strategy(it, k, self.pars)
+        for r in self.rhs:
+            k.kkt_associate_rhs(it, r)
+            k.compute_direction()
+        return nf, delta
+
+    def make_resident(self):
+        p = self.prob
+        self.h.upload_values(p.J.data, p.H.data, p.y, p.s)
+        self.h.upload_rhs(*p.rhs[0])
+
+    def resident_step(self):
+        h = self.h
+        h.form_resident()
+        h.delta_loop_resident(*self.dl_args)
+        for _ in range(N_DIRECTIONS):
+            h.direction_resident(N_REFINE)
+
+    def bytes_per_step(self):
+        p = self.prob
+        n, m = p.n, p.m
+        h2d = 8 * (p.J.nnz + p.H.nnz + 2 * m) + N_DIRECTIONS * 8 * (n + 2 * m)
+        d2h = 8 * n + 8 + N_DIRECTIONS * (8 * (n + 2 * m) + 48) + 3 * 8
+        return int(h2d), int(d2h)
+
+    def close(self):
+        self.k.finalize()
+
+
+def timed_events(torch, fn, reps, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def phase_rooflines(torch, inst, reps, hbm_peak, fp64_peak, nf):
+    """CUDA-event time of each phase and its algorithmic bytes / flops against the measured peaks."""
+    h = inst.h
+    cnt = algorithmic_counts(h)
+    ph = {"form_ms": timed_events(torch, h.form_resident, reps),
+          "factor_ms": timed_events(torch, lambda: h.delta_loop_resident(*inst.dl_args), reps) / max(nf, 1),
+          "direction_ms": timed_events(torch, lambda: h.direction_resident(N_REFINE), reps),
+          "solve_pair_ms": timed_events(torch, lambda: h.solve_resident(1), reps)}
+    fac_tflops = cnt["F_chol"] / (ph["factor_ms"] * 1e-3) / 1e12
+    fac_gbs = cnt["B_fac"] / (ph["factor_ms"] * 1e-3) / 1e9
+    asm_gbs = cnt["B_asm"] / (ph["form_ms"] * 1e-3) / 1e9
+    solve_gbs = cnt["B_solve"] / (ph["solve_pair_ms"] * 1e-3) / 1e9
+    dir_gbs = cnt["B_dir"] / (ph["direction_ms"] * 1e-3) / 1e9
+    rl = {
+        "assembly": {"bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak,
+                     "algorithmic_bytes": cnt["B_asm"]},
+        "factor": {"bound": "tensor", "achieved": fac_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                   "frac": fac_tflops / fp64_peak, "algorithmic_flops": cnt["F_chol"],
+                   "hbm_view": {"achieved": fac_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": fac_gbs / hbm_peak,
+                                "algorithmic_bytes": cnt["B_fac"]}},
+        "solve_pair": {"bound": "hbm", "achieved": solve_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": solve_gbs / hbm_peak,
+                       "algorithmic_bytes": cnt["B_solve"]},
+        "direction": {"bound": "hbm", "achieved": dir_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dir_gbs / hbm_peak,
+                      "algorithmic_bytes": cnt["B_dir"]},
+    }
+    return ph, rl, cnt
+
+
+def measure_other_workload(pkg, torch, wname, local, hbm_peak, fp64_peak, cpu=True, steps=5):
+    """value / e2e / per-phase rooflines / full-size CPU baseline of one of the other BASELINE shapes."""
+    prob = pin_problem(torch, make_problem(wname, seed=0))
+    inst = Instance(pkg, torch, prob, local)
+    for _ in range(3):
+        inst.e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        inst.e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    inst.make_resident()
+    ms = timed_events(torch, inst.resident_step, steps, warm=3)
+    d2, nf2, st2, err2 = inst.h.sync_state()
+    ph, rl, cnt = phase_rooflines(torch, inst, 3, hbm_peak, fp64_peak, nf2)
+    h2d, d2h = inst.bytes_per_step()
+    out = {"value": ms, "unit": "ms/iter", "e2e": {"value": e2e_ms, "unit": "ms/iter", "h2d_bytes_per_step": h2d,
+                                                    "d2h_bytes_per_step": d2h},
+           "n": prob.n, "m": prob.m, "num_fac": nf2, "delta": d2, "N_err": float(err2[5]),
+           "factor_flops": inst.h.info("flops"), "nnz_L": int(inst.h.info("nnzL_true")),
+           "phases_ms": ph, "rooflines_by_phase": rl, "symbolic_s_once": inst.t_symbolic}
+    inst.close()
+    if cpu:
+        try:
+            r = cpu_iteration(make_problem(wname, seed=0), os.cpu_count())
+            out["cpu_baseline"] = {"value": r["total_ms"], "unit": "ms/iter", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": "full size, 1 iteration: " + CPU_NOTE, "breakdown_ms": r}
+        except Exception as e:
+            out["cpu_baseline"] = {"error": str(e)[:200]}
+    return out
 
 
 def measure_sharded(pkg, torch, dist, args, local, world, workload):
     """ONE instance of `workload` over all `world` GPUs: subtrees of the elimination
     tree mapped to ranks, top separators pulling their children's update blocks over NVLink.
     Every rank makes the same calls with the same data; time = max over ranks (CUDA events)."""
-    prob = make_problem(pkg, workload, seed=0)
-    pars = pkg.Class_parameters(device=local)
-    it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=prob.delta_prev)
-    k = pkg.pick_KKT_solver(pars, shard=pkg.DistShard())
-    k.initialize(it)
-    stream = torch.cuda.current_stream()
-    k._h.set_stream(stream.cuda_stream)
-    for kv in args.opt:
-        key, val = kv.split("=")
-        k._h.set_option(key, float(val))
-    k.form_system(it)
-    h = k._h
-    d = pars.delta
-    dl_args = (prob.delta_prev, d.zero, d.min, d.max, d.start, d.inc, d.dec, 500)
-    rhs = [pkg.System_rhs(*r) for r in prob.rhs[:N_DIRECTIONS]]
-
-    def e2e_step():
-        k.form_system(it)
-        pkg.ipopt_strategy(it, k, pars)
-        for r in rhs:
-            k.kkt_associate_rhs(it, r)
-            k.compute_direction()
-
-    def resident_step():
-        h.form_resident()
-        h.delta_loop_resident(*dl_args)
-        for _ in range(N_DIRECTIONS):
-            h.direction_resident(N_REFINE)
+    prob = make_problem(workload, seed=0)
+    inst = Instance(pkg, torch, prob, local, args.opt, shard=pkg.DistShard())
+    h = inst.h
 
     def timed(fn, reps, warm):
         for _ in range(warm):
@@ -206,18 +410,16 @@ def measure_sharded(pkg, torch, dist, args, local, world, workload):
         return a.elapsed_time(b) / reps
 
     steps = max(2, min(args.steps, 5))
-    e2e_step()
-    t0 = time.perf_counter()
+    inst.e2e_step()
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
-        e2e_step()
+        inst.e2e_step()
     dist.barrier(); torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
-    h.upload_values(prob.J.data, prob.H.data, prob.y, prob.s)
-    h.upload_rhs(*prob.rhs[0])
-    ms = timed(resident_step, steps, 2)
-    fac = timed(lambda: h.delta_loop_resident(*dl_args), 2, 0)
+    inst.make_resident()
+    ms = timed(inst.resident_step, steps, 2)
+    fac = timed(lambda: h.delta_loop_resident(*inst.dl_args), 2, 0)
     sol = timed(lambda: h.solve_resident(1), 3, 1)
     delta_res, nf_res, st_res, kkt_err = h.sync_state()
     t = torch.tensor([ms, e2e_ms, fac, sol], device=torch.device("cuda", local), dtype=torch.float64)
@@ -233,38 +435,8 @@ def measure_sharded(pkg, torch, dist, args, local, world, workload):
            "how": "subtree-to-GPU mapping by factorisation flops; update blocks, forward update vectors and the "
                   "solution cross GPUs through peer-mapped HBM (CUDA IPC over NVLink) inside the consuming kernels; "
                   "flag barriers on the stream; no collective in the data path"}
-    k.finalize()
+    inst.close()
     return out
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    pkg = graft.package(); orc = graft.oracle()
-    prob = make_problem(pkg, args.workload, seed=0, sample=True)
-    hs = pkg.Handle(-1)
-    t0 = time.perf_counter()
-    hs.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
-    t_order = time.perf_counter() - t0
-    times = []
-    for i in range(args.warmup + args.steps):
-        r = cpu_iteration(orc, pkg, prob, hs)
-        if i >= args.warmup:
-            times.append(r["total_ms"] + t_order * 1e3)
-    ms = float(np.mean(times))
-    gen, kw, kws = WORKLOADS[args.workload]
-    sample = "%s%s: %s; analysis %.0f ms per call included" % (gen, kws, CPU_SAMPLE_NOTE, t_order * 1e3)
-    cores = os.cpu_count()
-    out = {"metric": "kkt_factor_solve_ms_per_iter", "value": ms, "unit": "ms/iter", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-           "config": {"workload": args.workload, "sample": kws, "directions_per_iter": N_DIRECTIONS,
-                      "refine": N_REFINE},
-           "cpu_baseline": {"value": ms, "unit": "ms/iter", "cores": cores, "kind": "port", "sample": sample},
-           "e2e": {"value": ms, "unit": "ms/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0}
-    print(json.dumps(out))
 
 
 def main():
@@ -275,7 +447,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the kernels-only timings of the other BASELINE shapes")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE shapes")
     ap.add_argument("--phase-repeat", type=int, default=3)
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
                     help="library tuning option passed to opb_set_option (e.g. outer_block=1024)")
@@ -307,34 +479,11 @@ def main():
 
     sharded = bool(args.shard and world > 1)
     # replicas: one independent instance per GPU;  --shard: the SAME instance on every rank
-    prob = make_problem(pkg, args.workload, seed=0 if sharded else rank)
-    # the e2e leg copies its inputs from PINNED host memory every step
-    def pinned(a):
-        t = torch.empty(a.shape[0], dtype=torch.float64, pin_memory=True)
-        v = t.numpy(); v[:] = a
-        return v
-    import scipy.sparse as sp
-    prob.J = sp.csc_matrix((pinned(prob.J.data), prob.J.indices, prob.J.indptr), shape=prob.J.shape)
-    prob.H = sp.csc_matrix((pinned(prob.H.data), prob.H.indices, prob.H.indptr), shape=prob.H.shape)
-    prob.y = pinned(prob.y); prob.s = pinned(prob.s)
-    prob.rhs = [tuple(pinned(v) for v in r) for r in prob.rhs]
-    pars = pkg.Class_parameters(device=local)
-    it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=prob.delta_prev)
-    k = pkg.pick_KKT_solver(pars, shard=pkg.DistShard() if sharded else None)
-    k.initialize(it)
-    stream = torch.cuda.current_stream()
-    k._h.set_stream(stream.cuda_stream)
-    for kv in args.opt:
-        key, val = kv.split("=")
-        k._h.set_option(key, float(val))
-    t0 = time.perf_counter()
-    k.form_system(it)                                           # symbolic analysis happens here, once
-    t_symbolic = time.perf_counter() - t0
-    h = k._h
+    prob = pin_problem(torch, make_problem(args.workload, seed=0 if sharded else rank))
+    inst = Instance(pkg, torch, prob, local, args.opt, shard=pkg.DistShard() if sharded else None)
+    h = inst.h
     cnt = algorithmic_counts(h)
-    rhs = [pkg.System_rhs(*r) for r in prob.rhs[:N_DIRECTIONS]]
-    d = pars.delta
-    dl_args = (prob.delta_prev, d.zero, d.min, d.max, d.start, d.inc, d.dec, 500)
+    n, m = prob.n, prob.m
 
     def barrier():
         if world > 1:
@@ -342,47 +491,29 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- e2e: plugin API with host buffers ----------------
-    def e2e_step():
-        k.form_system(it)
-        st, nf, delta = pkg.ipopt_strategy(it, k, pars)
-        for r in rhs:
-            k.kkt_associate_rhs(it, r)
-            k.compute_direction()
-        return nf, delta
-
     e2e_ms = float("nan")
     if not args.ncu:
         for _ in range(args.warmup):
-            nf, delta = e2e_step()
+            nf, delta = inst.e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            nf, delta = e2e_step()
+            nf, delta = inst.e2e_step()
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    n, m = prob.n, prob.m
-    h2d = 8 * (prob.J.nnz + prob.H.nnz + 2 * m) + N_DIRECTIONS * 8 * (n + 2 * m)
-    d2h = 8 * n + 8 + N_DIRECTIONS * (8 * (n + 2 * m) + 48) + 3 * 8
+    h2d, d2h = inst.bytes_per_step()
 
     # ---------------- value: inputs resident in HBM ----------------
-    h.upload_values(prob.J.data, prob.H.data, prob.y, prob.s)
-    h.upload_rhs(*prob.rhs[0])
-
-    def resident_step():
-        h.form_resident()
-        h.delta_loop_resident(*dl_args)
-        for _ in range(N_DIRECTIONS):
-            h.direction_resident(N_REFINE)
-
+    inst.make_resident()
     for _ in range(args.warmup):
-        resident_step()
+        inst.resident_step()
     barrier()
     sampler = ClockSampler(local); sampler.start()
     l0 = pkg.launch_count()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        resident_step()
+        inst.resident_step()
     e1.record()
     barrier()
     launches = pkg.launch_count() - l0
@@ -394,43 +525,30 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, e2e_ms = float(t[0]), float(t[1])
 
-    # ---------------- per-phase timing (rank 0) for the rooflines ----------------
-    phases = {}
     if args.ncu:
         if rank == 0:
             print(json.dumps({"ncu_run": True, "workload": args.workload, "ms_per_step_under_profiler": ms_step,
                               "launches": int(launches), "num_fac": nf_res}))
-        k.finalize()
+        inst.close()
         return
+
+    # ---------------- per-phase timing (rank 0) for the rooflines ----------------
+    phases, roofline, extra_rooflines, kernel_rooflines = {}, None, {}, {}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    fp64_peak_1 = measure_fp64_peak(torch, dev) if (rank == 0 or sharded) else None
     if rank == 0 or sharded:        # a sharded instance needs every rank in every call
-        def timed(fn, reps):
-            fn(); torch.cuda.synchronize()
-            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(reps):
-                fn()
-            b.record(); torch.cuda.synchronize()
-            return a.elapsed_time(b) / reps
-        reps = args.phase_repeat
-        phases["form_ms"] = timed(h.form_resident, reps)
-        phases["factor_ms"] = timed(lambda: h.delta_loop_resident(*dl_args), reps) / max(nf_res, 1)
-        phases["direction_ms"] = timed(lambda: h.direction_resident(N_REFINE), reps)
-        phases["solve_pair_ms"] = timed(lambda: h.solve_resident(1), reps)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        fp64_peak = measure_fp64_peak(torch, dev) * (world if sharded else 1)
-        fac_tflops = cnt["F_chol"] / (phases["factor_ms"] * 1e-3) / 1e12
-        asm_gbs = cnt["B_asm"] / (phases["form_ms"] * 1e-3) / 1e9
-        solve_gbs = cnt["B_solve"] / (phases["solve_pair_ms"] * 1e-3) / 1e9
-        dir_gbs = cnt["B_dir"] / (phases["direction_ms"] * 1e-3) / 1e9
-        share = {kk: phases[kk] for kk in ("form_ms", "factor_ms", "direction_ms")}
-        tot = share["form_ms"] + share["factor_ms"] * nf_res + share["direction_ms"] * N_DIRECTIONS
-        if share["factor_ms"] * nf_res >= 0.5 * tot:
+        fp64_peak = fp64_peak_1 * (world if sharded else 1)
+        phases, extra_rooflines, _ = phase_rooflines(torch, inst, args.phase_repeat, hbm_peak, fp64_peak, nf_res)
+        fac_tflops = extra_rooflines["factor"]["achieved"]
+        dir_gbs = extra_rooflines["direction"]["achieved"]
+        tot = phases["form_ms"] + phases["factor_ms"] * nf_res + phases["direction_ms"] * N_DIRECTIONS
+        if phases["factor_ms"] * nf_res >= 0.5 * tot:
             roofline = {"bound": "tensor", "kernel": "numeric factorisation (all fronts of all levels)",
                         "achieved": fac_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                         "frac": fac_tflops / fp64_peak, "traffic": None,
@@ -440,15 +558,17 @@ def main():
                         "achieved": dir_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dir_gbs / hbm_peak,
                         "traffic": None, "peak_source": hbm_src}
         tr = {}
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json"))).get(args.workload, {})
-        except Exception:
-            pass
+        for fn in ("r2_dram_traffic.json", "r1_dram_traffic.json"):
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", fn))).get(args.workload, {})
+                if tr:
+                    break
+            except Exception:
+                pass
         roofline["traffic"] = tr.get("factor_bytes_per_attempt" if roofline["bound"] == "tensor" else "direction_bytes")
         # the dominant KERNEL of a factorisation-bound step: CUDA events around its launches in one
         # extra attempt (opb_profile_factor: plain launches, no look-ahead, so the timed kernels do
         # not overlap anything); achieved = algorithmic flops it serves / its summed launch time
-        kernel_rooflines = {}
         if roofline["bound"] == "tensor" and not sharded:
             try:
                 pf = h.profile_factor(delta_res)
@@ -471,106 +591,93 @@ def main():
                     roofline["share_of_step"] = roofline["ms_per_attempt"] * max(nf_res, 1) / tot
             except Exception as e:      # the phase-level roofline stays
                 kernel_rooflines = {"error": str(e)[:200]}
-        extra_rooflines = {
-            "assembly": {"bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak},
-            "factor": {"bound": "tensor", "achieved": fac_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fac_tflops / fp64_peak},
-            "solve_pair": {"bound": "hbm", "achieved": solve_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": solve_gbs / hbm_peak},
-            "direction": {"bound": "hbm", "achieved": dir_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dir_gbs / hbm_peak},
-        }
 
-    # ---------------- the other BASELINE.json shapes, kernels only (rank 0, N = 1) ----------------
+    # ---------------- e2e from pageable host memory (what a Julia caller has), rank 0 ----------------
+    e2e_pageable = None
+    if rank == 0 and world == 1:
+        try:
+            p2 = make_problem(args.workload, seed=rank)
+            inst.prob, inst.it = p2, pkg.Class_iterate(p2.J, p2.H, p2.y, p2.s, delta=p2.delta_prev)
+            inst.rhs = [pkg.System_rhs(*r) for r in p2.rhs[:N_DIRECTIONS]]
+            inst.e2e_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = max(2, min(args.steps, 5))
+            for _ in range(reps):
+                inst.e2e_step()
+            torch.cuda.synchronize()
+            e2e_pageable = (time.perf_counter() - t0) * 1e3 / reps
+        except Exception:
+            e2e_pageable = None
+    config_extra = dict(nnz_M_lower=int(h.info("nnzM")), nnz_L=int(h.info("nnzL_true")), supernodes=int(h.info("nsuper")),
+                        etree_levels=int(h.info("nlevels")), max_front=int(h.info("max_front")),
+                        L_mb=8 * h.info("nnzL") / 1e6)
+    t_symbolic = inst.t_symbolic
+    inst.close()
+    del inst, h
+    torch.cuda.empty_cache()
+
+    # ---------------- the other BASELINE.json shapes (rank 0, N = 1) ----------------
     others = {}
     if rank == 0 and world == 1 and not args.no_extra:
-        for wname in ("c2_chain_n100k", "c3_sparse_qp_n200k", "c4_elec_n1200"):
+        for wname in OTHER_WORKLOADS:
             if wname == args.workload:
                 continue
             try:
-                p2 = make_problem(pkg, wname, seed=0)
-                it2 = pkg.Class_iterate(p2.J, p2.H, p2.y, p2.s, delta=p2.delta_prev)
-                k2 = pkg.pick_KKT_solver(pars); k2.initialize(it2)
-                k2._h.set_stream(stream.cuda_stream)
-                k2.form_system(it2)
-                h2 = k2._h
-                h2.upload_values(p2.J.data, p2.H.data, p2.y, p2.s); h2.upload_rhs(*p2.rhs[0])
-
-                def step2():
-                    h2.form_resident(); h2.delta_loop_resident(*dl_args)
-                    for _ in range(N_DIRECTIONS):
-                        h2.direction_resident(N_REFINE)
-                for _ in range(3):
-                    step2()
-                torch.cuda.synchronize()
-                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-                a.record()
-                for _ in range(5):
-                    step2()
-                b.record(); torch.cuda.synchronize()
-                d2, nf2, st2, err2 = h2.sync_state()
-                others[wname] = {"ms_per_iter": a.elapsed_time(b) / 5, "n": p2.n, "m": p2.m, "num_fac": nf2,
-                                 "N_err": float(err2[5]), "factor_flops": h2.info("flops"),
-                                 "nnz_L": int(h2.info("nnzL_true"))}
-                k2.finalize()
+                others[wname] = measure_other_workload(pkg, torch, wname, local, hbm_peak, fp64_peak_1,
+                                                       cpu=not args.no_cpu_baseline)
             except Exception as e:      # never lose the headline line to an extra
                 others[wname] = {"error": str(e)[:200]}
 
-    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    # ---------------- CPU baseline of the headline workload: bounded sample (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            orc = graft.oracle()
-            sp_prob = make_problem(pkg, args.workload, seed=0, sample=True)
-            hs = pkg.Handle(-1)
-            t0 = time.perf_counter()
-            hs.set_structure(sp_prob.n, sp_prob.m, sp_prob.J.indptr, sp_prob.J.indices,
-                             sp_prob.H.indptr, sp_prob.H.indices, 0)
-            t_order = time.perf_counter() - t0
-            r = cpu_iteration(orc, pkg, sp_prob, hs)
+            gen, kw, kws = WORKLOADS[args.workload]
+            sp_prob = make_problem(args.workload, seed=0, sample=True)
+            r = cpu_iteration(sp_prob, os.cpu_count())
             # the GPU on the same sample, through the plugin API (host buffers)
-            it_s = pkg.Class_iterate(sp_prob.J, sp_prob.H, sp_prob.y, sp_prob.s, delta=sp_prob.delta_prev)
-            ks = pkg.pick_KKT_solver(pars); ks.initialize(it_s)
-            rhs_s = [pkg.System_rhs(*q) for q in sp_prob.rhs[:N_DIRECTIONS]]
-
-            def step_s():
-                ks.form_system(it_s)
-                pkg.ipopt_strategy(it_s, ks, pars)
-                for q in rhs_s:
-                    ks.kkt_associate_rhs(it_s, q); ks.compute_direction()
-            step_s(); step_s()
+            si = Instance(pkg, torch, sp_prob, local)
+            si.e2e_step(); si.e2e_step()
+            torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(3):
-                step_s()
+                si.e2e_step()
             gpu_same = (time.perf_counter() - t0) * 1e3 / 3
-            gen, kw, kws = WORKLOADS[args.workload]
-            cpu = {"value": r["total_ms"] + t_order * 1e3, "unit": "ms/iter", "cores": os.cpu_count(), "kind": "port",
-                   "sample": "%s%s, 1 iteration: %s; analysis %.0f ms included" % (gen, kws, CPU_SAMPLE_NOTE, t_order * 1e3),
+            si.close()
+            cpu = {"value": r["total_ms"], "unit": "ms/iter", "cores": os.cpu_count(), "kind": "port",
+                   "sample": "%s%s (%s of the headline's size), 1 iteration: %s; the full-size CPU time is what "
+                             "`--impl reference` measures" % (gen, kws, "bounded sample" if kws != kw else "all", CPU_NOTE),
                    "breakdown_ms": r, "gpu_e2e_same_sample_ms": gpu_same, "host_cores_available": os.cpu_count()}
-            ks.finalize()
         except Exception as e:      # never lose the headline line to the baseline leg
             cpu = {"error": str(e)[:300]}
 
+    out = None
     if rank == 0:
         gen, kw, kws = WORKLOADS[args.workload]
+        cfg = {"workload": args.workload, "generator": gen, "generator_args": kw,
+               "n": n, "m": m, "nnz_J": int(prob.J.nnz), "nnz_M_lower": config_extra["nnz_M_lower"],
+               "nnz_L": config_extra["nnz_L"], "factor_flops": cnt["F_chol"],
+               "supernodes": config_extra["supernodes"], "etree_levels": config_extra["etree_levels"],
+               "max_front": config_extra["max_front"],
+               "directions_per_iter": N_DIRECTIONS, "refine": N_REFINE, "num_fac": nf_res,
+               "delta": delta_res, "N_err": float(kkt_err[5]),
+               "instances": 1 if sharded else world,
+               "parallelism": ("one instance, elimination-tree subtrees mapped to %d GPUs, top separators over "
+                               "NVLink peer memory" % world) if sharded else
+                              "one independent instance per GPU (replicas)",
+               "l2_policy": "working set larger than L2: factor L alone is %.0f MB and is streamed by every "
+                            "factorisation and solve" % config_extra["L_mb"],
+               "symbolic_s_once": t_symbolic}
         out = {
             "metric": "kkt_factor_solve_ms_per_iter", "value": ms_step if sharded else ms_step / world, "unit": "ms/iter",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": False, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": args.workload, "generator": gen, "generator_args": kw,
-                       "n": n, "m": m, "nnz_J": int(prob.J.nnz), "nnz_M_lower": int(h.info("nnzM")),
-                       "nnz_L": int(h.info("nnzL_true")), "factor_flops": cnt["F_chol"],
-                       "supernodes": int(h.info("nsuper")), "etree_levels": int(h.info("nlevels")),
-                       "max_front": int(h.info("max_front")),
-                       "directions_per_iter": N_DIRECTIONS, "refine": N_REFINE, "num_fac": nf_res,
-                       "delta": delta_res, "N_err": float(kkt_err[5]),
-                       "instances": 1 if sharded else world,
-                       "parallelism": ("one instance, elimination-tree subtrees mapped to %d GPUs, top separators over "
-                                       "NVLink peer memory" % world) if sharded else
-                                      "one independent instance per GPU (replicas)",
-                       "l2_policy": "working set larger than L2: factor L alone is %.0f MB and is streamed by every "
-                                    "factorisation and solve" % (8 * h.info("nnzL") / 1e6),
-                       "symbolic_s_once": t_symbolic},
+            "config": cfg,
             "e2e": {"value": e2e_ms if sharded else e2e_ms / world, "unit": "ms/iter", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h)},
+                    "d2h_bytes_per_step": int(d2h), "host_memory": "pinned",
+                    "pageable_host_memory_ms": e2e_pageable},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "phases_ms": phases,
@@ -578,12 +685,9 @@ def main():
             "rooflines_by_phase": extra_rooflines,
             "rooflines_by_kernel": kernel_rooflines,
             "cpu_baseline": cpu,
-            "other_workloads_kernels_only": others,
+            "workloads": others,
             "lib_launches_total": pkg.launch_count() - lib0,
         }
-    k.finalize()
-    del k, h
-    torch.cuda.empty_cache()
     if world > 1 and not sharded and not args.no_extra:
         # the same line also carries ONE instance sharded over the N GPUs
         try:

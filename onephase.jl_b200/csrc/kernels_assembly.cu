@@ -120,6 +120,7 @@ __device__ double next_delta(DeltaState* s) {
     if (s->it == 1) {
         if (s->delta_prev != 0.0) {
             double a = s->delta_min - s->tau, b = s->delta_prev * s->dec;
+            if (a != a || b != b) return a + b;   // Julia's max propagates NaN
             return a > b ? a : b;   // max(DELTA_MIN - tau, get_delta(iter) * dec)
         }
         return s->delta_start - s->tau;

@@ -25,6 +25,24 @@ struct Bundle {
     std::vector<int64_t> Mp;     // pattern of the lower triangle that is factorised
     std::vector<int> Mi;
     std::vector<int64_t> src;    // csc path: position in the caller's nzval (or -1)
+    // the caller's index arrays (0-based copies): a cache hit is accepted only when they are equal,
+    // so a 64-bit hash collision cannot hand out a wrong analysis
+    std::vector<int64_t> in_p[2];
+    std::vector<int> in_i[2];
+    void keep_pattern(int k, int64_t n, const int64_t* p, const int64_t* i, int base) {
+        in_p[k].resize(n + 1);
+        for (int64_t c = 0; c <= n; c++) in_p[k][c] = p[c] - base;
+        const int64_t nnz = in_p[k][n];
+        in_i[k].resize(nnz);
+        for (int64_t e = 0; e < nnz; e++) in_i[k][e] = (int)(i[e] - base);
+    }
+    bool same_pattern(int k, int64_t n, const int64_t* p, const int64_t* i, int base) const {
+        if ((int64_t)in_p[k].size() != n + 1) return false;
+        for (int64_t c = 0; c <= n; c++) if (in_p[k][c] != p[c] - base) return false;
+        const int64_t nnz = in_p[k][n];
+        for (int64_t e = 0; e < nnz; e++) if (in_i[k][e] != (int)(i[e] - base)) return false;
+        return true;
+    }
     Symbolic S;
     std::vector<LevelPlan> plan;
     std::vector<int> sched;
@@ -525,8 +543,8 @@ static int alloc_numeric(opb_handle* h) {
 static std::string cache_key(const opb_handle* h, uint64_t h1, uint64_t h2) {
     const SymOptions& o = h->opt;
     char buf[200];
-    snprintf(buf, sizeof buf, "%d|%d|%.4f|%d|%d|%d|%d|%d/%d|%016llx|%016llx", h->device, o.nd_leaf, o.nd_balance, o.ordering,
-             o.metis_max_n, o.relax_enable, h->user_perm.empty() ? 0 : 1, h->shard_rank, h->shard_world,
+    snprintf(buf, sizeof buf, "%d|%d|%.4f|%d|%d|%d|%.3f|%d|%d/%d|%016llx|%016llx", h->device, o.nd_leaf, o.nd_balance, o.ordering,
+             o.metis_max_n, o.relax_enable, o.relax_small, h->user_perm.empty() ? 0 : 1, h->shard_rank, h->shard_world,
              (unsigned long long)h1, (unsigned long long)h2);
     return buf;
 }
@@ -592,9 +610,11 @@ int opb_set_structure(opb_handle* h, int64_t n, int64_t m, const int64_t* Jp, co
     if (!h->user_perm.empty()) h2 ^= pattern_hash(0, h->user_perm.data(), h->user_perm.data(), (int64_t)h->user_perm.size());
     std::string key = "S|" + cache_key(h, h1, h2);
     if (auto B = cache_get(key)) {
-        if (B->S.n == n && B->P.m == m && B->P.nnzJ == nnzJ && B->P.nnzH == nnzH) {
+        if (B->S.n == n && B->P.m == m && B->P.nnzJ == nnzJ && B->P.nnzH == nnzH &&
+            B->same_pattern(0, n, Jp, Ji, base) && B->same_pattern(1, n, Hp, Hi, base)) {
+            const bool same = h->B == B;
             h->B = B; h->cached_hit = true; h->ready = opb_handle::NOT_READY;
-            if (h->device >= 0) return alloc_numeric(h);
+            if (h->device >= 0 && !same) return alloc_numeric(h);
             return OPB_OK;
         }
     }
@@ -602,6 +622,7 @@ int opb_set_structure(opb_handle* h, int64_t n, int64_t m, const int64_t* Jp, co
     B->schur = true;
     std::string err;
     if (!build_schur_pattern(n, m, Jp, Ji, Hp, Hi, base, B->P, err)) return h->fail(OPB_ERR_INVALID, err);
+    B->keep_pattern(0, n, Jp, Ji, base); B->keep_pattern(1, n, Hp, Hi, base);
     B->Mp = B->P.Mp; B->Mi = B->P.Mi;
     return finish_structure(h, B, key);
 }
@@ -937,15 +958,18 @@ int opb_ls_factor_csc(opb_handle* h, int64_t dim, const int64_t* cp, const int64
     uint64_t h1 = pattern_hash(dim, cp, ri, nnz) + (uint64_t)base;
     std::string key = "C|" + cache_key(h, h1, 0);
     std::shared_ptr<Bundle> B = cache_get(key);
-    if (B && (B->S.n != dim || B->schur)) B.reset();
+    if (B && (B->S.n != dim || B->schur || !B->same_pattern(0, dim, cp, ri, base))) B.reset();
     if (B) {
+        // the same analysis as last time (one ls_factor! per delta attempt): buffers and CUDA graphs stay
+        const bool same = h->B == B;
         h->B = B; h->cached_hit = true;
-        rc = alloc_numeric(h); if (rc) return rc;
+        if (!same) { rc = alloc_numeric(h); if (rc) return rc; }
     } else {
         B = std::make_shared<Bundle>();
         B->schur = false;
         std::string err;
         if (!build_csc_pattern(dim, cp, ri, base, B->Mp, B->Mi, B->src, err)) return h->fail(OPB_ERR_INVALID, err);
+        B->keep_pattern(0, dim, cp, ri, base);
         rc = finish_structure(h, B, key); if (rc) return rc;
     }
     cudaStream_t st = h->stream;

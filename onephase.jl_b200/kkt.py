@@ -226,12 +226,27 @@ class Schur_B200_KKT_solver:
         self._pattern_ident = None
 
     # -- form_system!  schur.jl:47-62
+    @staticmethod
+    def _pattern_sample(J, H):
+        """Cheap content fingerprint of the index arrays (a strided sample of <= 4096 entries of
+        each plus the ends): catches a caller that refills the SAME preallocated index arrays in
+        place with another pattern of equal nnz, which the id()-based shortcut alone would miss."""
+        out = []
+        for a in (J.indptr, J.indices, H.indptr, H.indices):
+            step = max(1, a.shape[0] // 4096)
+            out.append(hash(a[::step].tobytes()))
+            out.append(int(a[-1]) if a.shape[0] else 0)
+        return tuple(out)
+
     def form_system(self, it, timer=None):
         J = _csc(it.J); H = _csc(it.H)
         # pattern identity: same index arrays as last time (the usual case: the iterate's cached
-        # matrices keep their structure) -> no hashing; otherwise compare pattern hashes
-        ident = (id(J.indptr), id(J.indices), id(H.indptr), id(H.indices), J.shape, J.nnz, H.nnz)
-        if ident != self._pattern_ident:
+        # matrices keep their structure) and the same sampled content -> no full hashing; the full
+        # pattern hash is re-verified on every 16th call and whenever the shortcut does not apply
+        ident = (id(J.indptr), id(J.indices), id(H.indptr), id(H.indices), J.shape, J.nnz, H.nnz,
+                 self._pattern_sample(J, H))
+        self._form_calls = getattr(self, "_form_calls", 0) + 1
+        if ident != self._pattern_ident or self._form_calls % 16 == 0:
             key = (J.shape, hash(J.indptr.tobytes()), hash(J.indices.tobytes()),
                    hash(H.indptr.tobytes()), hash(H.indices.tobytes()))
             if key != self._pattern_key:
@@ -425,8 +440,11 @@ def respond_to_failed_step(it, kkt_solver, pars, old_delta, grad_lag_inf=None, r
     if response == "lag_delta_inc":
         if grad_lag_inf is None:
             raise ValueError("response_to_failure = :lag_delta_inc needs norm(grad L, Inf)")
-        dx_inf = float(np.abs(kkt_solver.dir.x).max())
-        new_delta = max(grad_lag_inf / dx_inf, get_delta(it) * d.inc, floor)
+        # Julia semantics (one_phase.jl:233): a zero direction gives Inf (or NaN for 0/0), no exception,
+        # and max() propagates NaN
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = np.float64(grad_lag_inf) / np.float64(np.abs(kkt_solver.dir.x).max())
+        new_delta = float(np.maximum(np.maximum(ratio, get_delta(it) * d.inc), floor))
     elif response == "default":
         new_delta = max(get_delta(it) * d.inc, floor)
     else:

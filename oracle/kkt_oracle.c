@@ -395,7 +395,7 @@ int orc_delta_loop(orc_factor *F, const double *Ax, const double *schur_diag,
         if (it == 1) {
             if (delta_prev != 0.0) {
                 double a = delta_min - tau, b = delta_prev * dec;
-                delta = a > b ? a : b;
+                delta = (a != a || b != b) ? a + b : (a > b ? a : b);   /* Julia's max propagates NaN */
             } else {
                 delta = delta_start - tau;
             }

@@ -23,8 +23,8 @@ _f64p = ctypes.POINTER(ctypes.c_double)
 
 def build(force=False):
     so = os.path.join(_HERE, "libkkt_oracle.so")
-    src = os.path.join(_HERE, "kkt_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("kkt_oracle.c", "snode.c", "Makefile")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B" if force else "-s"])
     return so
 

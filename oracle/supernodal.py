@@ -1,29 +1,28 @@
 """Supernodal (multifrontal) CPU restatement of the reference's KKT path with BLAS-3 dense
 kernels -- the performance class of what the reference actually runs: `cholesky(Symmetric(Q,:L))`
 (linear_system_solvers/julia.jl:34) is CHOLMOD's supernodal factorisation on top of a threaded
-BLAS.  oracle/kkt_oracle.c (scalar, up-looking, one core) is the checker; this module is the
-CPU BASELINE that bench.py times with all host cores (numpy/scipy -> OpenBLAS threads).
+BLAS.  oracle/kkt_oracle.c (scalar, up-looking, one core) is the small-case checker; this module
+(on oracle/snode.c) is the large-case checker and the CPU BASELINE that bench.py times with all
+host cores (scipy's OpenBLAS threads).
 
 TEST INFRASTRUCTURE ONLY (same rule as oracle.py): imported by tests/ and by bench.py's
-cpu_baseline / --impl reference legs, never by the product package.  Parity status: "parity
+cpu_baseline / --impl reference legs, never by the product package -- and it does not use the
+product either: ordering (METIS_NodeND / minimum degree / natural), elimination tree, column
+counts, supernodes and row structures all come from oracle/snode.c.  Parity status: "parity
 unpinned" (no CHOLMOD, no Julia here); tests/test_oracle.py pins it against kkt_oracle.c.
 
 What follows which reference lines:
+  SupernodalFactor(...)   CHOLMOD analyze (redone per ls_factor!, recycle = false)   julia.jl:34, parameters.jl:38
   delta_loop   ipopt_strategy!                      IPM/delta_strategy.jl:37-114, parameters.jl:147-158
   factorize    update_delta_vecs! + ls_factor!      schur.jl:64-87, julia.jl:28-46 (1 = PD, 0 = PosDefException)
   solve        ls_solve                             julia.jl:99-113
   direction    compute_direction_implementation!    schur.jl:89-182, kkt_system_solver.jl:27-96
-
-The elimination-tree structures (ordering, supernodes, row structures, child-to-parent maps)
-come from the host-side symbolic analysis of the library under test (a host-only handle, no
-device): they are index structures, the arithmetic below is independent of the CUDA code.
 """
 import ctypes
+import os
 
 import numpy as np
-import scipy.linalg as sla
 import scipy.sparse as sp
-from scipy.linalg import blas
 
 from . import oracle as _orc
 
@@ -32,87 +31,152 @@ _i64p = ctypes.POINTER(ctypes.c_int64)
 
 DELTA_PARS = dict(delta_zero=0.0, delta_min=1e-12, delta_max=1e50, delta_start=1e-6, inc=8.0, dec=1.0 / np.pi)
 
+_BLAS_SET = False
+
+
+def _capsule_pointer(mod, name):
+    cap = mod.__pyx_capi__[name]
+    api = ctypes.pythonapi
+    api.PyCapsule_GetName.restype = ctypes.c_char_p
+    api.PyCapsule_GetName.argtypes = [ctypes.py_object]
+    api.PyCapsule_GetPointer.restype = ctypes.c_void_p
+    api.PyCapsule_GetPointer.argtypes = [ctypes.py_object, ctypes.c_char_p]
+    return api.PyCapsule_GetPointer(cap, api.PyCapsule_GetName(cap))
+
+
+def lib():
+    """libkkt_oracle.so with the snode.c entry points typed and the BLAS / LAPACK routines of
+    scipy's OpenBLAS (dpotrf, dtrsm, dsyrk, dgemv, dtrsv) handed over as function pointers."""
+    global _BLAS_SET
+    L = _orc.lib()
+    if not _BLAS_SET:
+        vp, i64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+        L.orc_sn_set_blas.argtypes = [vp] * 5
+        L.orc_sn_has_blas.restype = ci
+        L.orc_order_metis.restype = ci
+        L.orc_order_metis.argtypes = [i64, _i64p, _i64p, _i64p]
+        L.orc_order_mindeg.restype = ci
+        L.orc_order_mindeg.argtypes = [i64, _i64p, _i64p, _i64p]
+        L.orc_sn_analyze.restype = vp
+        L.orc_sn_analyze.argtypes = [i64, _i64p, _i64p, _i64p, ci]
+        L.orc_sn_free.argtypes = [vp]
+        L.orc_sn_info.restype = ctypes.c_double
+        L.orc_sn_info.argtypes = [vp, ci]
+        L.orc_sn_copy.argtypes = [vp, ci, _i64p]
+        L.orc_sn_factorize.restype = ci
+        L.orc_sn_factorize.argtypes = [vp, _f64p, _f64p]
+        L.orc_sn_diag.argtypes = [vp, _f64p]
+        L.orc_sn_solve.argtypes = [vp, _f64p, _f64p]
+        from scipy.linalg import cython_blas, cython_lapack
+        L.orc_sn_set_blas(_capsule_pointer(cython_lapack, "dpotrf"), _capsule_pointer(cython_blas, "dtrsm"),
+                          _capsule_pointer(cython_blas, "dsyrk"), _capsule_pointer(cython_blas, "dgemv"),
+                          _capsule_pointer(cython_blas, "dtrsv"))
+        assert L.orc_sn_has_blas() == 1
+        _BLAS_SET = True
+    return L
+
+
+def blas_threads(n=None):
+    """Context manager that pins the BLAS thread count (torchrun exports OMP_NUM_THREADS=1, which
+    would silently serialise the baseline); n = None -> all host cores."""
+    from threadpoolctl import threadpool_limits
+    return threadpool_limits(limits=int(n or os.cpu_count() or 1), user_api="blas")
+
+
+def _ip(a):
+    return a.ctypes.data_as(_i64p)
+
+
+def order(QL, method="metis"):
+    """Fill-reducing ordering of the pattern of the lower-triangular CSC matrix QL, computed by
+    the oracle itself: 'metis' (METIS_NodeND), 'mindeg' (exact minimum degree, small n),
+    'natural'.  Returns perm with perm[new] = old."""
+    QL = sp.csc_matrix(QL)
+    n = QL.shape[0]
+    if method == "natural":
+        return np.arange(n, dtype=np.int64)
+    Ap = np.ascontiguousarray(QL.indptr, dtype=np.int64)
+    Ai = np.ascontiguousarray(QL.indices, dtype=np.int64)
+    perm = np.empty(n, np.int64)
+    fn = {"metis": lib().orc_order_metis, "mindeg": lib().orc_order_mindeg}[method]
+    if fn(n, _ip(Ap), _ip(Ai), _ip(perm)) != 1:
+        raise RuntimeError("ordering %s failed" % method)
+    return perm
+
 
 class SupernodalFactor:
-    def __init__(self, QL, handle):
-        """QL: scipy CSC, lower triangle with the full diagonal, sorted indices.
-        handle: host-only opb handle whose structure was set from the same (J, H) patterns."""
-        g = handle.symbolic
+    def __init__(self, QL, perm=None, ordering="metis", relax=True):
+        """QL: scipy CSC, lower triangle (entries above the diagonal are ignored).
+        perm: explicit permutation (perm[new] = old) or None -> `ordering` is computed here.
+        The whole analysis (ordering, elimination tree, column counts, supernodes, row
+        structures) runs in this constructor, like CHOLMOD's analyze inside cholesky()."""
         QL = sp.csc_matrix(QL)
         self.n = QL.shape[0]
-        Mp, Mi = g("Mp"), g("Mi")
-        if not (np.array_equal(Mp, QL.indptr) and np.array_equal(Mi, QL.indices)):
-            raise ValueError("QL does not have the pattern the symbolic analysis was made for")
-        self.perm = g("perm"); self.sfirst = g("sfirst"); self.sparent = g("sparent")
-        self.rowptr = g("rowptr"); self.rowidx = g("rowidx"); self.rel = g("rel")
-        self.Loff = g("Loff"); self.amap = g("amap"); self.dpos = g("dpos")
-        self.nsuper = len(self.sfirst) - 1
-        self.nnzL = int(handle.info("nnzL"))
-        self.children = [[] for _ in range(self.nsuper)]
-        for s in range(self.nsuper):
-            if self.sparent[s] >= 0:
-                self.children[self.sparent[s]].append(s)
-        self.L = None
+        self._Ap = np.ascontiguousarray(QL.indptr, dtype=np.int64)
+        self._Ai = np.ascontiguousarray(QL.indices, dtype=np.int64)
+        self.nnz = int(self._Ap[-1])
+        if perm is None:
+            perm = order(QL, ordering)
+        p = np.ascontiguousarray(perm, dtype=np.int64)
+        self._h = lib().orc_sn_analyze(self.n, _ip(self._Ap), _ip(self._Ai), _ip(p), 1 if relax else 0)
         self.delta = 0.0
-        # index arrays of the C solve (kept alive here)
-        cp = np.zeros(self.nsuper + 1, np.int64)
-        for s in range(self.nsuper):
-            cp[s + 1] = cp[s] + len(self.children[s])
-        cl = np.array([ch for s in range(self.nsuper) for ch in self.children[s]] or [0], np.int64)
-        self._keep = [np.ascontiguousarray(v, dtype=np.int64) for v in
-                      (self.sfirst, self.rowptr, self.rowidx if len(self.rowidx) else np.zeros(1), self.rel if len(self.rel) else np.zeros(1),
-                       self.Loff, cp, cl)]
-        self._solve_args = [v.ctypes.data_as(_i64p) for v in self._keep]
+        self._factored = False
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orc_sn_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def info(self, key):
+        keys = {"n": 0, "nsuper": 1, "nnzL": 2, "nnzL_true": 3, "flops": 4, "max_front": 5, "sum_rows": 6}
+        return lib().orc_sn_info(self._h, keys[key])
+
+    def array(self, name):
+        which = {"perm": 0, "sfirst": 1, "sparent": 2, "rowptr": 3, "rowidx": 4, "Loff": 5, "amap": 6, "dpos": 7}[name]
+        ns = int(self.info("nsuper"))
+        cnt = {"perm": self.n, "sfirst": ns + 1, "sparent": ns, "rowptr": ns + 1, "rowidx": int(self.info("sum_rows")),
+               "Loff": ns + 1, "amap": self.nnz, "dpos": self.n}[name]
+        out = np.empty(max(cnt, 1), np.int64)
+        lib().orc_sn_copy(self._h, which, _ip(out))
+        return out[:cnt]
+
+    @property
+    def perm(self):
+        return self.array("perm")
 
     # -- update_delta_vecs! + ls_factor!(:definite)
-    def factorize(self, nzval, delta):
-        """Returns 1 when Q + delta*I is positive definite (every pivot > 0), else 0."""
-        L = np.zeros(self.nnzL)
-        L[self.amap] = nzval
-        L[self.dpos] += delta                 # Q[i,i] = schur_diag[i] + delta (schur.jl:76)
-        CB = {}
-        sfirst, rowptr, Loff = self.sfirst, self.rowptr, self.Loff
-        rel = np.ascontiguousarray(self.rel, dtype=np.int64)
-        relp = rel.ctypes.data
-        extend_add = _orc.lib().orc_extend_add
-        for s in range(self.nsuper):          # supernodes are numbered in postorder
-            c = int(sfirst[s + 1] - sfirst[s])
-            r = int(rowptr[s + 1] - rowptr[s])
-            N = c + r
-            ld = (N + 1) & ~1
-            P = L[Loff[s]:Loff[s] + ld * c]                           # the panel in place: N x c, leading dimension ld
-            U = np.zeros((r, r), order="F")
-            for ch in self.children[s]:
-                cb = CB.pop(ch)
-                rc = cb.shape[0]
-                extend_add(P.ctypes.data_as(_f64p), ld, c, U.ctypes.data_as(_f64p), r,
-                           ctypes.cast(relp + 8 * int(rowptr[ch]), _i64p), rc, cb.ctypes.data_as(_f64p))
-            view = P.reshape(c, ld).T                                   # (ld x c) column-major view
-            L11, info = sla.lapack.dpotrf(view[:c], lower=1, clean=1, overwrite_a=0)
-            if info != 0 or not np.isfinite(L11[np.diag_indices(c)]).all():
-                self.L = None                                           # pivot <= 0 or NaN: not positive definite
-                return 0
-            view[:c] = L11
-            if r:
-                # L21 = A21 * L11^-T (dtrsm), update block U -= L21 L21' (dsyrk, lower part)
-                L21 = blas.dtrsm(1.0, L11, np.asfortranarray(view[c:N]), side=1, lower=1, trans_a=1)
-                view[c:N] = L21
-                U = blas.dsyrk(-1.0, L21, beta=1.0, c=U, lower=1, overwrite_c=1)
-                CB[s] = U
-        self.L = L
+    def factorize(self, nzval, delta=0.0, schur_diag=None):
+        """Factorise Q with its diagonal replaced by schur_diag + delta (schur.jl:76) when
+        schur_diag is given, else Q + nothing (delta must then be 0).  Returns 1 when positive
+        definite (every pivot > 0), else 0."""
+        x = np.ascontiguousarray(nzval, dtype=np.float64)
+        assert x.shape[0] == self.nnz
+        dp = None
+        if schur_diag is not None:
+            d = np.ascontiguousarray(np.asarray(schur_diag, dtype=np.float64) + delta)
+            dp = d.ctypes.data_as(_f64p)
+        else:
+            assert delta == 0.0
+        ok = lib().orc_sn_factorize(self._h, x.ctypes.data_as(_f64p), dp)
+        self._factored = ok == 1
         self.delta = delta
-        return 1
+        return ok
+
+    def diag(self):
+        d = np.empty(self.n)
+        lib().orc_sn_diag(self._h, d.ctypes.data_as(_f64p))
+        return d
 
     # -- ls_solve
     def solve(self, b):
-        x = np.ascontiguousarray(np.asarray(b, dtype=np.float64)[self.perm])
-        u = np.empty(max(int(self.rowptr[-1]), 1))
-        a = self._solve_args
-        _orc.lib().orc_snode_solve(self.nsuper, *a, self.L.ctypes.data_as(_f64p), x.ctypes.data_as(_f64p),
-                                   u.ctypes.data_as(_f64p))
-        out = np.empty(self.n)
-        out[self.perm] = x
-        return out
+        assert self._factored
+        bb = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty(self.n)
+        lib().orc_sn_solve(self._h, bb.ctypes.data_as(_f64p), x.ctypes.data_as(_f64p))
+        return x
 
     # -- ipopt_strategy!
     def delta_loop(self, nzval, schur_diag, delta_prev, **kw):
@@ -123,15 +187,15 @@ class SupernodalFactor:
         delta = p["delta_zero"]
         if tau > 0.0:
             tau = 0.0
-            ok = self.factorize(nzval, delta); num_fac += 1; tried.append(delta)
+            ok = self.factorize(nzval, delta, schur_diag); num_fac += 1; tried.append(delta)
             if ok == 1:
                 return "success", num_fac, delta, np.array(tried)
         for i in range(1, 501):
             if i == 1:
-                delta = max(p["delta_min"] - tau, delta_prev * p["dec"]) if delta_prev != 0.0 else p["delta_start"] - tau
+                delta = float(np.maximum(p["delta_min"] - tau, delta_prev * p["dec"])) if delta_prev != 0.0 else p["delta_start"] - tau
             else:
                 delta = delta * p["inc"]
-            ok = self.factorize(nzval, delta); num_fac += 1; tried.append(delta)
+            ok = self.factorize(nzval, delta, schur_diag); num_fac += 1; tried.append(delta)
             if ok == 1:
                 return "success", num_fac, delta, np.array(tried)
             if delta > p["delta_max"]:

@@ -13,6 +13,9 @@ import scipy.sparse as sp
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
+if os.path.dirname(HERE) not in sys.path:
+    sys.path.insert(0, os.path.dirname(HERE))
+import problems  # noqa: E402  (tests/problems.py)
 
 CASES = {
     "toy_lp1": ("toy", dict(name="toy_lp1"), 0.0),
@@ -30,7 +33,7 @@ CASES = {
 
 def run_case(pkg, orc, case):
     gen, kw, delta_prev = case
-    prob = getattr(pkg.problems, gen)(**kw)
+    prob = getattr(problems, gen)(**kw)
     Q, sd = orc.form_system(prob.J, prob.H, prob.y, prob.s)
     QL = sp.tril(Q, format="csc"); QL.sort_indices()
     F = orc.Factor(QL)          # natural ordering: independent of the library's ordering code

@@ -18,6 +18,8 @@ import numpy as np
 faulthandler.enable()
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import problems  # noqa: E402
 import __graft_entry__ as g  # noqa: E402
 
 
@@ -35,7 +37,7 @@ def main():
             k, v = a.split("=")
             kw[k] = float(v) if "." in v else int(v)
     pkg = g.package()
-    prob = getattr(pkg.problems, gen)(seed=2, **kw)
+    prob = getattr(problems, gen)(seed=2, **kw)
     pars = pkg.Class_parameters()
 
     def solve(shard):

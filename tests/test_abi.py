@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
+import problems
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -36,7 +38,7 @@ def test_library_is_sm100a_only(pkg):
 
 
 def test_numeric_calls_fail_loudly_without_device(pkg):
-    prob = pkg.problems.chain(5, seed=0)
+    prob = problems.chain(5, seed=0)
     h = pkg.Handle(-1)
     h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
     with pytest.raises(pkg.OPBError) as e:
@@ -95,7 +97,7 @@ def test_options_are_validated(pkg):
         h.set_option(key, v)
     with pytest.raises(pkg.OPBError):
         h.set_option("no_such_option", 1)
-    prob = pkg.problems.chain(nh=30, seed=1)
+    prob = problems.chain(nh=30, seed=1)
     h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
     assert h.info("n") == prob.n
     h.close()
@@ -113,7 +115,7 @@ def test_failure_driven_delta_increase_rule(pkg):
             self.calls.append(delta)
             return 1
     pars = pkg.Class_parameters()
-    prob = pkg.problems.toy("toy_lp1")
+    prob = problems.toy("toy_lp1")
     it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=1e-3)
     k = FakeSolver()
     new, inertia = pkg.respond_to_failed_step(it, k, pars, old_delta=1e-4, grad_lag_inf=10.0)

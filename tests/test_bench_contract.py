@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import problems
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -32,5 +34,5 @@ def test_workload_table_is_consistent():
     import __graft_entry__ as g
     pkg = g.package()
     for name, (gen, kw, kws) in bench.WORKLOADS.items():
-        assert hasattr(pkg.problems, gen), name
+        assert hasattr(problems, gen), name
         assert set(kws) <= set(kw) | {"N", "n", "m_gen", "nh", "n_p"}

@@ -10,6 +10,8 @@ import sys
 import numpy as np
 import pytest
 
+import problems
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -26,7 +28,7 @@ def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     pkg = g.package()
-    prob = pkg.problems.sparse_qp(2000, 1000, seed=rank)          # one instance per rank
+    prob = problems.sparse_qp(2000, 1000, seed=rank)          # one instance per rank
     h = pkg.Handle(-1)
     h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
     nnzL = h.info("nnzL_true")

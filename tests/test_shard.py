@@ -15,6 +15,8 @@ import sys
 import numpy as np
 import pytest
 
+import problems
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -32,7 +34,7 @@ def _maps(pkg, prob, world):
                                     ("chain", dict(nh=400)), ("elec", dict(n_p=12))])
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_mapping_properties(pkg, gen, kw, world):
-    prob = getattr(pkg.problems, gen)(seed=1, **kw)
+    prob = getattr(problems, gen)(seed=1, **kw)
     hs = _maps(pkg, prob, world)
     owner = hs[0].symbolic("owner"); top = hs[0].symbolic("top")
     sparent = hs[0].symbolic("sparent"); level = hs[0].symbolic("level")
@@ -66,7 +68,7 @@ def test_mapping_properties(pkg, gen, kw, world):
 
 
 def test_mapping_balances_subtrees(pkg):
-    prob = pkg.problems.sparse_qp(20000, 10000, seed=0)
+    prob = problems.sparse_qp(20000, 10000, seed=0)
     hs = _maps(pkg, prob, 4)
     owner = hs[0].symbolic("owner"); top = hs[0].symbolic("top")
     sf = hs[0].symbolic("sfirst"); rp = hs[0].symbolic("rowptr")
@@ -78,7 +80,7 @@ def test_mapping_balances_subtrees(pkg):
 
 
 def test_unsharded_world_one(pkg):
-    prob = pkg.problems.chain(nh=50, seed=0)
+    prob = problems.chain(nh=50, seed=0)
     h = pkg.Handle(-1)
     h.shard_init(0, 1)
     h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
@@ -101,7 +103,7 @@ def _gloo_worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     pkg = g.package()
-    prob = pkg.problems.pde_control(N=10, seed=0)            # the SAME instance on every rank
+    prob = problems.pde_control(N=10, seed=0)            # the SAME instance on every rank
     shard = pkg.DistShard()
     h = pkg.Handle(-1)
     h.shard_init(shard.rank, shard.world)
@@ -169,7 +171,7 @@ def test_virtual_ranks_delta_loop_failure_is_seen_by_every_rank():
 
 @pytest.mark.gpu
 def test_sharded_handle_requires_attached_peers(pkg):
-    prob = pkg.problems.chain(nh=40, seed=0)
+    prob = problems.chain(nh=40, seed=0)
     h = pkg.Handle(0)
     h.shard_init(0, 2)
     h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
@@ -190,8 +192,8 @@ def _mp_worker(rank, world, port, out):
         report = []
         for gen, kw, neg in (("chain", dict(nh=300), 0.0), ("chain", dict(nh=300), 5.0),
                              ("sparse_qp", dict(n=20000, m_gen=10000), None), ("pde_control", dict(N=20), None)):
-            prob = getattr(pkg.problems, gen)(seed=2, **kw) if neg is None else \
-                getattr(pkg.problems, gen)(seed=2, offdiag_curv=neg, **kw)
+            prob = getattr(problems, gen)(seed=2, **kw) if neg is None else \
+                getattr(problems, gen)(seed=2, offdiag_curv=neg, **kw)
             pars = pkg.Class_parameters(device=rank)
 
             def solve(shard):

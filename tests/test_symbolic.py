@@ -9,6 +9,8 @@ import scipy.sparse as sp
 
 import emulate
 
+import problems
+
 
 def _handle(pkg, prob, **opts):
     h = pkg.Handle(-1)
@@ -19,7 +21,7 @@ def _handle(pkg, prob, **opts):
 
 
 def _problems(pkg):
-    P = pkg.problems
+    P = problems
     return [P.toy(nm) for nm in P.TOY_NAMES] + [
         P.chain(50, seed=1), P.sparse_qp(600, 300, win=5, seed=2), P.elec(20, seed=3), P.pde_control(6, seed=4)]
 
@@ -56,7 +58,7 @@ def test_maps_reproduce_oracle(pkg, orc, opts):
 
 
 def test_ldlt_emulation_inertia(pkg, orc):
-    prob = pkg.problems.chain(20, seed=5, neg_curv=3.0)
+    prob = problems.chain(20, seed=5, neg_curv=3.0)
     h = _handle(pkg, prob)
     S = emulate.Sym(h)
     Mv = emulate.assemble_M_values(h, prob.J.indptr, prob.J.indices, prob.J.data, prob.H.data, prob.y, prob.s)
@@ -74,7 +76,7 @@ def test_ldlt_emulation_inertia(pkg, orc):
 
 
 def test_structure_invariants(pkg):
-    prob = pkg.problems.sparse_qp(3000, 1500, seed=7)
+    prob = problems.sparse_qp(3000, 1500, seed=7)
     h = _handle(pkg, prob)
     S = emulate.Sym(h)
     ns = S.nsuper
@@ -116,7 +118,7 @@ def test_missing_structural_diagonal_is_inserted(pkg):
 
 
 def test_one_based_indices_and_cache(pkg):
-    prob = pkg.problems.chain(30, seed=9)
+    prob = problems.chain(30, seed=9)
     h0 = _handle(pkg, prob)
     h1 = pkg.Handle(-1)
     h1.set_structure(prob.n, prob.m, prob.J.indptr + 1, prob.J.indices + 1, prob.H.indptr + 1, prob.H.indices + 1, 1)
@@ -142,8 +144,8 @@ def test_bad_patterns_are_rejected(pkg):
 
 def test_user_permutation(pkg, orc):
     N = 5
-    prob = pkg.problems.pde_control(N, seed=1)
-    perm = pkg.problems.grid_nd_perm(N, leaf=2)
+    prob = problems.pde_control(N, seed=1)
+    perm = problems.grid_nd_perm(N, leaf=2)
     h = pkg.Handle(-1)
     h.set_permutation(perm)
     h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
@@ -160,7 +162,7 @@ def test_user_permutation(pkg, orc):
 
 def test_forward_gather_lists_are_the_transpose_of_rel(pkg):
     """gptr/gsrc/gch (forward-solve gather lists) against the child-by-child scatter through `rel`."""
-    prob = pkg.problems.sparse_qp(3000, 1500, seed=4)
+    prob = problems.sparse_qp(3000, 1500, seed=4)
     h = pkg.Handle(-1)
     h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
     sfirst, sparent, rowptr, rel = (h.symbolic(k) for k in ("sfirst", "sparent", "rowptr", "rel"))
@@ -196,7 +198,7 @@ def test_update_block_storage_reuses_memory_without_overlap(pkg, gen, kw):
     """CBoff comes from a level-lifetime allocator: block s is live on the levels
     [level(s), level(parent(s))]; two blocks that are live on a common level must not overlap, and
     the arena must not be larger than the prefix-sum layout."""
-    prob = getattr(pkg.problems, gen)(seed=3, **kw)
+    prob = getattr(problems, gen)(seed=3, **kw)
     h = pkg.Handle(-1)
     h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
     sparent, rowptr, level, cboff = (h.symbolic(k) for k in ("sparent", "rowptr", "level", "CBoff"))
