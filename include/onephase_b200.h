@@ -64,7 +64,8 @@ int opb_set_stream(opb_handle* h, void* cuda_stream);
  * Numeric (any time): "attempts_per_sync" (delta-loop attempts enqueued per host
  * synchronisation, default 2), "graphs" (0/1: replay the launch sequences from CUDA graphs),
  * "outer_block" (columns of the outer block of the panel updates, 128 * 2^k, default 4096),
- * "lookahead" (0/1: side-stream look-ahead in the blocked panel factorisation),
+ * "lookahead" (0/1: side-stream look-ahead in the blocked panel factorisation), "chain_priority" (0/1: the
+ * latency chain of that factorisation runs on the highest-priority stream, default 1),
  * "barrier_timeout_s" (sharded instance: seconds a rank waits for its peers, default 20). */
 int opb_set_option(opb_handle* h, const char* key, double value);
 /* Optional fill-reducing permutation supplied by the caller (0-based, perm[new] = old). */
@@ -117,6 +118,13 @@ int opb_ls_factor_csc(opb_handle* h, int64_t dim, const int64_t* colptr, const i
                       int64_t n_pos_expected, int64_t m_neg_expected, int* inertia_ok);
 /* ls_solve! / ls_solve  (julia.jl:99-113): sol = F \ rhs with the last factor. */
 int opb_ls_solve(opb_handle* h, const double* rhs, double* sol);
+
+/* eval_diag_J_T_J(iter, diag_vals)  (utils/eval.jl:89-100): out[i] = sum_j J[j,i]^2 * diag_vals[j]
+ * for an m x n CSC matrix, in the reference's operation order.  compute_schur_diag
+ * (kkt_system_solver.jl:296-300) = diag(H) + this with diag_vals = y ./ s; used by the symmetric
+ * KKT solver (symmetric.jl:49).  Needs no opb_set_structure. */
+int opb_eval_diag_JtDJ(opb_handle* h, int64_t n, int64_t m, const int64_t* J_colptr, const int64_t* J_rowval,
+                       const double* J_nzval, int index_base, const double* diag_vals, double* out);
 
 /* --- device-resident variants used by bench.py's `value` leg: inputs are uploaded
  *     once, the timed region launches kernels only. --- */

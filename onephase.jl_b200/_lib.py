@@ -30,7 +30,7 @@ EXPORTS = [
     "opb_upload_values", "opb_upload_rhs", "opb_form_resident", "opb_delta_loop_resident",
     "opb_direction_resident", "opb_solve_resident", "opb_sync_state", "opb_get_info",
     "opb_get_symbolic", "opb_get_L_values", "opb_launch_count", "opb_version",
-    "opb_shard_init", "opb_shard_export", "opb_shard_attach", "opb_profile_factor",
+    "opb_shard_init", "opb_shard_export", "opb_shard_attach", "opb_profile_factor", "opb_eval_diag_JtDJ",
 ]
 SHARD_BLOB_BYTES = 320
 
@@ -90,6 +90,7 @@ def load():
     L.opb_shard_export.argtypes = [vp, ctypes.c_char_p]
     L.opb_shard_attach.argtypes = [vp, ci, ctypes.c_char_p]
     L.opb_profile_factor.argtypes = [vp, f64, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, c_intp]
+    L.opb_eval_diag_JtDJ.argtypes = [vp, i64, i64, c_i64p, c_i64p, c_f64p, ci, c_f64p, c_f64p]
     L.opb_launch_count.restype = ctypes.c_longlong
     L.opb_version.restype = ctypes.c_char_p
     _lib = L
@@ -237,6 +238,13 @@ class Handle:
         assert sol.dtype == np.float64 and sol.flags.c_contiguous
         self.check(self.L.opb_ls_solve(self.h, pf(r), pf(sol)))
         return sol
+
+    def diag_JtDJ(self, n, m, Jp, Ji, Jx, diag_vals, index_base=0):
+        Jp, Ji, Jx, d = i64(Jp), i64(Ji), f64(Jx), f64(diag_vals)
+        assert d.shape[0] == m
+        out = np.empty(n)
+        self.check(self.L.opb_eval_diag_JtDJ(self.h, n, m, pi(Jp), pi(Ji), pf(Jx), index_base, pf(d), pf(out)))
+        return out
 
     # --- resident variants (bench)
     def upload_values(self, Jx, Hx, y, s):

@@ -153,7 +153,7 @@ __global__ void ctl_begin_kernel(DeltaState* s) {
     s->fail = 0;
 }
 
-__global__ void ctl_end_kernel(DeltaState* s) {
+__device__ void ctl_end_rule(DeltaState* s) {
     if (s->done) return;
     s->num_fac += 1;
     if (!s->fail) { s->done = 1; s->status = 1; return; }
@@ -163,10 +163,38 @@ __global__ void ctl_end_kernel(DeltaState* s) {
     if (s->it > s->max_it) { s->done = 1; s->status = -1; return; }
     s->delta = next_delta(s);
 }
+__global__ void ctl_end_kernel(DeltaState* s) { ctl_end_rule(s); }
+// the same rule as the last node of the body of a CUDA-graph WHILE node: the device decides
+// whether the body (one factorisation attempt) runs again -- the host is not involved
+__global__ void ctl_end_loop_kernel(DeltaState* s, cudaGraphConditionalHandle loop) {
+    ctl_end_rule(s);
+    cudaGraphSetConditional(loop, s->done ? 0u : 1u);
+}
+
+// eval_diag_J_T_J (utils/eval.jl:89-100): one thread per column, the reference's operation
+// order (a^2 first, times diag_vals[row], summed over the rows ascending)
+__global__ void diag_JtDJ_kernel(const int64_t* __restrict__ Jp, const int64_t* __restrict__ Ji,
+                                 const double* __restrict__ Jx, const double* __restrict__ dv,
+                                 double* __restrict__ out, int n, int base) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc = 0.0;
+    for (int64_t p = Jp[i] - base; p < Jp[i + 1] - base; p++) {
+        const double a = Jx[p];
+        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(a, a), dv[Ji[p] - base]));
+    }
+    out[i] = acc;
+}
 
 inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
 
 }  // namespace
+
+void launch_diag_JtDJ(const int64_t* Jp, const int64_t* Ji, const double* Jx, const double* dv, double* out,
+                      int n, int base, cudaStream_t st) {
+    diag_JtDJ_kernel<<<nblk(n, 128), 128, 0, st>>>(Jp, Ji, Jx, dv, out, n, base);
+    count_launch();
+}
 
 void launch_sigma_T(const double* Jv, const int* Jrow, const double* y, const double* s,
                     double* sigma, double* T, int64_t nnzJ, int m, cudaStream_t st) {
@@ -218,6 +246,9 @@ void launch_scatter_fronts(const double* Mval, const int64_t* amap, const int64_
 
 void launch_ctl_begin(DeltaState* st_d, cudaStream_t st) { ctl_begin_kernel<<<1, 1, 0, st>>>(st_d); }
 void launch_ctl_end(DeltaState* st_d, cudaStream_t st) { ctl_end_kernel<<<1, 1, 0, st>>>(st_d); }
+void launch_ctl_end_loop(DeltaState* st_d, unsigned long long loop_handle, cudaStream_t st) {
+    ctl_end_loop_kernel<<<1, 1, 0, st>>>(st_d, (cudaGraphConditionalHandle)loop_handle);
+}
 void launch_ctl_init(DeltaState* st_d, double delta_prev, double delta_zero, double delta_min,
                      double delta_max, double delta_start, double inc, double dec, int max_it,
                      int mode, cudaStream_t st) {
@@ -246,8 +277,10 @@ cudaError_t preload_assembly() {
     e = cudaFuncGetAttributes(&a, scatter_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, ctl_begin_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, ctl_end_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, ctl_end_loop_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, ctl_init_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, ctl_single_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, diag_JtDJ_kernel); if (e != cudaSuccess) return e;
     return cudaSuccess;
 }
 

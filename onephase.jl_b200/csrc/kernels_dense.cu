@@ -147,10 +147,15 @@ __device__ __forceinline__ void gemm_kstep(const double* As, const double* Bs, i
 // barriers), warps 0..7 run the DMMAs and hand the stage back through the `empty` barriers; no
 // block-wide barrier inside the K loop.  On return every stage has been consumed (block barrier),
 // so the caller may reuse the shared memory; acc is valid on the compute warps only.
-template <bool B_KC>
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+// stages before the end of the K loop at which the compute warps run `hook` (front_cb_kernel:
+// L2 prefetch of the children's update-block entries the epilogue is about to merge)
+constexpr int HOOK_LEAD = 8;
+
+template <bool B_KC, class Hook = NoHook>
 __device__ __forceinline__ void gemm_mainloop(GemmSmem& sm, const double* Ag, int lda, int mrows,
                                               const double* Bg, int ldb, int nrows, int K,
-                                              double (&acc)[8][4][2]) {
+                                              double (&acc)[8][4][2], Hook hook = Hook()) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int a = 0; a < 8; a++)
@@ -174,7 +179,9 @@ __device__ __forceinline__ void gemm_mainloop(GemmSmem& sm, const double* Ag, in
         const int q = lane & 3, g = lane >> 2;
         const int aoff = wm * 64 + g;
         const int boff = B_KC ? (wn * 32 + g) * LDK : wn * 32 + g;
+        const int hook_at = nkb > HOOK_LEAD ? nkb - HOOK_LEAD : 0;
         for (int kb = 0; kb < nkb; kb++) {
+            if (kb == hook_at) hook();
             const int stage = kb % STAGES;
             mbar_wait(&sm.full[stage], (unsigned)((kb / STAGES) & 1));
             const double* As = sm.A[stage] + aoff;
@@ -573,8 +580,22 @@ big_extend_add_panel_kernel(DevSym S, const int* __restrict__ list, double* __re
         for (int tt = t0 + tx; tt < t1; tt += 32) {
             const int pi = relc[tt];
             const int ue = min(uc, tt + 1);
-            for (int u = ty; u < ue; u += 8)
-                Lval[d.loff + pi + (size_t)relc[u] * d.ld] += cb[tt + (size_t)u * rc];
+            // four independent read-modify-writes in flight per thread (distinct columns)
+            for (int u = ty; u < ue; u += 32) {
+                double v[4], l[4];
+                size_t off[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int uu = u + 8 * q;
+                    const bool ok = uu < ue;
+                    off[q] = (size_t)d.loff + pi + (size_t)relc[ok ? uu : u] * d.ld;
+                    v[q] = ok ? cb[tt + (size_t)uu * rc] : 0.0;
+                    l[q] = ok ? Lval[off[q]] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (u + 8 * q < ue) Lval[off[q]] = l[q] + v[q];
+            }
         }
         __syncthreads();     // the next child may hit the same panel entries from other threads
     }
@@ -665,6 +686,52 @@ chol_panel_update_kernel(DevSym S, const int* __restrict__ list, double* __restr
 // update block of a medium / big front, written once:
 //   CB[I,J] = sum_children (extend-add) - L21[I,:] * L21[J,:]^T      (K = all c pivot columns)
 constexpr int TLD = BM + 1;
+
+// rows [t0, t1) and columns [u0, u1) of child `ch` (positions in its update block) that land in
+// the tile [ri, ri+BM) x [rj, rj+BN) of the parent front
+struct ChildRange { int t0, t1, u0, u1, rc; const int* relc; };
+__device__ __forceinline__ int lower_bound_rel(const int* __restrict__ relc, int lo, int hi, int v) {
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ ChildRange child_range(const DevSym& S, int ch, int ri, int rj) {
+    ChildRange R;
+    const int64_t rp = S.rowptr[ch];
+    R.rc = (int)(S.rowptr[ch + 1] - rp);
+    R.relc = S.rel + rp;
+    R.t0 = lower_bound_rel(R.relc, 0, R.rc, ri);
+    R.t1 = lower_bound_rel(R.relc, R.t0, R.rc, ri + BM);
+    R.u0 = lower_bound_rel(R.relc, 0, R.rc, rj);
+    R.u1 = lower_bound_rel(R.relc, R.u0, R.rc, rj + BN);
+    return R;
+}
+
+// pulls the children's entries of this tile towards L2 a few stages before the K loop ends, so
+// the merge below finds them on chip instead of paying a DRAM round trip per dependent step
+struct CbPrefetch {
+    const DevSym& S; const double* CB; int s, ri, rj;
+    __device__ __forceinline__ void operator()() const {
+        const int tid = threadIdx.x;        // compute warps only: 0 .. GEMM_CWARPS*32-1
+        for (int k = S.child_ptr[s]; k < S.child_ptr[s + 1]; k++) {
+            const int ch = S.child_list[k];
+            const ChildRange R = child_range(S, ch, ri, rj);
+            if (R.t1 <= R.t0 || R.u1 <= R.u0) continue;
+            const double* __restrict__ cb = child_cb(S, CB, ch);
+            // one 128-byte line = 16 doubles; a column segment of <= 128 rows spans <= 9 lines
+            const int nu = R.u1 - R.u0;
+            for (int idx = tid; idx < nu * 9; idx += GEMM_CWARPS * 32) {
+                const int u = R.u0 + idx / 9, ln = idx % 9;
+                const int tb = max(R.t0, u);
+                const int tt = tb + 16 * ln;
+                if (tt < R.t1 + 15 && tt < R.rc) {
+                    const double* p = cb + (size_t)u * R.rc + min(tt, R.t1 - 1);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                }
+            }
+        }
+    }
+};
+
 __global__ void __launch_bounds__(GEMM_THREADS)
 front_cb_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lval,
                 double* __restrict__ CB, DeltaState* st) {
@@ -685,7 +752,8 @@ front_cb_kernel(DevSym S, const int* __restrict__ list, const double* __restrict
     const double* Ag = Lval + d.loff + ri;
     const double* Bg = Lval + d.loff + rj;
     double acc[8][4][2];
-    gemm_mainloop<false>(sm, Ag, d.ld, min(BM, d.N - ri), Bg, d.ld, min(BN, d.N - rj), d.c, acc);
+    gemm_mainloop<false>(sm, Ag, d.ld, min(BM, d.N - ri), Bg, d.ld, min(BN, d.N - rj), d.c, acc,
+                         CbPrefetch{S, CB, d.s, ri, rj});
     // the stage buffers are free now: reuse them as the 128 x 128 tile (ld 129)
     double* T = reinterpret_cast<double*>(smraw);
     if (gemm_compute_warp()) {
@@ -697,31 +765,41 @@ front_cb_kernel(DevSym S, const int* __restrict__ list, const double* __restrict
                 for (int e = 0; e < 2; e++) T[acc_row(mt) + acc_col(nt, e) * TLD] = -acc[mt][nt][e];
     }
     __syncthreads();
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = GEMM_THREADS / 32;
     for (int k = S.child_ptr[d.s]; k < S.child_ptr[d.s + 1]; k++) {
         const int ch = S.child_list[k];
-        const int64_t rp = S.rowptr[ch];
-        const int rc = (int)(S.rowptr[ch + 1] - rp);
-        const int* __restrict__ relc = S.rel + rp;
-        // child rows landing in [ri, ri+BM) and child columns landing in [rj, rj+BN)
-        int lo = 0, hi = rc;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < ri) lo = mid + 1; else hi = mid; }
-        const int t0 = lo;
-        hi = rc;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < ri + BM) lo = mid + 1; else hi = mid; }
-        const int t1 = lo;
-        lo = 0; hi = rc;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < rj) lo = mid + 1; else hi = mid; }
-        const int u0 = lo;
-        hi = rc;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < rj + BN) lo = mid + 1; else hi = mid; }
-        const int u1 = lo;
-        const int nt2 = t1 - t0, nu = u1 - u0;
-        if (nt2 <= 0 || nu <= 0) continue;          // uniform across the CTA
+        const ChildRange R = child_range(S, ch, ri, rj);
+        if (R.t1 <= R.t0 || R.u1 <= R.u0) continue;          // uniform across the CTA
         const double* __restrict__ cb = child_cb(S, CB, ch);
-        for (int idx = tid; idx < nt2 * nu; idx += GEMM_THREADS) {
-            const int tt = t0 + idx % nt2, u = u0 + idx / nt2;
-            if (tt >= u) T[(relc[tt] - ri) + (relc[u] - rj) * TLD] += cb[tt + (size_t)u * rc];
+        const int* __restrict__ relc = R.relc;
+        // a warp takes two child columns per round, a lane up to 4 rows of each: 8 independent
+        // loads in flight per lane before the first shared-memory update.  Distinct (row, column)
+        // pairs of one child land on distinct tile entries, so there are no conflicts inside a child;
+        // the barrier orders the children (ascending: fixed summation order).
+        for (int u = R.u0 + 2 * warp; u < R.u1; u += 2 * NW) {
+            double v[2][4];
+            int dst[2][4];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int uu = u + h;
+                const bool cok = uu < R.u1;
+                const int tb = max(R.t0, uu);
+                const int pc = cok ? (relc[uu] - rj) * TLD - ri : 0;
+                const double* col = cb + (size_t)(cok ? uu : u) * R.rc;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int tt = tb + lane + 32 * q;
+                    const bool ok = cok && tt < R.t1;
+                    v[h][q] = ok ? col[tt] : 0.0;
+                    dst[h][q] = ok ? relc[tt] + pc : -1;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (dst[h][q] >= 0) T[dst[h][q]] += v[h][q];
         }
         __syncthreads();
     }
@@ -1091,18 +1169,26 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
             count_launch();
             return true;
         };
-        bool pending_join = false;       // an update is still running on the side stream
+        // Two streams: C carries the latency chain (diagonal block, TRSM, update of the next block
+        // column), B the bulk of the right-looking updates.  Classic mode: C = the caller's stream,
+        // B = the side stream.  With a high-priority side stream (side->chain_on_side) the roles
+        // are swapped: the chain's short kernels then win every SM a bulk tile gives back instead
+        // of queueing behind the whole bulk grid.
+        cudaStream_t C = st, B = st;
+        if (side) { if (side->chain_on_side) C = side->stream; else B = side->stream; }
+        if (C != st) { cudaEventRecord(side->start, st); cudaStreamWaitEvent(C, side->start, 0); }
+        bool pending_join = false;       // a bulk update is still running on B
         for (int t = 0; t < nsteps; t++) {
             const int cnt = L.step_count[t];
             if (cnt <= 0) break;
             const int maxN = L.step_maxN[t];
-            chol_diag_kernel<<<cnt, PT, diag_smem(), st>>>(S, list, Lval, Xinv, t, st_d);
+            chol_diag_kernel<<<cnt, PT, diag_smem(), C>>>(S, list, Lval, Xinv, t, st_d);
             count_launch();
             const int rem = maxN - t * WB;     // rows from the start of the block (upper bound)
             if (rem <= 0) continue;
             const int nrow = (rem + BM - 1) / BM + 1;
             dim3 gt(nrow, cnt);
-            chol_trsm_kernel<<<gt, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, list, Lval, Xinv, t, st_d);
+            chol_trsm_kernel<<<gt, GEMM_THREADS, sizeof(GemmSmem), C>>>(S, list, Lval, Xinv, t, st_d);
             count_launch();
             // Recursive (binary) schedule of the right-looking updates: with tb blocks finished and
             // 2^j the largest power of two dividing tb, the last 2^j blocks update the next 2^j
@@ -1116,23 +1202,24 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
             const int cbeg = tb * WB;
             if (wblk >= sub) { k0 = (tb - sub) * WB; klen = sub * WB; cend = 1 << 30; }
             else { k0 = (tb - wblk) * WB; klen = wblk * WB; cend = (tb + wblk) * WB; }
-            // the previous step's side update wrote the columns this step updates
-            if (pending_join) { cudaStreamWaitEvent(st, side->join, 0); pending_join = false; }
+            // the previous step's bulk update wrote the columns this step updates
+            if (pending_join) { cudaStreamWaitEvent(C, side->join, 0); pending_join = false; }
             const bool has_rest = cend > cbeg + WB && tb + 1 < nsteps && L.step_count[tb + 1] > 0;
             if (side && has_rest) {
-                // look-ahead: block column tb (all the next diagonal block and TRSM need) on the main
-                // stream, the columns beyond it on the side stream, concurrently with those kernels
-                cudaEventRecord(side->fork, st);
-                cudaStreamWaitEvent(side->stream, side->fork, 0);
-                update(side->stream, k0, klen, cbeg + WB, cend);
-                cudaEventRecord(side->join, side->stream);      // always rejoin (stream capture demands it)
+                // look-ahead: block column tb (all the next diagonal block and TRSM need) on the chain
+                // stream, the columns beyond it on the bulk stream, concurrently with those kernels
+                cudaEventRecord(side->fork, C);
+                cudaStreamWaitEvent(B, side->fork, 0);
+                update(B, k0, klen, cbeg + WB, cend);
+                cudaEventRecord(side->join, B);      // always rejoin (stream capture demands it)
                 pending_join = true;
-                update(st, k0, klen, cbeg, cbeg + WB);
+                update(C, k0, klen, cbeg, cbeg + WB);
             } else {
-                update(st, k0, klen, cbeg, cend);
+                update(C, k0, klen, cbeg, cend);
             }
         }
-        if (pending_join) cudaStreamWaitEvent(st, side->join, 0);
+        if (pending_join) cudaStreamWaitEvent(C, side->join, 0);
+        if (C != st) { cudaEventRecord(side->fork, C); cudaStreamWaitEvent(st, side->fork, 0); }
     }
     // update blocks of all medium and big fronts, written once
     {

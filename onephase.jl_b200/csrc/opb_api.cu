@@ -197,6 +197,8 @@ struct opb_handle {
     DBuf<double> Jv, Hv, y, s, sigma, T, Rval, Mval, sdiag, Lval, CB;
     DBuf<double> dual_r, primal_r, comp_r, b, res, dx, dy, ds, tm, xw, xw2, uw, userval, Xinv, Twork;
     DBuf<unsigned long long> red;
+    DBuf<int64_t> scr_i0, scr_i1;        // scratch of opb_eval_diag_JtDJ
+    DBuf<double> scr_d0, scr_d1, scr_d2;
     char* d_state_raw = nullptr;
     DeltaState* d_state = nullptr;
     DeltaState h_state{};
@@ -206,9 +208,14 @@ struct opb_handle {
     // solve): captured once per structure, replayed afterwards
     struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; int key = -1; };
     GraphSlot g_attempt, g_direction, g_solve;
+    // the whole delta loop as ONE graph: a WHILE conditional node whose body is an attempt and
+    // whose condition is set on the device by the last kernel of the body (ctl_end_loop_kernel)
+    GraphSlot g_loop;
+    bool loop_graph = true;            // option "loop_graph"
+    long long loop_pending = 0;        // launches per attempt of a loop whose attempt count is not known yet
     bool use_graphs = true;
     void drop_graphs() {
-        for (GraphSlot* g : {&g_attempt, &g_direction, &g_solve}) {
+        for (GraphSlot* g : {&g_attempt, &g_direction, &g_solve, &g_loop}) {
             if (g->exec) cudaGraphExecDestroy(g->exec);
             *g = GraphSlot();
         }
@@ -303,9 +310,17 @@ int opb_create(opb_handle** out, int device_id, unsigned flags) {
         if (e != cudaSuccess) return h->cuda_fail(e, "dense_configure (is this an sm_100a device?)");
         e = h->red.alloc(8);
         if (e != cudaSuccess) return h->cuda_fail(e, "cudaMalloc(red)");
-        e = cudaStreamCreateWithFlags(&h->side.stream, cudaStreamNonBlocking);
+        {
+            // the side stream gets the highest priority the device offers: it carries the latency
+            // chain of the blocked panel factorisation (option "chain_priority", default on)
+            int least = 0, greatest = 0;
+            cudaDeviceGetStreamPriorityRange(&least, &greatest);
+            e = cudaStreamCreateWithPriority(&h->side.stream, cudaStreamNonBlocking, greatest);
+            h->side.chain_on_side = greatest < least;
+        }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.join, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.start, cudaEventDisableTiming);
         if (e != cudaSuccess) return h->cuda_fail(e, "side stream");
         for (auto pre : {preload_assembly, preload_vec, preload_solve, preload_factor, preload_dense, preload_shard}) {
             e = pre();
@@ -326,12 +341,14 @@ int opb_destroy(opb_handle* h) {
                                 &h->dx, &h->dy, &h->ds, &h->tm, &h->xw, &h->xw2, &h->uw, &h->userval, &h->Xinv, &h->Twork};
         for (auto* b : bufs) b->release();
         h->red.release();
+        h->scr_i0.release(); h->scr_i1.release(); h->scr_d0.release(); h->scr_d1.release(); h->scr_d2.release();
         h->drop_graphs();
         for (int p = 0; p < MAX_SHARD; p++) h->close_peer(p);
         h->ktimer.release();
         if (h->side.stream) { cudaStreamSynchronize(h->side.stream); cudaStreamDestroy(h->side.stream); }
         if (h->side.fork) cudaEventDestroy(h->side.fork);
         if (h->side.join) cudaEventDestroy(h->side.join);
+        if (h->side.start) cudaEventDestroy(h->side.start);
         if (h->d_flags) cudaFree(h->d_flags);
         if (h->d_state_raw) cudaFree(h->d_state_raw);
         if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -365,7 +382,9 @@ int opb_set_option(opb_handle* h, const char* key, double v) {
     else if (k == "outer_block") { h->outer_block = std::max(WB, ((int)v / WB) * WB); h->drop_graphs(); }
     else if (k == "barrier_timeout_s") { h->barrier_timeout_s = v; h->sctx.timeout_clocks = (long long)(v * 2.0e9); h->drop_graphs(); }
     else if (k == "lookahead") { h->lookahead = v != 0; h->drop_graphs(); }
+    else if (k == "chain_priority") { h->side.chain_on_side = v != 0; h->drop_graphs(); }
     else if (k == "graphs") { h->use_graphs = v != 0; h->drop_graphs(); }
+    else if (k == "loop_graph") { h->loop_graph = v != 0; h->drop_graphs(); }
     else return h->fail(OPB_ERR_INVALID, "unknown option " + k);
     return OPB_OK;
 }
@@ -652,7 +671,7 @@ static int stage_form(opb_handle* h) {
     return OPB_OK;
 }
 
-static void enqueue_attempt_raw(opb_handle* h, KernelTimer* timer = nullptr) {
+static void enqueue_attempt_raw(opb_handle* h, KernelTimer* timer = nullptr, unsigned long long loop_handle = 0) {
     Bundle& B = *h->B;
     cudaStream_t st = h->stream;
     launch_ctl_begin(h->d_state, st);
@@ -664,7 +683,42 @@ static void enqueue_attempt_raw(opb_handle* h, KernelTimer* timer = nullptr) {
         launch_trtri(h->dev, B.trtri, B.d_sched.p, h->Lval.p, h->Xinv.p, h->Twork.p, h->d_state, st);
     // sharded: every rank learns about a failed pivot anywhere before the delta rule is applied
     if (h->sharded()) launch_shard_barrier(h->sctx, st);
-    launch_ctl_end(h->d_state, st);
+    if (loop_handle) launch_ctl_end_loop(h->d_state, loop_handle, st);
+    else launch_ctl_end(h->d_state, st);
+}
+
+// Build (once per structure) the graph  WHILE(!done) { attempt }  -- delta_strategy.jl:37-114 with
+// the loop itself on the device.  Returns false when this runtime cannot do it (the caller falls
+// back to host-driven chunks of attempts).
+static bool build_loop_graph(opb_handle* h) {
+    cudaGraph_t graph = nullptr;
+    if (cudaGraphCreate(&graph, 0) != cudaSuccess) { cudaGetLastError(); return false; }
+    cudaGraphConditionalHandle ch;
+    bool ok = cudaGraphConditionalHandleCreate(&ch, graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = ch;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    ok = ok && cudaGraphAddNode(&node, graph, nullptr, 0, &np) == cudaSuccess;
+    const long long l0 = g_launches.load();
+    if (ok) {
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        ok = cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+        if (ok) {
+            enqueue_attempt_raw(h, nullptr, (unsigned long long)ch);
+            cudaGraph_t out = nullptr;
+            ok = cudaStreamEndCapture(h->stream, &out) == cudaSuccess;
+        }
+    }
+    h->g_loop.launches = g_launches.load() - l0;
+    g_launches.store(l0);
+    if (ok) ok = cudaGraphInstantiate(&h->g_loop.exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) { cudaGetLastError(); h->g_loop = opb_handle::GraphSlot(); return false; }
+    h->g_loop.key = h->mode;
+    return true;
 }
 
 static void enqueue_attempt(opb_handle* h) {
@@ -676,6 +730,10 @@ static int read_state(opb_handle* h) {
     int shard_err = 0;
     if (h->sharded()) CK(cudaMemcpyAsync(&shard_err, h->sctx.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->loop_pending) {       // the device ran num_fac attempts of the loop graph; one was counted at launch
+        if (h->h_state.num_fac > 1) count_launch((int)((h->h_state.num_fac - 1) * h->loop_pending));
+        h->loop_pending = 0;
+    }
     if (shard_err) {
         unsigned long long f[2 * MAX_SHARD + 2] = {0};
         cudaMemcpy(f, h->d_flags, sizeof f, cudaMemcpyDeviceToHost);
@@ -692,6 +750,17 @@ static int read_state(opb_handle* h) {
 
 // enqueue attempts until the device controller reports done
 static int run_delta_loop(opb_handle* h, bool first_chunk_only) {
+    // one graph launch runs the whole loop on the device; nothing to wait for here
+    if (h->use_graphs && h->loop_graph && !h->sharded()) {
+        if (h->g_loop.exec && h->g_loop.key != h->mode) { cudaGraphExecDestroy(h->g_loop.exec); h->g_loop = opb_handle::GraphSlot(); }
+        if (h->g_loop.exec || build_loop_graph(h)) {
+            CK(cudaGraphLaunch(h->g_loop.exec, h->stream));
+            count_launch((int)h->g_loop.launches);
+            h->loop_pending = h->g_loop.launches;
+            return OPB_OK;
+        }
+        h->loop_graph = false;
+    }
     for (;;) {
         for (int a = 0; a < h->attempts_per_sync; a++) enqueue_attempt(h);
         CK(cudaGetLastError());
@@ -759,7 +828,7 @@ int opb_delta_loop_resident(opb_handle* h, double delta_prev, double delta_zero,
     rc = run_delta_loop(h, false);
     if (rc) return rc;
     h->ready = opb_handle::FACTORED;
-    return OPB_OK;
+    return OPB_OK;       // with the loop graph the call is asynchronous: opb_sync_state / the next read waits
 }
 
 int opb_factor_delta_loop(opb_handle* h, double delta_prev, double delta_zero, double delta_min,
@@ -767,6 +836,7 @@ int opb_factor_delta_loop(opb_handle* h, double delta_prev, double delta_zero, d
                           double* delta_out, int* num_fac_out, int* status_out) {
     int rc = opb_delta_loop_resident(h, delta_prev, delta_zero, delta_min, delta_max, delta_start, inc, dec, max_it);
     if (rc) return rc;
+    rc = read_state(h); if (rc) return rc;
     if (delta_out) *delta_out = h->h_state.delta;
     if (num_fac_out) *num_fac_out = h->h_state.num_fac;
     if (status_out) *status_out = h->h_state.status;
@@ -1003,6 +1073,29 @@ int opb_ls_solve(opb_handle* h, const double* rhs, double* sol) {
     launch_permute_out_add(h->xw.p, B.d_perm.p, h->b.p, n, 0, st);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(sol, h->b.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return OPB_OK;
+}
+
+// eval_diag_J_T_J (utils/eval.jl:89-100), the building block of compute_schur_diag
+// (kkt_system_solver.jl:296-300): out[i] = sum_j J[j,i]^2 * diag_vals[j]
+int opb_eval_diag_JtDJ(opb_handle* h, int64_t n, int64_t m, const int64_t* Jp, const int64_t* Ji,
+                       const double* Jx, int base, const double* diag_vals, double* out) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!Jp || !out || n <= 0 || m < 0 || (base != 0 && base != 1)) return h->fail(OPB_ERR_INVALID, "bad arguments");
+    const int64_t nnz = Jp[n] - base;
+    if (nnz < 0 || (nnz > 0 && (!Ji || !Jx || !diag_vals))) return h->fail(OPB_ERR_INVALID, "bad arguments");
+    cudaStream_t st = h->stream;
+    CK(h->scr_i0.alloc(n + 1)); CK(h->scr_i1.alloc(nnz)); CK(h->scr_d0.alloc(nnz)); CK(h->scr_d1.alloc(m)); CK(h->scr_d2.alloc(n));
+    CK(cudaMemcpyAsync(h->scr_i0.p, Jp, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    if (nnz) {
+        CK(cudaMemcpyAsync(h->scr_i1.p, Ji, nnz * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->scr_d0.p, Jx, nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (m) CK(cudaMemcpyAsync(h->scr_d1.p, diag_vals, m * sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_diag_JtDJ(h->scr_i0.p, h->scr_i1.p, h->scr_d0.p, h->scr_d1.p, h->scr_d2.p, (int)n, base, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->scr_d2.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return OPB_OK;
 }

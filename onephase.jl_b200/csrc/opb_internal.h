@@ -161,17 +161,21 @@ void launch_scatter_fronts(const double* Mval, const int64_t* amap, const int64_
                            const DeltaState* st_d, int use_sdiag, cudaStream_t st);
 void launch_ctl_begin(DeltaState* st_d, cudaStream_t st);
 void launch_ctl_end(DeltaState* st_d, cudaStream_t st);
+void launch_ctl_end_loop(DeltaState* st_d, unsigned long long loop_handle, cudaStream_t st);
 void launch_ctl_init(DeltaState* st_d, double delta_prev, double delta_zero, double delta_min,
                      double delta_max, double delta_start, double inc, double dec, int max_it,
                      int mode, cudaStream_t st);
 void launch_ctl_single(DeltaState* st_d, double delta, int mode, cudaStream_t st);
+void launch_diag_JtDJ(const int64_t* Jp, const int64_t* Ji, const double* Jx, const double* dv, double* out,
+                      int n, int base, cudaStream_t st);
 
 // Second stream of a handle: the part of a panel update that does not touch the next block
 // column runs there, concurrently with the (latency-bound) diagonal-block and TRSM kernels of
 // the next step.  Fork / join through the two events (also while the main stream is captured).
 struct SideStream {
     cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, start = nullptr;
+    bool chain_on_side = false;   // the side stream has the highest priority and runs the latency chain
 };
 
 // Optional per-kernel timing of one factorisation attempt (opb_profile_factor): CUDA events

@@ -361,6 +361,210 @@ def diag_min(kkt_solver):
     return kkt_solver.diag_min()
 
 
+# ---------------------------------------------------------------------------
+# helpers of kkt_system_solver.jl:296-300 / utils/eval.jl:89-100 / init/guess-vars.jl:128-169
+# ---------------------------------------------------------------------------
+def eval_diag_J_T_J(it, diag_vals, handle=None, device=0):
+    """eval.jl:89-100: di[i] = sum_j J[j,i]^2 * diag_vals[j], on the device (column-parallel kernel,
+    the reference's operation order: square first, rows ascending)."""
+    J = _csc(it.J)
+    h = handle or _scratch_handle(device)
+    return h.diag_JtDJ(J.shape[1], J.shape[0], J.indptr, J.indices, J.data, diag_vals)
+
+
+def compute_schur_diag(it, handle=None, device=0):
+    """kkt_system_solver.jl:296-300: diag(H) + eval_diag_J_T_J(iter, y ./ s)."""
+    H = _csc(it.H)
+    return H.diagonal() + eval_diag_J_T_J(it, np.asarray(it.y, dtype=np.float64) / np.asarray(it.s, dtype=np.float64),
+                                          handle, device)
+
+
+_SCRATCH = {}
+
+
+def _scratch_handle(device):
+    if device not in _SCRATCH:
+        _SCRATCH[device] = _lib.Handle(device)
+    return _SCRATCH[device]
+
+
+def estimate_y_tilde(J, g, pars=None, device=0):
+    """init/guess-vars.jl:128-169 (the Cholesky branch): y = -J * (cholesky(lambda I + J'J) solve of -g), lambda = 1e-4.
+    The matrix is the primal Schur complement with y./s = 1 and H = lambda I, so it is assembled,
+    factorised and solved by the same device path (opb_form / opb_factor / opb_ls_solve).  Like
+    the reference, any failure returns ones(m)."""
+    J = _csc(J)
+    m, n = J.shape
+    lam = 1e-4
+    try:
+        h = _lib.Handle(pars.device if pars is not None else device)
+        try:
+            eye = sp.identity(n, format="csc")
+            h.set_structure(n, m, J.indptr, J.indices, eye.indptr, eye.indices, 0)
+            h.form(J.data, np.full(n, lam), np.ones(m), np.ones(m), want_diag=False)
+            if h.factor(0.0) != 1:
+                raise RuntimeError("lambda I + J'J not positive definite")      # PosDefException in the reference
+            dx = h.ls_solve(-np.asarray(g, dtype=np.float64))
+        finally:
+            h.close()
+        return -(J @ dx)
+    except Exception as e:                  # guess-vars.jl:163-167
+        print("error in estimate_y_tilde")
+        print(repr(e))
+        return np.ones(m)
+
+
+# ---------------------------------------------------------------------------
+# L2: Symmetric_KKT_solver on the LDL' back-end (kkt_system_solver/symmetric.jl, SURVEY 8 f2)
+# ---------------------------------------------------------------------------
+class Symmetric_B200_KKT_solver:
+    """Drop-in for Symmetric_KKT_solver (symmetric.jl:2-33): the quasi-definite system
+        [[H + delta I, J'], [J, -S/Y]]
+    factorised by the device LDL' (linear_solver_B200(:symmetric)) with the inertia test
+    pos == n, neg == m (julia.jl:72-80, linear_system_solvers.jl:48-91).  The lower triangle of
+    the matrix keeps one pattern across iterations, so its symbolic analysis is cached by the
+    library; only the values are refilled here."""
+
+    def __init__(self, device=0):
+        self.ls_solver = None
+        self.factor_it = None
+        self.delta_x_vec = None
+        self.delta_s_vec = None
+        self.rhs = None
+        self.dir = None
+        self.kkt_err_norm = Class_kkt_error()
+        self.rhs_norm = 0.0
+        self.pars = None
+        self.schur_diag = None
+        self.true_x_diag = None
+        self.ready = "not_ready"
+        self.Q = None
+        self.device = device
+        self._pat = None
+
+    def initialize(self, initial_it):
+        if self.ls_solver is None:
+            self.ls_solver = linear_solver_B200("symmetric", False, False, self.device)
+        self.ls_solver.initialize()
+        self.dir = Class_point(np.zeros(dim(initial_it)), np.zeros(ncon(initial_it)), np.zeros(ncon(initial_it)))
+
+    def finalize(self):
+        if self.ls_solver is not None:
+            self.ls_solver.finalize()
+
+    # -- form_system!  symmetric.jl:35-54
+    def form_system(self, it, timer=None):
+        J = _csc(it.J); H = _csc(it.H)
+        m, n = J.shape
+        key = (J.shape, J.nnz, H.nnz, id(J.indptr), id(J.indices), id(H.indptr), id(H.indices),
+               Schur_B200_KKT_solver._pattern_sample(J, H))
+        if self._pat is None or self._pat[0] != key:
+            # pattern of the lower triangle [[tril(H) + full diagonal, 0], [J, diag]] and where the
+            # values of H, J and -s./y go in its nzval (symmetric.jl:41: M = [[H J_T]; [J B]])
+            one = lambda A: sp.csc_matrix((np.ones(A.nnz), A.indices, A.indptr), shape=A.shape)      # noqa: E731
+            P = sp.bmat([[one(H) + sp.identity(n, format="csc"), None], [one(J), sp.identity(m, format="csc")]], format="csc")
+            P.sort_indices()
+            cols = np.repeat(np.arange(n + m), np.diff(P.indptr))
+            lookup = {}
+            pos = np.arange(P.nnz)
+            order = np.lexsort((P.indices, cols))
+            assert np.array_equal(order, pos)
+            keyarr = cols.astype(np.int64) * (n + m) + P.indices
+            def locate(rows, cls):
+                want = cls.astype(np.int64) * (n + m) + rows
+                idx = np.searchsorted(keyarr, want)
+                assert np.array_equal(keyarr[idx], want)
+                return idx
+            hcols = np.repeat(np.arange(n), np.diff(H.indptr))
+            jcols = np.repeat(np.arange(n), np.diff(J.indptr))
+            self._pat = (key, P.indptr.astype(np.int64), P.indices.astype(np.int64),
+                         locate(H.indices, hcols), locate(J.indices + n, jcols),
+                         locate(np.arange(n, n + m), np.arange(n, n + m)), locate(np.arange(n), np.arange(n)))
+        _, cp, ri, hpos, jpos, bpos, xdiag = self._pat
+        v = np.zeros(ri.shape[0])
+        np.add.at(v, hpos, H.data)
+        v[jpos] = J.data
+        v[bpos] = -np.asarray(it.s, dtype=np.float64) / np.asarray(it.y, dtype=np.float64)
+        self.Q = sp.csc_matrix((v, ri, cp), shape=(n + m, n + m))
+        self._xdiag = xdiag
+        self.factor_it = it
+        self.schur_diag = compute_schur_diag(it, self.ls_solver._h)
+        self.true_x_diag = v[xdiag].copy()
+        self.ready = "system_formed"
+
+    # -- update_delta_vecs!  symmetric.jl:87-104
+    def update_delta(self, delta_x, delta_s, timer=None):
+        n = dim(self.factor_it)
+        self.update_delta_vecs(delta_x * np.ones(n), delta_s * self.factor_it.s ** (-2.0), timer)
+
+    def update_delta_vecs(self, delta_x_vec, delta_s_vec, timer=None):
+        self.delta_x_vec = delta_x_vec
+        self.delta_s_vec = delta_s_vec
+        if np.sum(np.abs(delta_s_vec)) > 0.0:
+            raise RuntimeError("not implemented")          # symmetric.jl:94
+        self.Q.data[self._xdiag] = self.true_x_diag + delta_x_vec
+        self.ready = "delta_updated"
+
+    def factor(self, delta_x, timer=None, delta_s=0.0):
+        self.update_delta(delta_x, delta_s, timer)
+        if self.ready != "delta_updated":
+            raise RuntimeError("kkt solver not ready to factor kkt_solver.ready = %s != :delta_updated" % self.ready)
+        self.ready = "factored"
+        return self.factor_implementation(timer)
+
+    # -- factor_implementation!  symmetric.jl:56-58
+    def factor_implementation(self, timer=None):
+        return self.ls_solver.ls_factor(self.Q, dim(self.factor_it), ncon(self.factor_it), timer)
+
+    def kkt_associate_rhs(self, it, rhs, reduct_factors=None, timer=None):
+        self.rhs = rhs
+        if reduct_factors is not None:
+            self.dir.mu = -(1.0 - reduct_factors[2]) * it.mu
+            self.dir.primal_scale = -(1.0 - reduct_factors[0]) * it.primal_scale
+
+    def compute_direction(self, timer=None):
+        if self.ready != "factored":
+            raise RuntimeError("kkt solver not ready to compute direction!")
+        self.compute_direction_implementation(timer)
+        for v in (self.dir.x, self.dir.y, self.dir.s):
+            if np.isnan(np.sum(v)) and np.isnan(v).any():
+                raise FloatingPointError("NaN in direction")
+
+    # -- compute_direction_implementation!  symmetric.jl:60-85
+    def compute_direction_implementation(self, timer=None):
+        it = self.factor_it
+        y_org = np.asarray(it.y, dtype=np.float64)
+        rhs = self.rhs
+        n = dim(it)
+        symmetric_rhs = np.concatenate([rhs.dual_r, rhs.primal_r + rhs.comp_r / y_org])
+        sol = self.ls_solver.ls_solve(symmetric_rhs, timer)
+        d = self.dir
+        d.x = sol[:n].copy()
+        d.y = -sol[n:]
+        J = _csc(it.J)
+        d.s = J @ d.x - rhs.primal_r                         # eval_jac_prod(factor_it, dir.x) - rhs.primal_r
+        self.update_kkt_error()
+
+    def update_kkt_error(self):
+        """update_kkt_error! (kkt_system_solver.jl:67-96): generic host code of the reference,
+        evaluated from the factorisation iterate's matrices."""
+        it, d, rhs = self.factor_it, self.dir, self.rhs
+        J = _csc(it.J); H = _csc(it.H)
+        Hs = H + sp.tril(H, -1).T
+        eD = (self.delta_x_vec * d.x + Hs @ d.x - J.T @ d.y) - rhs.dual_r
+        eP = J @ d.x - d.s - rhs.primal_r
+        eM = np.asarray(it.s) * d.y + np.asarray(it.y) * d.s - rhs.comp_r
+        nrm = lambda v: float(np.abs(v).max()) if v.size else 0.0      # noqa: E731
+        overall = max(nrm(eD), nrm(eP), nrm(eM))
+        rn = max(nrm(rhs.dual_r), nrm(rhs.primal_r), nrm(rhs.comp_r))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            self.kkt_err_norm = Class_kkt_error(nrm(eD), nrm(eP), nrm(eM), overall, rn, float(np.float64(overall) / np.float64(rn)))
+        self.rhs_norm = rn
+
+    def diag_min(self):
+        return float(np.min(self.schur_diag))
+
+
 def ipopt_strategy(it, kkt_solver, pars, timer=None):
     """delta_strategy.jl:37-114 for the B200 solver: one library call runs the
     probe at delta.zero, the first shift and the x8 retries on the device.
@@ -462,6 +666,12 @@ def pick_KKT_solver(pars, shard=None):
             raise ValueError("pick a valid solver!")
         k = Schur_B200_KKT_solver(pars.device, shard)
         k.ls_solver = linear_solver_B200("definite", pars.kkt.linear_solver_safe_mode,
+                                         pars.kkt.linear_solver_recycle, pars.device)
+    elif t == "symmetric_b200":
+        if ls != "b200":
+            raise ValueError("pick a valid solver!")
+        k = Symmetric_B200_KKT_solver(pars.device)
+        k.ls_solver = linear_solver_B200("symmetric", pars.kkt.linear_solver_safe_mode,
                                          pars.kkt.linear_solver_recycle, pars.device)
     else:
         raise ValueError("pick a solver!")

@@ -193,3 +193,43 @@ class Factor:
                             dx.ctypes.data_as(_f64p), dy.ctypes.data_as(_f64p),
                             ds.ctypes.data_as(_f64p), err.ctypes.data_as(_f64p))
         return dx, dy, ds, err
+
+
+# ---------------------------------------------------------------------------
+# SURVEY 8 f4 restatements (numpy; small cases)
+# ---------------------------------------------------------------------------
+def eval_diag_J_T_J(J, diag_vals):
+    """utils/eval.jl:89-100: di[i] += a[j]^2 * diag_vals[j] over the stored entries of column i,
+    rows ascending (square first, then the product, then the sum)."""
+    import scipy.sparse as sp
+    J = sp.csc_matrix(J); J.sort_indices()
+    d = np.asarray(diag_vals, dtype=np.float64)
+    n = J.shape[1]
+    di = np.zeros(n)
+    for i in range(n):
+        acc = 0.0
+        for p in range(J.indptr[i], J.indptr[i + 1]):
+            a = J.data[p]
+            acc = acc + (a * a) * d[J.indices[p]]
+        di[i] = acc
+    return di
+
+
+def compute_schur_diag(J, H, y, s):
+    """kkt_system_solver.jl:296-300: diag(get_lag_hess(iter)) + eval_diag_J_T_J(iter, y ./ s)."""
+    import scipy.sparse as sp
+    return sp.csc_matrix(H).diagonal() + eval_diag_J_T_J(J, np.asarray(y, float) / np.asarray(s, float))
+
+
+def estimate_y_tilde(J, g, lam=1e-4):
+    """init/guess-vars.jl:128-169 (Cholesky branch): H = lam I + J'J; dx = H \\ -g; y = -J dx."""
+    import scipy.sparse as sp
+    J = sp.csc_matrix(J)
+    m, n = J.shape
+    Q, sd = form_system(J, sp.identity(n, format="csc") * lam, np.ones(m), np.ones(m))
+    QL = sp.tril(Q, format="csc"); QL.sort_indices()
+    F = Factor(QL)
+    if F.factorize(QL.data, mode="chol") != 1:
+        return np.ones(m)
+    dx = F.solve(-np.asarray(g, dtype=np.float64))
+    return -(J @ dx)

@@ -101,7 +101,7 @@ def _compare(pkg, orc, prob, delta_prev=0.0, opts=None, rel_tol=REL_TOL, big=Fal
                 assert _rel(a, dirs_own[q][idx]) <= max(rel_tol, 2.0 * spread), (prob.name, nm, "vs own-ordering oracle", spread)
             assert rel <= bar, (prob.name, nm, rel, "oracle spread between orderings", bar / 2.0)
         assert err[4] == pytest.approx(erro[4], rel=1e-14)
-        assert err[5] <= 10 * max(erro[5], 1e-16), (err[5], erro[5])
+        assert err[5] <= max(10 * erro[5], 1e-13), (err[5], erro[5])      # a ratio of rounding residuals
     k.finalize()
     return nf, delta
 
