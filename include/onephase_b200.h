@@ -136,6 +136,25 @@ int opb_delta_loop_resident(opb_handle* h, double delta_prev, double delta_zero,
                             double delta_max, double delta_start, double inc, double dec, int max_it);
 int opb_direction_resident(opb_handle* h, int n_refine);
 int opb_solve_resident(opb_handle* h, int nsolves);   /* triangular solves only, on the residual vector */
+/* --- the iterate's (J, H, y, s) stay resident between the calls of one outer iteration; the
+ *     right-hand side is built and the step bounds are reduced on the device, so per direction only the NLP's
+ *     gradient / constraint values go up and a few scalars come back. ---
+ * System_rhs(iter, reduct_factors)  (kkt_system_solver/system_rhs.jl:57-73 with eval_grad_lag / eval_grad_r,
+ * utils/eval.jl:59-63,136-142) from the resident (J, y, s) and the caller's grad (n) and cons (m):
+ *   dual_r = -(grad - J'y + (mu*eta_mu) * (a_norm_penalty * J'1)) * (1 - eta_D)
+ *   primal_r = -(cons - s) * (1 - eta_P),   comp_r = mu*eta_mu - s .* y
+ * The three vectors become the resident rhs of the next opb_direction_resident; the *_out pointers may be
+ * NULL (nothing is copied back then and the call does not synchronise). */
+int opb_system_rhs(opb_handle* h, const double* grad, const double* cons, double mu, double a_norm_penalty,
+                   double eta_P, double eta_D, double eta_mu, double* dual_r_out, double* primal_r_out,
+                   double* comp_r_out);
+/* Fraction-to-the-boundary scalars of the resident direction (line_search/frac_boundary.jl:3-40):
+ * out4 = [norm(dx,Inf), norm(dy,Inf), norm(ds,Inf), simple_max_step(s, ds, lb_s)] with
+ * lb_s = frac_bd * min.(s, norm(dx,Inf) * norm(dx,Inf)^predict_exp). */
+int opb_step_bounds(opb_handle* h, double frac_bd, double predict_exp, double* out4);
+/* The resident direction of the last opb_direction_resident and its Class_kkt_error (any pointer may be NULL). */
+int opb_get_direction(opb_handle* h, double* dx_out, double* dy_out, double* ds_out, double* kkt_err_out);
+
 /* One factorisation attempt at shift `delta` (like opb_factor) with CUDA events around every
  * launch of the two FP64 tensor-pipe kernels: time of the whole attempt, summed time of the
  * update-block kernel and of the panel-update kernel, and the algorithmic flops those kernels

@@ -31,6 +31,7 @@ EXPORTS = [
     "opb_direction_resident", "opb_solve_resident", "opb_sync_state", "opb_get_info",
     "opb_get_symbolic", "opb_get_L_values", "opb_launch_count", "opb_version",
     "opb_shard_init", "opb_shard_export", "opb_shard_attach", "opb_profile_factor", "opb_eval_diag_JtDJ",
+    "opb_system_rhs", "opb_step_bounds", "opb_get_direction",
 ]
 SHARD_BLOB_BYTES = 320
 
@@ -91,6 +92,9 @@ def load():
     L.opb_shard_attach.argtypes = [vp, ci, ctypes.c_char_p]
     L.opb_profile_factor.argtypes = [vp, f64, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, c_intp]
     L.opb_eval_diag_JtDJ.argtypes = [vp, i64, i64, c_i64p, c_i64p, c_f64p, ci, c_f64p, c_f64p]
+    L.opb_system_rhs.argtypes = [vp, c_f64p, c_f64p] + [f64] * 5 + [c_f64p, c_f64p, c_f64p]
+    L.opb_step_bounds.argtypes = [vp, f64, f64, c_f64p]
+    L.opb_get_direction.argtypes = [vp, c_f64p, c_f64p, c_f64p, c_f64p]
     L.opb_launch_count.restype = ctypes.c_longlong
     L.opb_version.restype = ctypes.c_char_p
     _lib = L
@@ -267,6 +271,25 @@ class Handle:
 
     def direction_resident(self, n_refine=3):
         self.check(self.L.opb_direction_resident(self.h, n_refine))
+
+    def system_rhs(self, grad, cons, mu, a_norm_penalty, eta_P, eta_D, eta_mu, fetch=False):
+        """System_rhs(iter, reduct_factors) on the device; the result is the resident rhs of the next
+        direction_resident.  fetch=True also returns (dual_r, primal_r, comp_r)."""
+        g, c = f64(grad), f64(cons)
+        out = (np.empty(self.n), np.empty(self.m), np.empty(self.m)) if fetch else (None, None, None)
+        self.check(self.L.opb_system_rhs(self.h, pf(g), pf(c), float(mu), float(a_norm_penalty), float(eta_P),
+                                         float(eta_D), float(eta_mu), pf(out[0]), pf(out[1]), pf(out[2])))
+        return out if fetch else None
+
+    def step_bounds(self, frac_bd, predict_exp):
+        out = np.empty(4)
+        self.check(self.L.opb_step_bounds(self.h, float(frac_bd), float(predict_exp), pf(out)))
+        return dict(norm_dx=out[0], norm_dy=out[1], norm_ds=out[2], max_step_s=out[3])
+
+    def get_direction(self):
+        dx = np.empty(self.n); dy = np.empty(self.m); ds = np.empty(self.m); err = np.empty(6)
+        self.check(self.L.opb_get_direction(self.h, pf(dx), pf(dy), pf(ds), pf(err)))
+        return dx, dy, ds, err
 
     def solve_resident(self, nsolves=1):
         self.check(self.L.opb_solve_resident(self.h, nsolves))

@@ -1035,8 +1035,16 @@ wide_bwd_upd_kernel(DevSym S, const int* __restrict__ list, const double* __rest
         const double* xs = x + d.first;
         const double* us = u + S.rowptr[d.s];
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        // later pivot rows [b1, c): groups of 128 rows dealt round-robin to the WPC warps
+        // later pivot rows [b1, c): groups of 128 rows dealt round-robin to the WPC warps; two groups
+        // (eight independent loads per lane) are in flight where the column is long enough
         int base = b1 + 128 * part;
+        for (; base + 128 * (WPC + 1) <= d.c; base += 256 * WPC) {
+            const int i = base + lane, j = i + 128 * WPC;
+            const double l0 = col[i], l1 = col[i + 32], l2 = col[i + 64], l3 = col[i + 96];
+            const double m0 = col[j], m1 = col[j + 32], m2 = col[j + 64], m3 = col[j + 96];
+            a0 += l0 * xs[i]; a1 += l1 * xs[i + 32]; a2 += l2 * xs[i + 64]; a3 += l3 * xs[i + 96];
+            a0 += m0 * xs[j]; a1 += m1 * xs[j + 32]; a2 += m2 * xs[j + 64]; a3 += m3 * xs[j + 96];
+        }
         for (; base + 128 <= d.c; base += 128 * WPC) {
             const int i = base + lane;
             a0 += col[i] * xs[i]; a1 += col[i + 32] * xs[i + 32];
@@ -1046,6 +1054,13 @@ wide_bwd_upd_kernel(DevSym S, const int* __restrict__ list, const double* __rest
         // rows below the pivot block
         const double* colr = col + d.c;
         base = 128 * part;
+        for (; base + 128 * (WPC + 1) <= d.r; base += 256 * WPC) {
+            const int t = base + lane, v = t + 128 * WPC;
+            const double l0 = colr[t], l1 = colr[t + 32], l2 = colr[t + 64], l3 = colr[t + 96];
+            const double m0 = colr[v], m1 = colr[v + 32], m2 = colr[v + 64], m3 = colr[v + 96];
+            a0 += l0 * us[t]; a1 += l1 * us[t + 32]; a2 += l2 * us[t + 64]; a3 += l3 * us[t + 96];
+            a0 += m0 * us[v]; a1 += m1 * us[v + 32]; a2 += m2 * us[v + 64]; a3 += m3 * us[v + 96];
+        }
         for (; base + 128 <= d.r; base += 128 * WPC) {
             const int t = base + lane;
             a0 += colr[t] * us[t]; a1 += colr[t + 32] * us[t + 32];

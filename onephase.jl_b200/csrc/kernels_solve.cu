@@ -298,7 +298,7 @@ cudaError_t solve_configure() { return cudaSuccess; }
 
 void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                   const double* Lval, const double* Xinv, double* x, double* xnew, double* u, int mode,
-                  const ShardCtx* shard, const int* colowner, cudaStream_t st) {
+                  const ShardCtx* shard, const int* colowner, const SideStream* side, cudaStream_t st) {
     // Cholesky: BIG supernodes take the multi-CTA path through inv(L11) (kernels_dense.cu), the
     // other classes (front or panel fits in shared memory) are solved by one CTA each;
     // LDL': every supernode is solved by one CTA.
@@ -308,21 +308,33 @@ void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int
     // to every peer before the ranks below continue, and at the end every rank publishes the
     // columns it owns.
     const bool wide = (mode == 0);
+    // The supernodes of one level are independent of each other: where a level has both
+    // CTA-per-supernode classes (latency-bound) and BIG supernodes (bandwidth-bound), the two
+    // groups run concurrently on two streams and meet again before the next level.
+    if (shard) side = nullptr;
     for (size_t l = 0; l < plan.size(); l++) {
         const LevelPlan& L = plan[l];
         if (shard && L.barrier_before) launch_shard_barrier(*shard, st);
         // warp per supernode for the tiny class, CTA per supernode above
         const int solo = (wide ? L.all_count - L.count[FC_BIG] : L.all_count) - L.count[FC_T32];
-        launch_small_classes(true, S, L, d_sched, Lval, x, u, mode, st);
-        launch_cta_classes(true, S, L, d_sched, solo, Lval, x, u, mode, st);
+        const bool par = side && wide && L.count[FC_BIG] > 0 && (solo + L.count[FC_T32]) > 0;
+        cudaStream_t s2 = par ? side->stream : st;
+        if (par) { cudaEventRecord(side->fork, st); cudaStreamWaitEvent(s2, side->fork, 0); }
+        launch_small_classes(true, S, L, d_sched, Lval, x, u, mode, s2);
+        launch_cta_classes(true, S, L, d_sched, solo, Lval, x, u, mode, s2);
         if (wide) launch_solve_wide_fwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
+        if (par) { cudaEventRecord(side->join, s2); cudaStreamWaitEvent(st, side->join, 0); }
     }
     for (size_t l = plan.size(); l-- > 0;) {
         const LevelPlan& L = plan[l];
         const int solo = (wide ? L.all_count - L.count[FC_BIG] : L.all_count) - L.count[FC_T32];
-        launch_small_classes(false, S, L, d_sched, Lval, x, u, mode, st);
-        launch_cta_classes(false, S, L, d_sched, solo, Lval, x, u, mode, st);
+        const bool par = side && wide && L.count[FC_BIG] > 0 && (solo + L.count[FC_T32]) > 0;
+        cudaStream_t s2 = par ? side->stream : st;
+        if (par) { cudaEventRecord(side->fork, st); cudaStreamWaitEvent(s2, side->fork, 0); }
+        launch_small_classes(false, S, L, d_sched, Lval, x, u, mode, s2);
+        launch_cta_classes(false, S, L, d_sched, solo, Lval, x, u, mode, s2);
         if (wide) launch_solve_wide_bwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
+        if (par) { cudaEventRecord(side->join, s2); cudaStreamWaitEvent(st, side->join, 0); }
         if (shard) {
             launch_push_supernodes(S, d_sched + L.push_begin, L.push_count, L.push_maxc, x, st);
             if (L.barrier_before) launch_shard_barrier(*shard, st);

@@ -136,9 +136,85 @@ __global__ void kkt_err_finish_kernel(DirBuffers B) {
     o[0] = eD; o[1] = eP; o[2] = eM; o[3] = overall; o[4] = rhs_norm; o[5] = overall / rhs_norm;
 }
 
+// ---- System_rhs on the device (kkt_system_solver/system_rhs.jl:57-73) -------------------------
+// dual_r = -(grad - J'y + mu_t * (a_pen * J'1)) * (1 - eta_D), mu_t = mu * eta_mu, in the reference's
+// operation order (eval.jl:59-63,136-142; the products J'y and J'1 accumulate over the rows ascending)
+__global__ void sysrhs_n_kernel(DirBuffers B, const double* __restrict__ grad, double mu_t, double a_pen,
+                                double one_minus_eta_D) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= B.n) return;
+    double jty = 0.0, jt1 = 0.0;
+    for (int64_t p = B.Jp[j]; p < B.Jp[j + 1]; p++) {
+        const double a = B.Jv[p];
+        jty = __dadd_rn(jty, __dmul_rn(a, B.y[B.Jrow[p]]));
+        jt1 = __dadd_rn(jt1, a);                       // a * 1.0
+    }
+    const double gl = __dadd_rn(__dsub_rn(grad[j], jty), __dmul_rn(mu_t, __dmul_rn(a_pen, jt1)));
+    B.tm2[j] = __dmul_rn(-gl, one_minus_eta_D);        // tm2 aliases the resident dual_r buffer
+}
+// primal_r = -(cons - s) * (1 - eta_P);  comp_r = mu_t - s .* y
+__global__ void sysrhs_m_kernel(DirBuffers B, const double* __restrict__ cons, double* __restrict__ primal_r,
+                                double* __restrict__ comp_r, double mu_t, double one_minus_eta_P) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= B.m) return;
+    primal_r[k] = __dmul_rn(-__dsub_rn(cons[k], B.s[k]), one_minus_eta_P);
+    comp_r[k] = __dsub_rn(mu_t, __dmul_rn(B.s[k], B.y[k]));
+}
+
+// ---- fraction-to-the-boundary quantities (line_search/frac_boundary.jl:3-35) -------------------
+// red[0] = |dx|_inf, red[1] = |dy|_inf, red[2] = |ds|_inf
+__global__ void step_norms_kernel(DirBuffers B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    max_abs_to(B.red + 0, i < B.n ? B.dx[i] : 0.0);
+    max_abs_to(B.red + 1, i < B.m ? B.dy[i] : 0.0);
+    max_abs_to(B.red + 2, i < B.m ? B.ds[i] : 0.0);
+}
+// red[3] = max(1, max_i -ds_i / (s_i - lb_i)) as an ordered key, lb = frac_bd * min(s, |dx| * |dx|^ex)
+// (lb_s, frac_boundary.jl:28-33; simple_max_step :35-40 returns 1 / that maximum)
+__global__ void step_ratio_kernel(DirBuffers B, double frac_bd, double ex) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const double ndx = __longlong_as_double((long long)B.red[0]);
+    const double thres = ndx * pow(ndx, ex);
+    double ratio = 1.0;
+    if (k < B.m) {
+        const double sk = B.s[k];
+        const double lb = frac_bd * fmin(sk, thres);
+        ratio = -B.ds[k] / (sk - lb);
+        if (!(ratio > 1.0) && ratio == ratio) ratio = 1.0;       // keep NaN visible, clamp the rest at 1
+    }
+    // max over positive doubles (and NaN, which sorts above +inf as a key)
+    unsigned long long key = (unsigned long long)__double_as_longlong(ratio);
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(B.red + 3, key);
+}
+
 inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
+
+void launch_system_rhs(const DirBuffers& B, const double* grad, const double* cons, double mu_t, double a_pen,
+                       double eta_P, double eta_D, cudaStream_t st) {
+    DirBuffers D = B;
+    D.tm2 = const_cast<double*>(B.dual_r);
+    sysrhs_n_kernel<<<nblk(B.n), 256, 0, st>>>(D, grad, mu_t, a_pen, 1.0 - eta_D);
+    count_launch();
+    if (B.m > 0) {
+        sysrhs_m_kernel<<<nblk(B.m), 256, 0, st>>>(D, cons, const_cast<double*>(B.primal_r), const_cast<double*>(B.comp_r),
+                                                 mu_t, 1.0 - eta_P);
+        count_launch();
+    }
+}
+
+void launch_step_bounds(const DirBuffers& B, double frac_bd, double ex, cudaStream_t st) {
+    red_reset_kernel<<<1, 32, 0, st>>>(B.red);
+    const int nm = B.n > B.m ? B.n : B.m;
+    step_norms_kernel<<<nblk(nm), 256, 0, st>>>(B);
+    step_ratio_kernel<<<nblk(B.m > 0 ? B.m : 1), 256, 0, st>>>(B, frac_bd, ex);
+    count_launch(3);
+}
 
 // rows * W threads
 inline unsigned nblkw(int64_t rows, int W) { return (unsigned)((rows * W + 255) / 256); }
@@ -191,6 +267,10 @@ cudaError_t preload_vec() {
     e = cudaFuncGetAttributes(&a, recover_n_kernel<1>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, recover_n_kernel<32>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, kkt_err_finish_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, sysrhs_n_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, sysrhs_m_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, step_norms_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, step_ratio_kernel); if (e != cudaSuccess) return e;
     return cudaSuccess;
 }
 

@@ -212,6 +212,7 @@ struct opb_handle {
     // whose condition is set on the device by the last kernel of the body (ctl_end_loop_kernel)
     GraphSlot g_loop;
     bool loop_graph = true;            // option "loop_graph"
+    std::string loop_diag = "not built";
     long long loop_pending = 0;        // launches per attempt of a loop whose attempt count is not known yet
     bool use_graphs = true;
     void drop_graphs() {
@@ -238,6 +239,7 @@ struct opb_handle {
 
     SideStream side;                     // look-ahead stream of the blocked panel factorisation
     bool lookahead = true;
+    bool solve_overlap = true;           // option "solve_overlap": solo and BIG supernodes of a level on two streams
     KernelTimer ktimer;                  // opb_profile_factor
 
     int fail(int code, const std::string& msg) { err = msg; return code; }
@@ -385,6 +387,7 @@ int opb_set_option(opb_handle* h, const char* key, double v) {
     else if (k == "chain_priority") { h->side.chain_on_side = v != 0; h->drop_graphs(); }
     else if (k == "graphs") { h->use_graphs = v != 0; h->drop_graphs(); }
     else if (k == "loop_graph") { h->loop_graph = v != 0; h->drop_graphs(); }
+    else if (k == "solve_overlap") { h->solve_overlap = v != 0; h->drop_graphs(); }
     else return h->fail(OPB_ERR_INVALID, "unknown option " + k);
     return OPB_OK;
 }
@@ -692,31 +695,43 @@ static void enqueue_attempt_raw(opb_handle* h, KernelTimer* timer = nullptr, uns
 // back to host-driven chunks of attempts).
 static bool build_loop_graph(opb_handle* h) {
     cudaGraph_t graph = nullptr;
-    if (cudaGraphCreate(&graph, 0) != cudaSuccess) { cudaGetLastError(); return false; }
-    cudaGraphConditionalHandle ch;
-    bool ok = cudaGraphConditionalHandleCreate(&ch, graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+    cudaError_t e = cudaGraphCreate(&graph, 0);
+    const char* where = "cudaGraphCreate";
+    cudaGraphConditionalHandle ch = 0;
     cudaGraphNodeParams np = {};
-    np.type = cudaGraphNodeTypeConditional;
-    np.conditional.handle = ch;
-    np.conditional.type = cudaGraphCondTypeWhile;
-    np.conditional.size = 1;
     cudaGraphNode_t node;
-    ok = ok && cudaGraphAddNode(&node, graph, nullptr, 0, &np) == cudaSuccess;
     const long long l0 = g_launches.load();
-    if (ok) {
+    if (e == cudaSuccess) { where = "cudaGraphConditionalHandleCreate"; e = cudaGraphConditionalHandleCreate(&ch, graph, 1, cudaGraphCondAssignDefault); }
+    if (e == cudaSuccess) {
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = ch;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        where = "cudaGraphAddNode(conditional)";
+        e = cudaGraphAddNode(&node, graph, nullptr, 0, &np);
+    }
+    if (e == cudaSuccess) {
         cudaGraph_t body = np.conditional.phGraph_out[0];
-        ok = cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
-        if (ok) {
+        where = "cudaStreamBeginCaptureToGraph";
+        e = cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed);
+        if (e == cudaSuccess) {
             enqueue_attempt_raw(h, nullptr, (unsigned long long)ch);
             cudaGraph_t out = nullptr;
-            ok = cudaStreamEndCapture(h->stream, &out) == cudaSuccess;
+            where = "cudaStreamEndCapture";
+            e = cudaStreamEndCapture(h->stream, &out);
         }
     }
     h->g_loop.launches = g_launches.load() - l0;
     g_launches.store(l0);
-    if (ok) ok = cudaGraphInstantiate(&h->g_loop.exec, graph, 0) == cudaSuccess;
+    if (e == cudaSuccess) { where = "cudaGraphInstantiate"; e = cudaGraphInstantiate(&h->g_loop.exec, graph, 0); }
     if (graph) cudaGraphDestroy(graph);
-    if (!ok) { cudaGetLastError(); h->g_loop = opb_handle::GraphSlot(); return false; }
+    if (e != cudaSuccess) {
+        h->loop_diag = std::string(where) + ": " + cudaGetErrorString(e);
+        cudaGetLastError();
+        h->g_loop = opb_handle::GraphSlot();
+        return false;
+    }
+    h->loop_diag = "active";
     h->g_loop.key = h->mode;
     return true;
 }
@@ -946,7 +961,7 @@ int opb_direction_resident(opb_handle* h, int n_refine) {
         for (int it = 0; it < n_refine; it++) {
             launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, D.n, st);
             launch_solve(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode,
-                         h->shard_ctx(), B.d_colowner.p, st);
+                         h->shard_ctx(), B.d_colowner.p, h->solve_overlap ? &h->side : nullptr, st);
             launch_permute_out_add(h->xw.p, B.d_perm.p, h->dx.p, D.n, 1, st);
             // the reference also evaluates the residual after the last correction but only
             // prints it (schur.jl:177-179); it does not influence the direction
@@ -972,6 +987,58 @@ int opb_direction(opb_handle* h, const double* dual_r, const double* primal_r, c
     return OPB_OK;
 }
 
+// ---- the iterate stays resident, only (grad, cons) go up and scalars come back ----
+int opb_system_rhs(opb_handle* h, const double* grad, const double* cons, double mu, double a_norm_penalty,
+                   double eta_P, double eta_D, double eta_mu, double* dual_r_out, double* primal_r_out,
+                   double* comp_r_out) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || !h->B->schur) return h->fail(OPB_ERR_STATE, "opb_set_structure has not been called");
+    if (h->ready == opb_handle::NOT_READY) return h->fail(OPB_ERR_STATE, "no resident iterate (opb_form / opb_upload_values + opb_form_resident first)");
+    if (!grad || (h->B->P.m && !cons)) return h->fail(OPB_ERR_INVALID, "bad arguments");
+    const int n = h->B->S.n, m = h->B->P.m;
+    cudaStream_t st = h->stream;
+    // grad -> b (n), cons -> tm (m): both are scratch of the direction, rewritten before they are read there
+    CK(cudaMemcpyAsync(h->b.p, grad, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (m) CK(cudaMemcpyAsync(h->tm.p, cons, m * sizeof(double), cudaMemcpyHostToDevice, st));
+    DirBuffers D = dir_buffers(h);
+    launch_system_rhs(D, h->b.p, h->tm.p, mu * eta_mu, a_norm_penalty, eta_P, eta_D, st);
+    CK(cudaGetLastError());
+    if (dual_r_out) CK(cudaMemcpyAsync(dual_r_out, h->dual_r.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (primal_r_out && m) CK(cudaMemcpyAsync(primal_r_out, h->primal_r.p, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (comp_r_out && m) CK(cudaMemcpyAsync(comp_r_out, h->comp_r.p, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (dual_r_out || primal_r_out || comp_r_out) CK(cudaStreamSynchronize(st));
+    return OPB_OK;
+}
+
+int opb_step_bounds(opb_handle* h, double frac_bd, double predict_exp, double* out4) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || !h->B->schur) return h->fail(OPB_ERR_STATE, "opb_set_structure has not been called");
+    if (h->ready != opb_handle::FACTORED || !out4) return h->fail(OPB_ERR_STATE, "no direction");
+    DirBuffers D = dir_buffers(h);
+    launch_step_bounds(D, frac_bd, predict_exp, h->stream);
+    CK(cudaGetLastError());
+    unsigned long long red[4];
+    CK(cudaMemcpyAsync(red, h->red.p, sizeof red, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 4; k++) memcpy(&out4[k], &red[k], 8);
+    out4[3] = 1.0 / (out4[3] > 1.0 || out4[3] != out4[3] ? out4[3] : 1.0);       // simple_max_step = 1 / max(1, ratios)
+    return OPB_OK;
+}
+
+int opb_get_direction(opb_handle* h, double* dx, double* dy, double* ds, double* kkt_err) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || !h->B->schur) return h->fail(OPB_ERR_STATE, "opb_set_structure has not been called");
+    if (h->ready != opb_handle::FACTORED) return h->fail(OPB_ERR_STATE, "no direction");
+    const int n = h->B->S.n, m = h->B->P.m;
+    cudaStream_t st = h->stream;
+    if (dx) CK(cudaMemcpyAsync(dx, h->dx.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (dy && m) CK(cudaMemcpyAsync(dy, h->dy.p, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (ds && m) CK(cudaMemcpyAsync(ds, h->ds.p, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    rc = read_state(h); if (rc) return rc;
+    if (kkt_err) memcpy(kkt_err, h->h_state.kkt_err, 6 * sizeof(double));
+    return OPB_OK;
+}
+
 int opb_solve_resident(opb_handle* h, int nsolves) {
     int rc = need_device(h); if (rc) return rc;
     if (!h->B || h->ready != opb_handle::FACTORED) return h->fail(OPB_ERR_STATE, "no factor");
@@ -980,7 +1047,7 @@ int opb_solve_resident(opb_handle* h, int nsolves) {
         run_captured(h, h->g_solve, h->mode, [&] {
             launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, B.S.n, h->stream);
             launch_solve(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode,
-                         h->shard_ctx(), B.d_colowner.p, h->stream);
+                         h->shard_ctx(), B.d_colowner.p, h->solve_overlap ? &h->side : nullptr, h->stream);
             launch_permute_out_add(h->xw.p, B.d_perm.p, h->b.p, B.S.n, 0, h->stream);
         });
     CK(cudaGetLastError());
@@ -1069,7 +1136,7 @@ int opb_ls_solve(opb_handle* h, const double* rhs, double* sol) {
     CK(cudaMemcpyAsync(h->res.p, rhs, n * sizeof(double), cudaMemcpyHostToDevice, st));
     launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, n, st);
     launch_solve(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode,
-                         h->shard_ctx(), B.d_colowner.p, st);
+                         h->shard_ctx(), B.d_colowner.p, h->solve_overlap ? &h->side : nullptr, st);
     launch_permute_out_add(h->xw.p, B.d_perm.p, h->b.p, n, 0, st);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(sol, h->b.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1124,6 +1191,7 @@ int opb_get_info(opb_handle* h, const char* key, double* out) {
     else if (k == "n_small") *out = B.n_small;
     else if (k == "n_big") *out = B.n_big;
     else if (k == "symbolic_cached") *out = h->cached_hit ? 1 : 0;
+    else if (k == "loop_graph_active") { *out = h->g_loop.exec ? 1 : 0; h->err = "loop graph: " + h->loop_diag; }
     else if (k == "sum_rows") *out = (double)S.rowidx.size();
     else if (k == "x_total") *out = (double)B.x_total;
     else if (k == "n_trtri") *out = B.trtri.count;

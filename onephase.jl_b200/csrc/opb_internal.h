@@ -239,7 +239,7 @@ cudaError_t solve_configure();
 // x (permuted order, length n) is overwritten with the solution; u = workspace (len rowidx)
 void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                   const double* Lval, const double* Xinv, double* x, double* xnew, double* u, int mode,
-                  const ShardCtx* shard, const int* colowner, cudaStream_t st);
+                  const ShardCtx* shard, const int* colowner, const SideStream* side, cudaStream_t st);
 void launch_permute_in(const double* b, const int* perm, double* x, int n, cudaStream_t st);
 void launch_permute_out_add(const double* x, const int* perm, double* dst, int n, int accumulate, cudaStream_t st);
 
@@ -260,5 +260,10 @@ struct DirBuffers {
 void launch_schur_rhs(const DirBuffers& B, cudaStream_t st);
 void launch_residual(const DirBuffers& B, cudaStream_t st);          // res = b - (J'(S.(J dx)) + Hsym dx + delta dx)
 void launch_recover_and_error(const DirBuffers& B, cudaStream_t st);  // dy, ds, kkt_err[6]
+// System_rhs(iter, reduct_factors) into the resident rhs buffers (system_rhs.jl:57-73)
+void launch_system_rhs(const DirBuffers& B, const double* grad, const double* cons, double mu_t, double a_pen,
+                       double eta_P, double eta_D, cudaStream_t st);
+// |dx|, |dy|, |ds| (inf norms) and the fraction-to-the-boundary ratio into B.red[0..3] (frac_boundary.jl:3-40)
+void launch_step_bounds(const DirBuffers& B, double frac_bd, double ex, cudaStream_t st);
 
 }  // namespace opb

@@ -233,3 +233,36 @@ def estimate_y_tilde(J, g, lam=1e-4):
         return np.ones(m)
     dx = F.solve(-np.asarray(g, dtype=np.float64))
     return -(J @ dx)
+
+
+# ---------------------------------------------------------------------------
+# SURVEY 8 f3 restatements (numpy, explicit loops where the operation order matters)
+# ---------------------------------------------------------------------------
+def system_rhs(J, y, s, grad, cons, mu, a_norm_penalty, eta_P, eta_D, eta_mu):
+    """System_rhs(it, reduct) (kkt_system_solver/system_rhs.jl:57-73) with eval_grad_lag / eval_grad_r
+    (utils/eval.jl:59-63,136-142); J'y and J'1 accumulate over the rows ascending like Julia's CSC product."""
+    import scipy.sparse as sp
+    J = sp.csc_matrix(J); J.sort_indices()
+    y = np.asarray(y, float); s = np.asarray(s, float)
+    n = J.shape[1]
+    mu_t = mu * eta_mu
+    dual = np.empty(n)
+    for j in range(n):
+        jty = 0.0; jt1 = 0.0
+        for p in range(J.indptr[j], J.indptr[j + 1]):
+            jty = jty + J.data[p] * y[J.indices[p]]
+            jt1 = jt1 + J.data[p]
+        gl = (grad[j] - jty) + mu_t * (a_norm_penalty * jt1)
+        dual[j] = (-gl) * (1.0 - eta_D)
+    primal = -(np.asarray(cons, float) - s) * (1.0 - eta_P)
+    comp = mu_t - s * y
+    return dual, primal, comp
+
+
+def step_bounds(s, dx, dy, ds, frac_bd, predict_exp):
+    """frac_boundary.jl:3-40: inf norms, lb_s = frac_bd * min.(s, |dx| * |dx|^ex), simple_max_step(s, ds, lb_s)."""
+    ndx = float(np.abs(dx).max()) if len(dx) else 0.0
+    lb = frac_bd * np.minimum(s, ndx * ndx ** predict_exp)
+    ratio = max(1.0, float(np.max(-np.asarray(ds) / (np.asarray(s) - lb)))) if len(s) else 1.0
+    return dict(norm_dx=ndx, norm_dy=float(np.abs(dy).max()) if len(dy) else 0.0,
+                norm_ds=float(np.abs(ds).max()) if len(ds) else 0.0, max_step_s=1.0 / ratio)

@@ -422,3 +422,39 @@ def test_estimate_y_tilde_and_schur_diag(pkg, orc, name):
     assert np.array_equal(sd, orc.compute_schur_diag(prob.J, prob.H, prob.y, prob.s))      # same operation order: bit-exact
     d = np.random.default_rng(2).random(prob.m)
     assert np.array_equal(pkg.eval_diag_J_T_J(it, d), orc.eval_diag_J_T_J(prob.J, d))
+
+
+# ---------------------------------------------------------------------------
+# System_rhs and the step bounds on the device, resident iterate
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["toy_lp5", "chain", "sparse_qp"])
+@pytest.mark.parametrize("etas", [(0.0, 0.0, 0.0), (1.0, 0.0, 1.0), (0.3, 0.0, 0.3)])      # affine, stabilisation, aggressive
+def test_device_system_rhs_and_step_bounds(pkg, orc, name, etas):
+    prob = {"toy_lp5": lambda: problems.toy("toy_lp5"), "chain": lambda: problems.chain(nh=80, seed=8),
+            "sparse_qp": lambda: problems.sparse_qp(1500, 700, seed=8)}[name]()
+    rng = np.random.default_rng(5)
+    grad, cons = rng.standard_normal(prob.n), prob.s + 0.1 * rng.standard_normal(prob.m)
+    mu, a_pen = 0.37, 1e-4
+    pars = pkg.Class_parameters()
+    it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s)
+    k = pkg.pick_KKT_solver(pars); k.initialize(it); k.form_system(it)
+    st, nf, delta = pkg.ipopt_strategy(it, k, pars)
+    assert st == "success"
+    h = k._h
+    got = h.system_rhs(grad, cons, mu, a_pen, *etas, fetch=True)
+    want = orc.system_rhs(prob.J, prob.y, prob.s, grad, cons, mu, a_pen, *etas)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)                       # same operation order: bit-exact
+    # the resident rhs feeds the next direction: identical to passing the same vectors through the host
+    h.direction_resident(3)
+    dx, dy, ds, err = h.get_direction()
+    k.kkt_associate_rhs(it, pkg.System_rhs(*want))
+    k.compute_direction()
+    assert np.array_equal(dx, k.dir.x) and np.array_equal(dy, k.dir.y) and np.array_equal(ds, k.dir.s)
+    assert err[5] == k.kkt_err_norm.ratio
+    # fraction-to-the-boundary scalars: only four doubles cross PCIe
+    sb = h.step_bounds(0.1, 1.5)
+    so = orc.step_bounds(prob.s, dx, dy, ds, 0.1, 1.5)
+    assert sb["norm_dx"] == so["norm_dx"] and sb["norm_dy"] == so["norm_dy"] and sb["norm_ds"] == so["norm_ds"]
+    assert sb["max_step_s"] == pytest.approx(so["max_step_s"], rel=1e-14)
+    k.finalize()
