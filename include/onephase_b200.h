@@ -64,7 +64,9 @@ int opb_set_stream(opb_handle* h, void* cuda_stream);
  * Numeric (any time): "attempts_per_sync" (delta-loop attempts enqueued per host
  * synchronisation, default 2), "graphs" (0/1: replay the launch sequences from CUDA graphs),
  * "outer_block" (columns of the outer block of the panel updates, 128 * 2^k, default 4096),
- * "lookahead" (0/1: side-stream look-ahead in the blocked panel factorisation), "chain_priority" (0/1: the
+ * "lookahead" (blocked panel factorisation of the big fronts: 0 = one stream, 1 = the bulk of each
+ * update on a side stream, 2 [default] = deep look-ahead: every update cut into pieces by the step at which
+ * its columns are next touched, one prioritised stream per piece class), "chain_priority" (0/1: the
  * latency chain of that factorisation runs on the highest-priority stream, default 1),
  * "barrier_timeout_s" (sharded instance: seconds a rank waits for its peers, default 20). */
 int opb_set_option(opb_handle* h, const char* key, double value);
@@ -161,6 +163,12 @@ int opb_get_direction(opb_handle* h, double* dx_out, double* dy_out, double* ds_
  * serve (for bench.py's per-kernel roofline).  Plain launches, no look-ahead stream. */
 int opb_profile_factor(opb_handle* h, double delta, double* total_ms, double* cb_ms, double* update_ms,
                        double* cb_flops, double* update_flops, int* inertia_ok);
+/* One factorisation attempt at shift `delta` with the look-ahead streams as configured (plain launches, no
+ * graph) and event marks on the main stream at the phase boundaries of every elimination-tree level:
+ * out[3*l + 0] = ms before the big panels of level l (small fronts, medium panels, extend-add), out[3*l + 1] =
+ * blocked panel factorisation of the big fronts, out[3*l + 2] = update blocks; out[3*nlevels] = front fill
+ * before the first level, out[3*nlevels + 1] = pivot-block inverses after the last. */
+int opb_profile_levels(opb_handle* h, double delta, double* out, int cap, int* nlevels_out, double* total_ms);
 /* blocks until the stream is idle and reads the controller state */
 int opb_sync_state(opb_handle* h, double* delta_out, int* num_fac_out, int* status_out, double* kkt_err_out);
 

@@ -31,7 +31,7 @@ EXPORTS = [
     "opb_direction_resident", "opb_solve_resident", "opb_sync_state", "opb_get_info",
     "opb_get_symbolic", "opb_get_L_values", "opb_launch_count", "opb_version",
     "opb_shard_init", "opb_shard_export", "opb_shard_attach", "opb_profile_factor", "opb_eval_diag_JtDJ",
-    "opb_system_rhs", "opb_step_bounds", "opb_get_direction",
+    "opb_system_rhs", "opb_step_bounds", "opb_get_direction", "opb_profile_levels",
 ]
 SHARD_BLOB_BYTES = 320
 
@@ -91,6 +91,7 @@ def load():
     L.opb_shard_export.argtypes = [vp, ctypes.c_char_p]
     L.opb_shard_attach.argtypes = [vp, ci, ctypes.c_char_p]
     L.opb_profile_factor.argtypes = [vp, f64, c_f64p, c_f64p, c_f64p, c_f64p, c_f64p, c_intp]
+    L.opb_profile_levels.argtypes = [vp, f64, c_f64p, ci, c_intp, c_f64p]
     L.opb_eval_diag_JtDJ.argtypes = [vp, i64, i64, c_i64p, c_i64p, c_f64p, ci, c_f64p, c_f64p]
     L.opb_system_rhs.argtypes = [vp, c_f64p, c_f64p] + [f64] * 5 + [c_f64p, c_f64p, c_f64p]
     L.opb_step_bounds.argtypes = [vp, f64, f64, c_f64p]
@@ -304,6 +305,17 @@ class Handle:
         out = {k: x.value for k, x in zip(keys, v)}
         out["inertia_ok"] = ok.value
         return out
+
+    def profile_levels(self, delta):
+        """One attempt with the look-ahead streams as configured and CUDA-event marks at the phase
+        boundaries of every level (opb_profile_levels): rows [pre_ms, panel_ms, cb_ms] per level."""
+        nl = int(self.info("nlevels"))
+        out = np.zeros(3 * nl + 2)
+        n = ctypes.c_int(); tot = ctypes.c_double()
+        self.check(self.L.opb_profile_levels(self.h, float(delta), pf(out), out.size, ctypes.byref(n),
+                                             ctypes.cast(ctypes.byref(tot), c_f64p)))
+        return {"levels": out[:3 * nl].reshape(nl, 3), "fill_ms": out[3 * nl], "trtri_ms": out[3 * nl + 1],
+                "total_ms": tot.value}
 
     def sync_state(self):
         d = ctypes.c_double(); nf = ctypes.c_int(); st = ctypes.c_int(); err = np.empty(6)

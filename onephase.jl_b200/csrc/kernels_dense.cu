@@ -81,6 +81,7 @@ __device__ __forceinline__ bool stop_requested(const DeltaState* st) {
 // 256 threads = 8 warps (2 x 4), warp tile 64 x 32, thread accumulators 8 x 4 x 2.
 // ---------------------------------------------------------------------------
 constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
+static_assert(BM == CB_TILE && BN == CB_TILE, "tile-cut table of symbolic.cpp");
 constexpr int LDM = BM + 4;   // [BK][LDM]: fragment reads are bank-conflict free (LDM % 16 == 4)
 constexpr int LDK = BK + 4;   // [BN][LDK]
 constexpr int A_STAGE = BK * LDM;                                  // 2112 doubles
@@ -688,33 +689,30 @@ chol_panel_update_kernel(DevSym S, const int* __restrict__ list, double* __restr
 constexpr int TLD = BM + 1;
 
 // rows [t0, t1) and columns [u0, u1) of child `ch` (positions in its update block) that land in
-// the tile [ri, ri+BM) x [rj, rj+BN) of the parent front
+// tile (I, J) of the parent's update block: read from the tile-cut table built at symbolic time
+// (four independent loads; the binary searches they replace were 30-50 dependent L2 round trips per
+// child and tile, the bulk of a short-K tile's epilogue)
 struct ChildRange { int t0, t1, u0, u1, rc; const int* relc; };
-__device__ __forceinline__ int lower_bound_rel(const int* __restrict__ relc, int lo, int hi, int v) {
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (relc[mid] < v) lo = mid + 1; else hi = mid; }
-    return lo;
-}
-__device__ __forceinline__ ChildRange child_range(const DevSym& S, int ch, int ri, int rj) {
+__device__ __forceinline__ ChildRange child_range(const DevSym& S, int ch, int I, int J) {
     ChildRange R;
     const int64_t rp = S.rowptr[ch];
     R.rc = (int)(S.rowptr[ch + 1] - rp);
     R.relc = S.rel + rp;
-    R.t0 = lower_bound_rel(R.relc, 0, R.rc, ri);
-    R.t1 = lower_bound_rel(R.relc, R.t0, R.rc, ri + BM);
-    R.u0 = lower_bound_rel(R.relc, 0, R.rc, rj);
-    R.u1 = lower_bound_rel(R.relc, R.u0, R.rc, rj + BN);
+    const int* __restrict__ tc = S.tcut + S.tcut_ptr[ch];
+    R.t0 = tc[I]; R.t1 = tc[I + 1];
+    R.u0 = tc[J]; R.u1 = tc[J + 1];
     return R;
 }
 
 // pulls the children's entries of this tile towards L2 a few stages before the K loop ends, so
 // the merge below finds them on chip instead of paying a DRAM round trip per dependent step
 struct CbPrefetch {
-    const DevSym& S; const double* CB; int s, ri, rj;
+    const DevSym& S; const double* CB; int s, I, J;
     __device__ __forceinline__ void operator()() const {
         const int tid = threadIdx.x;        // compute warps only: 0 .. GEMM_CWARPS*32-1
         for (int k = S.child_ptr[s]; k < S.child_ptr[s + 1]; k++) {
             const int ch = S.child_list[k];
-            const ChildRange R = child_range(S, ch, ri, rj);
+            const ChildRange R = child_range(S, ch, I, J);
             if (R.t1 <= R.t0 || R.u1 <= R.u0) continue;
             const double* __restrict__ cb = child_cb(S, CB, ch);
             // one 128-byte line = 16 doubles; a column segment of <= 128 rows spans <= 9 lines
@@ -753,7 +751,7 @@ front_cb_kernel(DevSym S, const int* __restrict__ list, const double* __restrict
     const double* Bg = Lval + d.loff + rj;
     double acc[8][4][2];
     gemm_mainloop<false>(sm, Ag, d.ld, min(BM, d.N - ri), Bg, d.ld, min(BN, d.N - rj), d.c, acc,
-                         CbPrefetch{S, CB, d.s, ri, rj});
+                         CbPrefetch{S, CB, d.s, I, J});
     // the stage buffers are free now: reuse them as the 128 x 128 tile (ld 129)
     double* T = reinterpret_cast<double*>(smraw);
     if (gemm_compute_warp()) {
@@ -769,7 +767,7 @@ front_cb_kernel(DevSym S, const int* __restrict__ list, const double* __restrict
     constexpr int NW = GEMM_THREADS / 32;
     for (int k = S.child_ptr[d.s]; k < S.child_ptr[d.s + 1]; k++) {
         const int ch = S.child_list[k];
-        const ChildRange R = child_range(S, ch, ri, rj);
+        const ChildRange R = child_range(S, ch, I, J);
         if (R.t1 <= R.t0 || R.u1 <= R.u0) continue;          // uniform across the CTA
         const double* __restrict__ cb = child_cb(S, CB, ch);
         const int* __restrict__ relc = R.relc;
@@ -1152,6 +1150,8 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
                             double* CB, double* Xinv, DeltaState* st_d, int outer_block, const SideStream* side,
                             KernelTimer* timer, cudaStream_t st) {
     if (!L.wide_count) return;
+    KernelTimer* phase_timer = (timer && timer->phases) ? timer : nullptr;
+    if (phase_timer) timer = nullptr;
     // medium fronts: panel in shared memory
     for (int fc = FC_MID; fc <= FC_MIDL; fc++) {
         if (!L.count[fc]) continue;
@@ -1164,6 +1164,7 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
         dim3 gea((L.maxN[FC_BIG] + EAP_RB - 1) / EAP_RB, L.count[FC_BIG]);
         big_extend_add_panel_kernel<<<gea, 256, 0, st>>>(S, list, Lval, CB, st_d);
         count_launch();
+        if (phase_timer) phase_timer->put_mark(1, st);
         int sub = 1;                                            // WB blocks per outer block (power of two)
         while (sub * 2 * WB <= outer_block) sub *= 2;
         const int nsteps = (int)L.step_count.size();
@@ -1184,6 +1185,64 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
             count_launch();
             return true;
         };
+        if (side && side->deep && sub <= (1 << LA_CLASSES)) {
+            // Deep look-ahead.  With tb blocks finished and w the largest power of two dividing tb, the
+            // update U(tb) targets the block columns [tb, tb + w) (w < sub) or everything from tb on
+            // (w >= sub).  Its columns are next touched as follows: block tb right away (diagonal block
+            // tb), the blocks [tb + 2^i, tb + 2^(i+1)) by U(tb + 2^i), the blocks from tb + sub on by
+            // U(tb + sub).  So U(tb) is issued as: block tb on the chain stream, piece i on cls[i],
+            // the rest on the lowest-priority stream; and U(tb) itself waits for exactly one earlier
+            // piece, the last writer of its own target range: piece log2(w) of U(tb - w), or the rest
+            // of U(tb - sub).  At most one piece per class is outstanding (the next producer of class
+            // i comes at tb + 2^(i+1), its consumer at tb + 2^i), so one event per class is enough.
+            cudaStream_t C = side->stream;
+            cudaEventRecord(side->start, st); cudaStreamWaitEvent(C, side->start, 0);
+            bool out_cls[LA_CLASSES] = {false}, out_rest = false;
+            for (int t = 0; t < nsteps; t++) {
+                const int cnt = L.step_count[t];
+                if (cnt <= 0) break;
+                const int maxN = L.step_maxN[t];
+                chol_diag_kernel<<<cnt, PT, diag_smem(), C>>>(S, list, Lval, Xinv, t, st_d);
+                count_launch();
+                const int rem = maxN - t * WB;
+                if (rem <= 0) continue;
+                const int nrow = (rem + BM - 1) / BM + 1;
+                dim3 gt(nrow, cnt);
+                chol_trsm_kernel<<<gt, GEMM_THREADS, sizeof(GemmSmem), C>>>(S, list, Lval, Xinv, t, st_d);
+                count_launch();
+                const int tb = t + 1;
+                if (tb >= nsteps || L.step_count[tb] <= 0) continue;       // no panel columns left
+                const int w = tb & -tb;
+                const bool outer = w >= sub;
+                const int k0 = (tb - (outer ? sub : w)) * WB, klen = (outer ? sub : w) * WB;
+                const int near_end = tb + (outer ? sub : w);               // blocks [tb, near_end) in pieces
+                // the last writer of the target range
+                if (outer) { if (out_rest) { cudaStreamWaitEvent(C, side->rest_done, 0); out_rest = false; } }
+                else {
+                    const int i = __builtin_ctz((unsigned)w);
+                    if (out_cls[i]) { cudaStreamWaitEvent(C, side->cls_done[i], 0); out_cls[i] = false; }
+                }
+                cudaEventRecord(side->fork, C);
+                update(C, k0, klen, tb * WB, (tb + 1) * WB);
+                for (int i = 0; tb + (1 << i) < near_end; i++) {
+                    const int lo = tb + (1 << i), hi = std::min(tb + (2 << i), near_end);
+                    if (lo >= nsteps || L.step_count[lo] <= 0) break;
+                    cudaStreamWaitEvent(side->cls[i], side->fork, 0);
+                    update(side->cls[i], k0, klen, lo * WB, hi * WB);
+                    cudaEventRecord(side->cls_done[i], side->cls[i]);
+                    out_cls[i] = true;
+                }
+                if (outer && near_end < nsteps && L.step_count[near_end] > 0) {
+                    cudaStreamWaitEvent(side->rest, side->fork, 0);
+                    update(side->rest, k0, klen, near_end * WB, 1 << 30);
+                    cudaEventRecord(side->rest_done, side->rest);
+                    out_rest = true;
+                }
+            }
+            for (int i = 0; i < LA_CLASSES; i++) if (out_cls[i]) cudaStreamWaitEvent(C, side->cls_done[i], 0);
+            if (out_rest) cudaStreamWaitEvent(C, side->rest_done, 0);
+            cudaEventRecord(side->join, C); cudaStreamWaitEvent(st, side->join, 0);
+        } else {
         // Two streams: C carries the latency chain (diagonal block, TRSM, update of the next block
         // column), B the bulk of the right-looking updates.  Classic mode: C = the caller's stream,
         // B = the side stream.  With a high-priority side stream (side->chain_on_side) the roles
@@ -1235,11 +1294,13 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
         }
         if (pending_join) cudaStreamWaitEvent(C, side->join, 0);
         if (C != st) { cudaEventRecord(side->fork, C); cudaStreamWaitEvent(st, side->fork, 0); }
+        }
     }
     // update blocks of all medium and big fronts, written once
     {
         const long long nt = (L.wide_maxR + 1 + BM - 1) / BM + 1;
         dim3 g((unsigned)(nt * (nt + 1) / 2), L.wide_count);
+        if (phase_timer) phase_timer->put_mark(2, st);
         if (timer) cudaEventRecord(timer->next(0), st);
         front_cb_kernel<<<g, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, d_sched + L.wide_begin, Lval, CB, st_d);
         if (timer) cudaEventRecord(timer->next(0), st);

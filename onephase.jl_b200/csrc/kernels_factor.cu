@@ -372,6 +372,7 @@ void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, c
         // attempt covers the last level.
         if (shard && (L.barrier_before || prev_cross)) launch_shard_barrier(*shard, st);
         prev_cross = L.barrier_before != 0;
+        if (timer && timer->phases) timer->put_mark(0, st);
         if (L.count[FC_T32]) {
             front_small_kernel<64><<<L.count[FC_T32], 64, small_smem(L.maxN[FC_T32]), st>>>(
                 S, d_sched + L.begin[FC_T32], Lval, CB, st_d);
@@ -409,6 +410,7 @@ void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, c
             count_launch();
         }
     }
+    if (timer && timer->phases) timer->put_mark(3, st);
 }
 
 void launch_ldlt_inertia(const DevSym& S, const double* Lval, const int64_t* dpos, int n,

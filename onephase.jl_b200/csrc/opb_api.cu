@@ -60,7 +60,7 @@ struct Bundle {
     // device copies
     DBuf<int> d_sfirst, d_rowidx, d_rel, d_sparent, d_child_ptr, d_child_list, d_perm, d_sched;
     DBuf<int64_t> d_rowptr, d_Loff, d_CBoff, d_amap, d_dpos, d_Mp, d_src, d_Xoff, d_gptr, d_gsrc;
-    DBuf<int> d_gch;
+    DBuf<int> d_gch, d_tcut_ptr, d_tcut;
     DBuf<int64_t> d_pair_ptr, d_Jp, d_Rp, d_Sp;
     DBuf<int> d_pairA, d_pairB, d_hmap, d_Jrow, d_Rcol, d_Rpos, d_Scol, d_Spos;
     DevSym dev{};
@@ -73,6 +73,7 @@ struct Bundle {
         d_pairA.release(); d_pairB.release(); d_hmap.release(); d_Jrow.release(); d_Rcol.release();
         d_Rpos.release(); d_Scol.release(); d_Spos.release();
         d_owner.release(); d_colowner.release(); d_gptr.release(); d_gsrc.release(); d_gch.release();
+        d_tcut_ptr.release(); d_tcut.release();
     }
 };
 
@@ -319,6 +320,15 @@ int opb_create(opb_handle** out, int device_id, unsigned flags) {
             cudaDeviceGetStreamPriorityRange(&least, &greatest);
             e = cudaStreamCreateWithPriority(&h->side.stream, cudaStreamNonBlocking, greatest);
             h->side.chain_on_side = greatest < least;
+            // deep look-ahead: one stream per piece class, the sooner a piece is needed the higher its
+            // priority; the rest of an outer update runs at the lowest
+            for (int i = 0; i < LA_CLASSES && e == cudaSuccess; i++) {
+                e = cudaStreamCreateWithPriority(&h->side.cls[i], cudaStreamNonBlocking, std::min(least, greatest + 1 + i));
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.cls_done[i], cudaEventDisableTiming);
+            }
+            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->side.rest, cudaStreamNonBlocking, least);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.rest_done, cudaEventDisableTiming);
+            h->side.deep = true;
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.join, cudaEventDisableTiming);
@@ -348,6 +358,12 @@ int opb_destroy(opb_handle* h) {
         for (int p = 0; p < MAX_SHARD; p++) h->close_peer(p);
         h->ktimer.release();
         if (h->side.stream) { cudaStreamSynchronize(h->side.stream); cudaStreamDestroy(h->side.stream); }
+        for (int i = 0; i < LA_CLASSES; i++) {
+            if (h->side.cls[i]) { cudaStreamSynchronize(h->side.cls[i]); cudaStreamDestroy(h->side.cls[i]); }
+            if (h->side.cls_done[i]) cudaEventDestroy(h->side.cls_done[i]);
+        }
+        if (h->side.rest) { cudaStreamSynchronize(h->side.rest); cudaStreamDestroy(h->side.rest); }
+        if (h->side.rest_done) cudaEventDestroy(h->side.rest_done);
         if (h->side.fork) cudaEventDestroy(h->side.fork);
         if (h->side.join) cudaEventDestroy(h->side.join);
         if (h->side.start) cudaEventDestroy(h->side.start);
@@ -383,7 +399,7 @@ int opb_set_option(opb_handle* h, const char* key, double v) {
     else if (k == "attempts_per_sync") h->attempts_per_sync = std::max(1, (int)v);
     else if (k == "outer_block") { h->outer_block = std::max(WB, ((int)v / WB) * WB); h->drop_graphs(); }
     else if (k == "barrier_timeout_s") { h->barrier_timeout_s = v; h->sctx.timeout_clocks = (long long)(v * 2.0e9); h->drop_graphs(); }
-    else if (k == "lookahead") { h->lookahead = v != 0; h->drop_graphs(); }
+    else if (k == "lookahead") { h->lookahead = v != 0; h->side.deep = v >= 2; h->drop_graphs(); }
     else if (k == "chain_priority") { h->side.chain_on_side = v != 0; h->drop_graphs(); }
     else if (k == "graphs") { h->use_graphs = v != 0; h->drop_graphs(); }
     else if (k == "loop_graph") { h->loop_graph = v != 0; h->drop_graphs(); }
@@ -497,6 +513,7 @@ static int upload_bundle(opb_handle* h, Bundle& B) {
     CK(B.d_sched.upload(B.sched, st));
     CK(B.d_Xoff.upload(B.Xoff, st));
     CK(B.d_gptr.upload(S.gptr, st)); CK(B.d_gsrc.upload(S.gsrc, st)); CK(B.d_gch.upload(S.gch, st));
+    CK(B.d_tcut_ptr.upload(S.tcut_ptr, st)); CK(B.d_tcut.upload(S.tcut, st));
     if (B.world > 1) { CK(B.d_owner.upload(B.shard.owner, st)); CK(B.d_colowner.upload(B.colowner, st)); }
     {
         // diagonal entries carry a flag so the scatter kernel adds delta to them
@@ -524,6 +541,7 @@ static int upload_bundle(opb_handle* h, Bundle& B) {
     B.dev.sparent = B.d_sparent.p; B.dev.child_ptr = B.d_child_ptr.p; B.dev.child_list = B.d_child_list.p;
     B.dev.perm = B.d_perm.p; B.dev.Xoff = B.d_Xoff.p;
     B.dev.gptr = B.d_gptr.p; B.dev.gsrc = B.d_gsrc.p; B.dev.gch = B.d_gch.p;
+    B.dev.tcut_ptr = B.d_tcut_ptr.p; B.dev.tcut = B.d_tcut.p;
     B.dev.owner = B.world > 1 ? B.d_owner.p : nullptr;
     B.dev.rank = B.rank; B.dev.world = B.world;
     return OPB_OK;
@@ -681,7 +699,7 @@ static void enqueue_attempt_raw(opb_handle* h, KernelTimer* timer = nullptr, uns
     launch_scatter_fronts(h->Mval.p, B.d_amap.p, B.d_dpos.p, h->sdiag.p, h->Lval.p, B.S.nnzL,
                           B.Mp[B.S.n], B.S.n, h->d_state, 1, st);
     launch_factor_levels(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->Xinv.p, h->d_state, h->mode,
-                         h->outer_block, h->shard_ctx(), (h->lookahead && !timer) ? &h->side : nullptr, timer, st);
+                         h->outer_block, h->shard_ctx(), (h->lookahead && (!timer || timer->phases)) ? &h->side : nullptr, timer, st);
     if (h->mode == OPB_MODE_CHOLESKY && B.trtri.count)
         launch_trtri(h->dev, B.trtri, B.d_sched.p, h->Lval.p, h->Xinv.p, h->Twork.p, h->d_state, st);
     // sharded: every rank learns about a failed pivot anywhere before the delta rule is applied
@@ -917,6 +935,42 @@ int opb_profile_factor(opb_handle* h, double delta, double* total_ms, double* cb
     }
     if (cb_flops) *cb_flops = fcb;
     if (update_flops) *update_flops = fup;
+    return OPB_OK;
+}
+
+int opb_profile_levels(opb_handle* h, double delta, double* out, int cap, int* nlevels_out, double* total_ms) {
+    int rc = need_device(h); if (rc) return rc;
+    if (!h->B || h->ready == opb_handle::NOT_READY) return h->fail(OPB_ERR_STATE, "kkt solver not ready to factor (form_system first)");
+    if (h->sharded()) return h->fail(OPB_ERR_INVALID, "opb_profile_levels is not available on a sharded handle");
+    h->mode = OPB_MODE_CHOLESKY;
+    cudaStream_t st = h->stream;
+    KernelTimer& T = h->ktimer;
+    T.used = 0; T.marks_used = 0; T.phases = true;
+    launch_ctl_single(h->d_state, delta, OPB_MODE_CHOLESKY, st);
+    T.put_mark(4, st);
+    enqueue_attempt_raw(h, &T);          // plain launches (no graph) on the look-ahead streams as configured
+    T.put_mark(5, st);
+    T.phases = false;
+    CK(cudaGetLastError());
+    rc = read_state(h); if (rc) return rc;
+    h->ready = opb_handle::FACTORED;
+    // per level: [before the big panels (small fronts, medium panels, extend-add), big panels, update blocks]
+    const int nl = h->B->S.nlevels;
+    if (nlevels_out) *nlevels_out = nl;
+    std::vector<double> acc((size_t)nl * 3 + 2, 0.0);     // + [scatter before the levels, pivot-block inverses after them]
+    int lvl = -1, phase = 0;
+    float ms = 0.f;
+    for (size_t k = 0; k + 1 < T.marks_used; k++) {
+        const int kd = T.mark_kind[k];
+        CK(cudaEventElapsedTime(&ms, T.mark[k], T.mark[k + 1]));
+        if (kd == 4) { acc[(size_t)nl * 3] += ms; continue; }
+        if (kd == 3) { acc[(size_t)nl * 3 + 1] += ms; continue; }
+        if (kd == 0) { lvl++; phase = 0; } else if (kd == 1) phase = 1; else if (kd == 2) phase = 2; else continue;
+        if (lvl < 0 || lvl >= nl) continue;
+        acc[(size_t)lvl * 3 + phase] += ms;
+    }
+    for (int k = 0; k < nl * 3 + 2 && k < cap; k++) out[k] = acc[k];
+    if (total_ms) { CK(cudaEventElapsedTime(&ms, T.mark[0], T.mark[T.marks_used - 1])); *total_ms = ms; }
     return OPB_OK;
 }
 
@@ -1231,6 +1285,8 @@ int64_t opb_get_symbolic(opb_handle* h, const char* name, int64_t* out, int64_t 
     if (k == "gptr") return copy_out(S.gptr, out, cap);
     if (k == "gsrc") return copy_out(S.gsrc, out, cap);
     if (k == "gch") return copy_out(S.gch, out, cap);
+    if (k == "tcut_ptr") return copy_out(S.tcut_ptr, out, cap);
+    if (k == "tcut") return copy_out(S.tcut, out, cap);
     if (k == "owner") { if (B.world > 1) return copy_out(B.shard.owner, out, cap); return copy_out(std::vector<int>(S.nsuper, 0), out, cap); }
     if (k == "top") { std::vector<int> t(S.nsuper, 0); if (B.world > 1) for (int q = 0; q < S.nsuper; q++) t[q] = B.shard.top[q]; return copy_out(t, out, cap); }
     return h->fail(OPB_ERR_INVALID, "unknown symbolic array " + k);

@@ -58,6 +58,8 @@ struct DevSym {
     const int64_t* gptr;  // forward-solve gather lists (symbolic.h)
     const int64_t* gsrc;
     const int* gch;
+    const int* tcut_ptr;  // tile cuts of every update block inside its parent's (symbolic.h)
+    const int* tcut;
     // ---- one instance sharded over several GPUs; owner == nullptr on a single GPU
     const int* owner;     // per supernode: rank that owns it
     int rank, world;
@@ -169,13 +171,23 @@ void launch_ctl_single(DeltaState* st_d, double delta, int mode, cudaStream_t st
 void launch_diag_JtDJ(const int64_t* Jp, const int64_t* Ji, const double* Jx, const double* dv, double* out,
                       int n, int base, cudaStream_t st);
 
-// Second stream of a handle: the part of a panel update that does not touch the next block
-// column runs there, concurrently with the (latency-bound) diagonal-block and TRSM kernels of
-// the next step.  Fork / join through the two events (also while the main stream is captured).
+// Extra streams of a handle for the blocked panel factorisation of the big fronts.
+// Legacy look-ahead (deep == false): the part of a panel update that does not touch the next block
+// column runs on `stream`, concurrently with the (latency-bound) diagonal-block and TRSM kernels of
+// the next step.  Deep look-ahead (deep == true): `stream` (highest priority) carries the latency
+// chain; every panel update is cut into pieces by the step at which its columns are next touched --
+// piece i = block columns [tb + 2^i, tb + 2^(i+1)) is needed 2^i steps later and runs on cls[i]; the
+// part of an outer update beyond the next outer block runs on `rest` (lowest priority) -- and the
+// chain waits only for the one piece that last wrote the columns it is about to update.  Fork / join
+// through events (also while the main stream is captured into a graph).
+constexpr int LA_CLASSES = 6;      // outer blocks of up to 2^6 block columns
 struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr, start = nullptr;
     bool chain_on_side = false;   // the side stream has the highest priority and runs the latency chain
+    bool deep = false;
+    cudaStream_t cls[LA_CLASSES] = {nullptr}, rest = nullptr;
+    cudaEvent_t cls_done[LA_CLASSES] = {nullptr}, rest_done = nullptr;
 };
 
 // Optional per-kernel timing of one factorisation attempt (opb_profile_factor): CUDA events
@@ -184,12 +196,28 @@ struct KernelTimer {
     std::vector<cudaEvent_t> ev;       // pairs (begin, end)
     std::vector<int> kind;             // per pair: 0 = front_cb_kernel, 1 = chol_panel_update_kernel
     size_t used = 0;
+    // phases == true (opb_profile_levels): no per-kernel events (the attempt runs with the look-ahead
+    // streams as configured); instead single marks on the main stream at the phase boundaries of
+    // every level: level start, panels of the big fronts start, update blocks start
+    bool phases = false;
+    std::vector<cudaEvent_t> mark;
+    std::vector<int> mark_kind;        // 0 level start, 1 big panels start, 2 update blocks start, 3 end of the levels
+    size_t marks_used = 0;
+    void put_mark(int k, cudaStream_t st) {
+        if (marks_used == mark.size()) { cudaEvent_t e; cudaEventCreate(&e); mark.push_back(e); mark_kind.push_back(k); }
+        mark_kind[marks_used] = k;
+        cudaEventRecord(mark[marks_used++], st);
+    }
     cudaEvent_t next(int k) {
         if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
         if ((used & 1) == 0) { if (kind.size() <= used / 2) kind.push_back(k); else kind[used / 2] = k; }
         return ev[used++];
     }
-    void release() { for (cudaEvent_t e : ev) cudaEventDestroy(e); ev.clear(); kind.clear(); used = 0; }
+    void release() {
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        for (cudaEvent_t e : mark) cudaEventDestroy(e);
+        ev.clear(); kind.clear(); used = 0; mark.clear(); mark_kind.clear(); marks_used = 0;
+    }
 };
 
 // ---- kernels_factor.cu

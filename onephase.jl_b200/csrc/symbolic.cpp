@@ -898,6 +898,28 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
             }
         }
     }
+    // ---- tile cuts of the update blocks inside the parents' update blocks (front_cb_kernel)
+    S.tcut_ptr.assign(NS + 1, 0);
+    for (int s = 0; s < NS; s++) {
+        const int p = S.sparent[s];
+        int cnt = 0;
+        if (p >= 0) {
+            const int pc = S.sfirst[p + 1] - S.sfirst[p], pN = pc + (int)(S.rowptr[p + 1] - S.rowptr[p]);
+            cnt = (pN - (pc & ~1) + CB_TILE - 1) / CB_TILE + 1;
+        }
+        S.tcut_ptr[s + 1] = S.tcut_ptr[s] + cnt;
+    }
+    S.tcut.assign(S.tcut_ptr[NS], 0);
+    for (int s = 0; s < NS; s++) {
+        const int p = S.sparent[s];
+        if (p < 0) continue;
+        const int ce = (S.sfirst[p + 1] - S.sfirst[p]) & ~1;
+        const int* r0 = S.rel.data() + S.rowptr[s];
+        const int* r1 = S.rel.data() + S.rowptr[s + 1];
+        const int cnt = S.tcut_ptr[s + 1] - S.tcut_ptr[s];
+        for (int k = 0; k < cnt; k++)
+            S.tcut[S.tcut_ptr[s] + k] = (int)(std::lower_bound(r0, r1, ce + k * CB_TILE) - r0);
+    }
     // ---- map M_L entries into the L panels
     S.amap.assign(Mp[n], -1);
     S.dpos.assign(n, -1);

@@ -220,3 +220,27 @@ def test_update_block_storage_reuses_memory_without_overlap(pkg, gen, kw):
         for (a0, a1), (b0, b1) in zip(iv, iv[1:]):
             assert a1 <= b0, "update blocks live on level %d overlap" % l
     h.close()
+
+
+def test_tile_cut_table(pkg):
+    """tcut (symbolic.cpp): row position at which every update block crosses the 128-row tile
+    boundaries of its parent's update block == a binary search in `rel` (what front_cb_kernel did
+    per tile before the table existed)."""
+    for prob in [problems.sparse_qp(600, 300, win=5, seed=2), problems.pde_control(9, seed=4), problems.elec(60, seed=3)]:
+        h = _handle(pkg, prob)
+        sfirst = np.array(h.symbolic("sfirst")); rowptr = np.array(h.symbolic("rowptr"))
+        rel = np.array(h.symbolic("rel")); par = np.array(h.symbolic("sparent"))
+        tp = np.array(h.symbolic("tcut_ptr")); tc = np.array(h.symbolic("tcut"))
+        assert len(tp) == len(par) + 1 and tp[-1] == len(tc)
+        for s in range(len(par)):
+            p = par[s]
+            if p < 0:
+                assert tp[s + 1] == tp[s]
+                continue
+            c = sfirst[p + 1] - sfirst[p]; N = c + rowptr[p + 1] - rowptr[p]
+            ce = c & ~1
+            nt = (N - ce + 127) // 128
+            assert tp[s + 1] - tp[s] == nt + 1
+            want = np.searchsorted(rel[rowptr[s]:rowptr[s + 1]], ce + 128 * np.arange(nt + 1), side="left")
+            assert np.array_equal(tc[tp[s]:tp[s + 1]], want)
+        h.close()
