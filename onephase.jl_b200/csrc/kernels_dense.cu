@@ -73,35 +73,53 @@ __device__ __forceinline__ bool stop_requested(const DeltaState* st) {
 }
 
 // ---------------------------------------------------------------------------
-// Tile engine:  acc(128 x 128) = sum_k A[m,k] * B[n,k]
+// Tile engine:  acc(BM x 128) = sum_k A[m,k] * B[n,k],  BM = 64 * WM
 //   A: m-contiguous (column-major M x K, element (m,k) at A[m + k*lda])
 //   B: m-contiguous (B_KC = false, element (n,k) at B[n + k*ldb]) or
 //      k-contiguous (B_KC = true,  element (n,k) at B[k + n*ldb])
 // Requirements: A, B 16-byte aligned, lda/ldb even, K origin a multiple of 2.
-// 256 threads = 8 warps (2 x 4), warp tile 64 x 32, thread accumulators 8 x 4 x 2.
+// WM = 2: 128 x 128 tile, 8 compute warps (2 x 4), one CTA per SM -- the bulk kernels.
+// WM = 1:  64 x 128 tile, 4 compute warps (1 x 4), TWO CTAs per SM (registers and shared memory
+//          both allow it): the prologue / epilogue of one tile overlaps the K loop of the other and
+//          the wave granularity halves -- the short-K and narrow kernels (TRSM, update of a single
+//          block column, update blocks of the low levels), where a tile is mostly fixed cost.
+// Warp tile 64 x 32 either way, thread accumulators 8 x 4 x 2.
 // ---------------------------------------------------------------------------
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
-static_assert(BM == CB_TILE && BN == CB_TILE, "tile-cut table of symbolic.cpp");
-constexpr int LDM = BM + 4;   // [BK][LDM]: fragment reads are bank-conflict free (LDM % 16 == 4)
+constexpr int BN = 128, BK = 16, STAGES = 4;
+constexpr int LDN = BN + 4;   // [BK][LDN]: fragment reads are bank-conflict free (LDN % 16 == 4)
 constexpr int LDK = BK + 4;   // [BN][LDK]
-constexpr int A_STAGE = BK * LDM;                                  // 2112 doubles
-constexpr int B_STAGE = (BN * LDK > BK * LDM) ? BN * LDK : BK * LDM;  // 2560 doubles
-constexpr int GEMM_CWARPS = 8;                      // compute warps (2 x 4)
-constexpr int GEMM_THREADS = (GEMM_CWARPS + 1) * 32;   // + one producer warp that only issues the TMA copies
+template <int WM>
+struct TileCfg {
+    static constexpr int BM = 64 * WM;
+    static constexpr int LDM = BM + 4;                    // % 16 == 4 as well
+    static constexpr int A_STAGE = BK * LDM;
+    // WM = 1 is used with m-contiguous B only
+    static constexpr int B_STAGE = (WM == 2 && BN * LDK > BK * LDN) ? BN * LDK : BK * LDN;
+    static constexpr int CWARPS = 4 * WM;                 // compute warps
+    static constexpr int THREADS = (CWARPS + 1) * 32;     // + one producer warp that only issues the TMA copies
+};
+constexpr int BM = TileCfg<2>::BM;
+static_assert(BM == 2 * CB_TILE && BN == 2 * CB_TILE, "tile-cut table of symbolic.cpp");
+constexpr int GEMM_CWARPS = TileCfg<2>::CWARPS;
+constexpr int GEMM_THREADS = TileCfg<2>::THREADS;
 
-struct GemmSmem {
-    double A[STAGES][A_STAGE];
-    double B[STAGES][B_STAGE];
+template <int WM>
+struct GemmSmemT {
+    double A[STAGES][TileCfg<WM>::A_STAGE];
+    double B[STAGES][TileCfg<WM>::B_STAGE];
     unsigned long long full[STAGES];    // producer -> compute warps: the stage has landed (tx bytes)
     unsigned long long empty[STAGES];   // compute warps -> producer: the stage has been read
 };
+using GemmSmem = GemmSmemT<2>;
 
 // true for the threads that hold accumulators after gemm_mainloop
-__device__ __forceinline__ bool gemm_compute_warp() { return threadIdx.x < GEMM_CWARPS * 32; }
+template <int WM = 2>
+__device__ __forceinline__ bool gemm_compute_warp() { return threadIdx.x < TileCfg<WM>::CWARPS * 32; }
 
-template <bool B_KC>
-__device__ __forceinline__ void gemm_issue(GemmSmem& sm, int stage, int kb, const double* Ag, int lda, int mrows,
+template <int WM, bool B_KC>
+__device__ __forceinline__ void gemm_issue(GemmSmemT<WM>& sm, int stage, int kb, const double* Ag, int lda, int mrows,
                                            const double* Bg, int ldb, int nrows, int K, int lane) {
+    constexpr int LDM = TileCfg<WM>::LDM;
     const int k0 = kb * BK;
     const int nk = min(BK, K - k0);
     const unsigned bytesA = (unsigned)(((mrows + 1) & ~1) * 8);
@@ -115,7 +133,7 @@ __device__ __forceinline__ void gemm_issue(GemmSmem& sm, int stage, int kb, cons
     if (!B_KC) {
         const unsigned bytesB = (unsigned)(((nrows + 1) & ~1) * 8);
         for (int kk = lane; kk < nk; kk += 32)
-            bulk_g2s(&sm.B[stage][kk * LDM], Bg + (size_t)(k0 + kk) * ldb, bytesB, &sm.full[stage]);
+            bulk_g2s(&sm.B[stage][kk * LDN], Bg + (size_t)(k0 + kk) * ldb, bytesB, &sm.full[stage]);
     } else {
         const unsigned bytesB = (unsigned)(((nk + 1) & ~1) * 8);
         for (int n = lane; n < nrows; n += 32)
@@ -124,9 +142,10 @@ __device__ __forceinline__ void gemm_issue(GemmSmem& sm, int stage, int kb, cons
 }
 
 // one k-step (4 columns) of the warp tile: 12 fragment loads, 32 DMMAs
-template <bool B_KC, bool TAIL>
+template <int WM, bool B_KC, bool TAIL>
 __device__ __forceinline__ void gemm_kstep(const double* As, const double* Bs, int kk, bool kvalid,
                                            double (&acc)[8][4][2]) {
+    constexpr int LDM = TileCfg<WM>::LDM;
     double av[8], bv[4];
 #pragma unroll
     for (int mt = 0; mt < 8; mt++) {
@@ -135,7 +154,7 @@ __device__ __forceinline__ void gemm_kstep(const double* As, const double* Bs, i
     }
 #pragma unroll
     for (int nt = 0; nt < 4; nt++) {
-        const double v = B_KC ? Bs[(nt * 8) * LDK + kk] : Bs[kk * LDM + nt * 8];
+        const double v = B_KC ? Bs[(nt * 8) * LDK + kk] : Bs[kk * LDN + nt * 8];
         bv[nt] = (!TAIL || kvalid) ? v : 0.0;
     }
 #pragma unroll
@@ -144,8 +163,8 @@ __device__ __forceinline__ void gemm_kstep(const double* As, const double* Bs, i
         for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], bv[nt]);
 }
 
-// Warp-specialised main loop: warp GEMM_CWARPS streams the operands (TMA bulk copies, `full`
-// barriers), warps 0..7 run the DMMAs and hand the stage back through the `empty` barriers; no
+// Warp-specialised main loop: the last warp streams the operands (TMA bulk copies, `full`
+// barriers), the compute warps run the DMMAs and hand the stage back through the `empty` barriers; no
 // block-wide barrier inside the K loop.  On return every stage has been consumed (block barrier),
 // so the caller may reuse the shared memory; acc is valid on the compute warps only.
 struct NoHook { __device__ __forceinline__ void operator()() const {} };
@@ -153,10 +172,11 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 // L2 prefetch of the children's update-block entries the epilogue is about to merge)
 constexpr int HOOK_LEAD = 8;
 
-template <bool B_KC, class Hook = NoHook>
-__device__ __forceinline__ void gemm_mainloop(GemmSmem& sm, const double* Ag, int lda, int mrows,
+template <int WM, bool B_KC, class Hook = NoHook>
+__device__ __forceinline__ void gemm_mainloop(GemmSmemT<WM>& sm, const double* Ag, int lda, int mrows,
                                               const double* Bg, int ldb, int nrows, int K,
                                               double (&acc)[8][4][2], Hook hook = Hook()) {
+    constexpr int CW = TileCfg<WM>::CWARPS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int a = 0; a < 8; a++)
@@ -164,19 +184,19 @@ __device__ __forceinline__ void gemm_mainloop(GemmSmem& sm, const double* Ag, in
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], GEMM_CWARPS); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], CW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int nkb = (K + BK - 1) / BK;
-    if (warp == GEMM_CWARPS) {
+    if (warp == CW) {
         for (int kb = 0; kb < nkb; kb++) {
             const int stage = kb % STAGES;
             if (kb >= STAGES) mbar_wait(&sm.empty[stage], (unsigned)(((kb / STAGES) - 1) & 1));
-            gemm_issue<B_KC>(sm, stage, kb, Ag, lda, mrows, Bg, ldb, nrows, K, lane);
+            gemm_issue<WM, B_KC>(sm, stage, kb, Ag, lda, mrows, Bg, ldb, nrows, K, lane);
         }
     } else {
-        const int wm = warp >> 2, wn = warp & 3;     // 2 x 4 warps, warp tile 64 x 32
+        const int wm = warp >> 2, wn = warp & 3;     // WM x 4 warps, warp tile 64 x 32
         const int q = lane & 3, g = lane >> 2;
         const int aoff = wm * 64 + g;
         const int boff = B_KC ? (wn * 32 + g) * LDK : wn * 32 + g;
@@ -190,10 +210,10 @@ __device__ __forceinline__ void gemm_mainloop(GemmSmem& sm, const double* Ag, in
             const int nk = K - kb * BK;
             if (nk >= BK) {
 #pragma unroll
-                for (int ks = 0; ks < BK / 4; ks++) gemm_kstep<B_KC, false>(As, Bs, ks * 4 + q, true, acc);
+                for (int ks = 0; ks < BK / 4; ks++) gemm_kstep<WM, B_KC, false>(As, Bs, ks * 4 + q, true, acc);
             } else {
 #pragma unroll 1
-                for (int ks = 0; ks * 4 < nk; ks++) gemm_kstep<B_KC, true>(As, Bs, ks * 4 + q, ks * 4 + q < nk, acc);
+                for (int ks = 0; ks * 4 < nk; ks++) gemm_kstep<WM, B_KC, true>(As, Bs, ks * 4 + q, ks * 4 + q < nk, acc);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[stage]);
@@ -202,7 +222,7 @@ __device__ __forceinline__ void gemm_mainloop(GemmSmem& sm, const double* Ag, in
     __syncthreads();
 }
 
-// coordinates of accumulator element (mt, nt, e) inside the 128 x 128 tile
+// coordinates of accumulator element (mt, nt, e) inside the tile (warp rows 0 .. WM-1: threadIdx.x >> 7)
 __device__ __forceinline__ int acc_row(int mt) { return ((threadIdx.x >> 5) >> 2) * 64 + mt * 8 + ((threadIdx.x & 31) >> 2); }
 __device__ __forceinline__ int acc_col(int nt, int e) { return ((threadIdx.x >> 5) & 3) * 32 + nt * 8 + 2 * (threadIdx.x & 3) + e; }
 
@@ -551,9 +571,12 @@ mid_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
     }
 }
 
-// big fronts: add the children's update blocks into the panel columns only
-constexpr int EAP_RB = 32;
-__global__ void __launch_bounds__(256)
+// big fronts: add the children's update blocks into the panel columns only.  A CTA owns EAP_RB
+// consecutive front rows; a warp walks the child's columns for 32 of the child's rows (coalesced along
+// the rows on both sides) with EAP_Q independent read-modify-writes in flight per lane -- the kernel is
+// a chain of DRAM round trips, so its speed is the number of them in flight.
+constexpr int EAP_RB = 32, EAP_T = 256, EAP_W = EAP_T / 32, EAP_Q = 4;
+__global__ void __launch_bounds__(EAP_T)
 big_extend_add_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval,
                             const double* __restrict__ CB, DeltaState* st) {
     if (stop_requested(st)) return;
@@ -581,47 +604,49 @@ big_extend_add_panel_kernel(DevSym S, const int* __restrict__ list, double* __re
         for (int tt = t0 + tx; tt < t1; tt += 32) {
             const int pi = relc[tt];
             const int ue = min(uc, tt + 1);
-            // four independent read-modify-writes in flight per thread (distinct columns)
-            for (int u = ty; u < ue; u += 32) {
-                double v[4], l[4];
-                size_t off[4];
+            for (int u = ty; u < ue; u += EAP_W * EAP_Q) {
+                double v[EAP_Q], l[EAP_Q];
+                size_t off[EAP_Q];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int uu = u + 8 * q;
+                for (int q = 0; q < EAP_Q; q++) {
+                    const int uu = u + EAP_W * q;
                     const bool ok = uu < ue;
                     off[q] = (size_t)d.loff + pi + (size_t)relc[ok ? uu : u] * d.ld;
                     v[q] = ok ? cb[tt + (size_t)uu * rc] : 0.0;
                     l[q] = ok ? Lval[off[q]] : 0.0;
                 }
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (u + 8 * q < ue) Lval[off[q]] = l[q] + v[q];
+                for (int q = 0; q < EAP_Q; q++)
+                    if (u + EAP_W * q < ue) Lval[off[q]] = l[q] + v[q];
             }
         }
         __syncthreads();     // the next child may hit the same panel entries from other threads
     }
 }
 
-// rows below the diagonal block:  L21 = A21 * inv(L_kk)^T  as a tensor-core GEMM
-__global__ void __launch_bounds__(GEMM_THREADS)
+// rows below the diagonal block:  L21 = A21 * inv(L_kk)^T  as a tensor-core GEMM (64-row tiles, two
+// CTAs per SM: K is only 128, a tile is mostly prologue and epilogue)
+template <int WM>
+__global__ void __launch_bounds__(TileCfg<WM>::THREADS, 3 - WM)
 chol_trsm_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval,
                  const double* __restrict__ Xinv, int t, DeltaState* st) {
+    constexpr int BM_ = TileCfg<WM>::BM;
     extern __shared__ __align__(16) unsigned char smraw[];
-    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smraw);
+    GemmSmemT<WM>& sm = *reinterpret_cast<GemmSmemT<WM>*>(smraw);
     if (stop_requested(st)) return;
     const Front d = get_front(S, list[blockIdx.y]);
     const int j0 = t * WB;
     if (j0 >= d.c) return;
     const int b = min(WB, d.c - j0);
     const int j1 = j0 + b;
-    const int row0 = (j1 & ~1) + blockIdx.x * BM;
+    const int row0 = (j1 & ~1) + blockIdx.x * BM_;
     if (row0 >= d.N) return;
-    const int mrows = min(BM, d.N - row0);
+    const int mrows = min(BM_, d.N - row0);
     double* Ag = Lval + d.loff + row0 + (size_t)j0 * d.ld;
     const double* Bg = Xinv + d.xoff + j0 + (size_t)j0 * d.ldx;
     double acc[8][4][2];
-    gemm_mainloop<false>(sm, Ag, d.ld, mrows, Bg, d.ldx, b, b, acc);
-    if (!gemm_compute_warp()) return;
+    gemm_mainloop<WM, false>(sm, Ag, d.ld, mrows, Bg, d.ldx, b, b, acc);
+    if (!gemm_compute_warp<WM>()) return;
 #pragma unroll
     for (int mt = 0; mt < 8; mt++) {
         const int i = row0 + acc_row(mt);
@@ -644,30 +669,47 @@ chol_trsm_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
 // with a long K loop and the panel is read-modify-written c/outer instead of c/WB times.
 // cbeg and k0 are multiples of WB.  (The update block of the front is formed once, at the end,
 // by front_cb_kernel.)
-__global__ void __launch_bounds__(GEMM_THREADS)
+// WM = 1: 64-row tiles, two CTAs per SM.
+template <int WM>
+__global__ void __launch_bounds__(TileCfg<WM>::THREADS, 3 - WM)
 chol_panel_update_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval,
                          int k0, int klen, int cbeg, int cend, DeltaState* st) {
+    constexpr int BM_ = TileCfg<WM>::BM;
     extern __shared__ __align__(16) unsigned char smraw[];
-    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smraw);
+    GemmSmemT<WM>& sm = *reinterpret_cast<GemmSmemT<WM>*>(smraw);
     if (stop_requested(st)) return;
     const Front d = get_front(S, list[blockIdx.y]);
     if (cbeg >= d.c) return;               // no panel columns left
     const int ce = min(cend, d.c);
     const int kl = min(klen, d.c - k0);
-    const int nrow = (d.N - cbeg + BM - 1) / BM;
+    const int nrow = (d.N - cbeg + BM_ - 1) / BM_;
+    int I = -1, J = 0;
     const int ncol = (ce - cbeg + BN - 1) / BN;
-    int tp = blockIdx.x, I = -1, J = 0;
-    for (; J < ncol; J++) {
-        if (tp < nrow - J) { I = J + tp; break; }
-        tp -= nrow - J;
+    if (WM == 1) {
+        // 64-row tiles: column tile J (128 wide) starts at row tile 2J; J (nrow + 1) - J^2 tiles precede it
+        const long long tp = blockIdx.x;
+        const double b = (double)nrow + 1.0;
+        const double disc = b * b - 4.0 * (double)tp;
+        J = disc > 0.0 ? (int)((b - sqrt(disc)) * 0.5) : nrow / 2;
+        while (J > 0 && (long long)J * (nrow + 1) - (long long)J * J > tp) J--;
+        while ((long long)(J + 1) * (nrow + 1) - (long long)(J + 1) * (J + 1) <= tp && 2 * (J + 1) < nrow) J++;
+        const long long before = (long long)J * (nrow + 1) - (long long)J * J;
+        const long long off = tp - before;
+        if (J < ncol && 2 * J + off < nrow) I = 2 * J + (int)off;
+    } else {
+        int tp = blockIdx.x;
+        for (; J < ncol; J++) {
+            if (tp < nrow - J) { I = J + tp; break; }
+            tp -= nrow - J;
+        }
     }
     if (I < 0) return;
-    const int ri = cbeg + I * BM, rj = cbeg + J * BN;
+    const int ri = cbeg + I * BM_, rj = cbeg + J * BN;
     const double* Ag = Lval + d.loff + ri + (size_t)k0 * d.ld;
     const double* Bg = Lval + d.loff + rj + (size_t)k0 * d.ld;
     double acc[8][4][2];
-    gemm_mainloop<false>(sm, Ag, d.ld, min(BM, d.N - ri), Bg, d.ld, min(BN, d.N - rj), kl, acc);
-    if (!gemm_compute_warp()) return;
+    gemm_mainloop<WM, false>(sm, Ag, d.ld, min(BM_, d.N - ri), Bg, d.ld, min(BN, d.N - rj), kl, acc);
+    if (!gemm_compute_warp<WM>()) return;
 #pragma unroll
     for (int nt = 0; nt < 4; nt++)
 #pragma unroll
@@ -686,33 +728,33 @@ chol_panel_update_kernel(DevSym S, const int* __restrict__ list, double* __restr
 
 // update block of a medium / big front, written once:
 //   CB[I,J] = sum_children (extend-add) - L21[I,:] * L21[J,:]^T      (K = all c pivot columns)
-constexpr int TLD = BM + 1;
 
 // rows [t0, t1) and columns [u0, u1) of child `ch` (positions in its update block) that land in
 // tile (I, J) of the parent's update block: read from the tile-cut table built at symbolic time
 // (four independent loads; the binary searches they replace were 30-50 dependent L2 round trips per
 // child and tile, the bulk of a short-K tile's epilogue)
 struct ChildRange { int t0, t1, u0, u1, rc; const int* relc; };
-__device__ __forceinline__ ChildRange child_range(const DevSym& S, int ch, int I, int J) {
+// the tile covers the 64-row cuts [r64, r64 + nr64) and the 128-column tile J = cuts [2J, 2J + 2)
+__device__ __forceinline__ ChildRange child_range(const DevSym& S, int ch, int r64, int nr64, int J) {
     ChildRange R;
     const int64_t rp = S.rowptr[ch];
     R.rc = (int)(S.rowptr[ch + 1] - rp);
     R.relc = S.rel + rp;
     const int* __restrict__ tc = S.tcut + S.tcut_ptr[ch];
-    R.t0 = tc[I]; R.t1 = tc[I + 1];
-    R.u0 = tc[J]; R.u1 = tc[J + 1];
+    R.t0 = tc[r64]; R.t1 = tc[r64 + nr64];
+    R.u0 = tc[2 * J]; R.u1 = tc[2 * J + 2];
     return R;
 }
 
 // pulls the children's entries of this tile towards L2 a few stages before the K loop ends, so
 // the merge below finds them on chip instead of paying a DRAM round trip per dependent step
 struct CbPrefetch {
-    const DevSym& S; const double* CB; int s, I, J;
+    const DevSym& S; const double* CB; int s, r64, nr64, J;
     __device__ __forceinline__ void operator()() const {
         const int tid = threadIdx.x;        // compute warps only: 0 .. GEMM_CWARPS*32-1
         for (int k = S.child_ptr[s]; k < S.child_ptr[s + 1]; k++) {
             const int ch = S.child_list[k];
-            const ChildRange R = child_range(S, ch, I, J);
+            const ChildRange R = child_range(S, ch, r64, nr64, J);
             if (R.t1 <= R.t0 || R.u1 <= R.u0) continue;
             const double* __restrict__ cb = child_cb(S, CB, ch);
             // one 128-byte line = 16 doubles; a column segment of <= 128 rows spans <= 9 lines
@@ -730,63 +772,79 @@ struct CbPrefetch {
     }
 };
 
-__global__ void __launch_bounds__(GEMM_THREADS)
-front_cb_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lval,
-                double* __restrict__ CB, DeltaState* st) {
+template <int WM>
+__global__ void __launch_bounds__(TileCfg<WM>::THREADS, 3 - WM)
+front_cb_kernel(DevSym S, const int* __restrict__ list, const int2* __restrict__ tiles,
+                const double* __restrict__ Lval, double* __restrict__ CB, DeltaState* st) {
+    constexpr int BM_ = TileCfg<WM>::BM, NTHR = TileCfg<WM>::THREADS, TLD_ = BM_ + 1;
     extern __shared__ __align__(16) unsigned char smraw[];
-    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smraw);
+    GemmSmemT<WM>& sm = *reinterpret_cast<GemmSmemT<WM>*>(smraw);
     if (stop_requested(st)) return;
-    const Front d = get_front(S, list[blockIdx.y]);
-    if (d.r <= 0) return;
+    // exact tile list of the level (built with the schedule): a grid sized for the largest front
+    // times the number of fronts would be mostly CTAs that find nothing to do, and each of those
+    // still holds a 100+ KB shared-memory slot for a few dependent loads
+    const int2 wt = tiles[blockIdx.x];
+    const Front d = get_front(S, list[wt.x]);
     const int ce = d.c & ~1;
-    const int nt_ = (d.N - ce + BM - 1) / BM;
-    const long long tp = blockIdx.x;
-    if (tp >= (long long)nt_ * (nt_ + 1) / 2) return;
-    int I = (int)((sqrt(8.0 * (double)tp + 1.0) - 1.0) * 0.5);
-    while ((long long)I * (I + 1) / 2 > tp) I--;
-    while ((long long)(I + 1) * (I + 2) / 2 <= tp) I++;
-    const int J = (int)(tp - (long long)I * (I + 1) / 2);
-    const int ri = ce + I * BM, rj = ce + J * BN;
+    const long long tp = wt.y;
+    int I, J;
+    if (WM == 2) {
+        I = (int)((sqrt(8.0 * (double)tp + 1.0) - 1.0) * 0.5);
+        while ((long long)I * (I + 1) / 2 > tp) I--;
+        while ((long long)(I + 1) * (I + 2) / 2 <= tp) I++;
+        J = (int)(tp - (long long)I * (I + 1) / 2);
+    } else {
+        int a = (int)((sqrt(4.0 * (double)tp + 1.0) - 1.0) * 0.5);
+        while ((long long)a * (a + 1) > tp) a--;
+        while ((long long)(a + 1) * (a + 2) <= tp) a++;
+        const int rem = (int)(tp - (long long)a * (a + 1));
+        if (rem <= a) { I = 2 * a; J = rem; } else { I = 2 * a + 1; J = rem - (a + 1); }
+    }
+    const int ri = ce + I * BM_, rj = ce + J * BN;
+    const int r64 = I * WM;                    // first 64-row cut of the tile
     const double* Ag = Lval + d.loff + ri;
     const double* Bg = Lval + d.loff + rj;
     double acc[8][4][2];
-    gemm_mainloop<false>(sm, Ag, d.ld, min(BM, d.N - ri), Bg, d.ld, min(BN, d.N - rj), d.c, acc,
-                         CbPrefetch{S, CB, d.s, I, J});
-    // the stage buffers are free now: reuse them as the 128 x 128 tile (ld 129)
+    gemm_mainloop<WM, false>(sm, Ag, d.ld, min(BM_, d.N - ri), Bg, d.ld, min(BN, d.N - rj), d.c, acc,
+                             CbPrefetch{S, CB, d.s, r64, WM, J});
+    // the stage buffers are free now: reuse them as the BM_ x 128 tile (ld BM_ + 1)
     double* T = reinterpret_cast<double*>(smraw);
-    if (gemm_compute_warp()) {
+    static_assert((size_t)TLD_ * BN * sizeof(double) <= sizeof(GemmSmemT<WM>) - 2 * STAGES * sizeof(unsigned long long),
+                  "merge tile must fit in the stage ring");
+    if (gemm_compute_warp<WM>()) {
 #pragma unroll
         for (int mt = 0; mt < 8; mt++)
 #pragma unroll
             for (int nt = 0; nt < 4; nt++)
 #pragma unroll
-                for (int e = 0; e < 2; e++) T[acc_row(mt) + acc_col(nt, e) * TLD] = -acc[mt][nt][e];
+                for (int e = 0; e < 2; e++) T[acc_row(mt) + acc_col(nt, e) * TLD_] = -acc[mt][nt][e];
     }
     __syncthreads();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = GEMM_THREADS / 32;
+    constexpr int NW = NTHR / 32;
+    constexpr int NQ = 2 * WM;                 // 32-row groups per tile column
     for (int k = S.child_ptr[d.s]; k < S.child_ptr[d.s + 1]; k++) {
         const int ch = S.child_list[k];
-        const ChildRange R = child_range(S, ch, I, J);
+        const ChildRange R = child_range(S, ch, r64, WM, J);
         if (R.t1 <= R.t0 || R.u1 <= R.u0) continue;          // uniform across the CTA
         const double* __restrict__ cb = child_cb(S, CB, ch);
         const int* __restrict__ relc = R.relc;
-        // a warp takes two child columns per round, a lane up to 4 rows of each: 8 independent
+        // a warp takes two child columns per round, a lane up to NQ rows of each: 2 NQ independent
         // loads in flight per lane before the first shared-memory update.  Distinct (row, column)
         // pairs of one child land on distinct tile entries, so there are no conflicts inside a child;
         // the barrier orders the children (ascending: fixed summation order).
         for (int u = R.u0 + 2 * warp; u < R.u1; u += 2 * NW) {
-            double v[2][4];
-            int dst[2][4];
+            double v[2][NQ];
+            int dst[2][NQ];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int uu = u + h;
                 const bool cok = uu < R.u1;
                 const int tb = max(R.t0, uu);
-                const int pc = cok ? (relc[uu] - rj) * TLD - ri : 0;
+                const int pc = cok ? (relc[uu] - rj) * TLD_ - ri : 0;
                 const double* col = cb + (size_t)(cok ? uu : u) * R.rc;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
+                for (int q = 0; q < NQ; q++) {
                     const int tt = tb + lane + 32 * q;
                     const bool ok = cok && tt < R.t1;
                     v[h][q] = ok ? col[tt] : 0.0;
@@ -796,16 +854,16 @@ front_cb_kernel(DevSym S, const int* __restrict__ list, const double* __restrict
 #pragma unroll
             for (int h = 0; h < 2; h++)
 #pragma unroll
-                for (int q = 0; q < 4; q++)
+                for (int q = 0; q < NQ; q++)
                     if (dst[h][q] >= 0) T[dst[h][q]] += v[h][q];
         }
         __syncthreads();
     }
     double* out = CB + d.cboff;
-    for (int idx = tid; idx < BM * BN; idx += GEMM_THREADS) {
-        const int i = ri + idx % BM, kk = rj + idx / BM;
+    for (int idx = tid; idx < BM_ * BN; idx += NTHR) {
+        const int i = ri + idx % BM_, kk = rj + idx / BM_;
         if (i < d.N && kk >= d.c && kk < d.N && i >= kk)
-            out[(i - d.c) + (size_t)(kk - d.c) * d.r] = T[(i - ri) + (kk - rj) * TLD];
+            out[(i - d.c) + (size_t)(kk - d.c) * d.r] = T[(i - ri) + (kk - rj) * TLD_];
     }
 }
 
@@ -817,18 +875,20 @@ front_cb_kernel(DevSym S, const int* __restrict__ list, const double* __restrict
 //   phase 1:  X21 = -Ci * T
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEMM_THREADS)
-trtri_merge_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ Lval,
-                   double* __restrict__ Xinv, double* __restrict__ Twork, int lvl, int phase,
-                   const DeltaState* st) {
+trtri_merge_kernel(DevSym S, const int* __restrict__ list, const int2* __restrict__ items,
+                   const double* __restrict__ Lval, double* __restrict__ Xinv, double* __restrict__ Twork,
+                   int lvl, int phase, const DeltaState* st) {
     extern __shared__ __align__(16) unsigned char smraw[];
     GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smraw);
     if (stop_requested(st)) return;
-    const Front d = get_front(S, list[blockIdx.y]);
+    // exact work list of the merge level (built with the schedule): (supernode, pair * nsub^2 + I * nsub + J)
+    const int2 it = items[blockIdx.x];
+    const Front d = get_front(S, list[it.x]);
     const int nsub = 1 << lvl;              // 128-blocks per half
     const int Sz = WB * nsub;
     const int per_pair = nsub * nsub;
-    const int pair = blockIdx.x / per_pair;
-    const int ij = blockIdx.x % per_pair;
+    const int pair = it.y / per_pair;
+    const int ij = it.y % per_pair;
     const int I = ij / nsub, J = ij % nsub;
     const int a0 = pair * 2 * Sz, a1 = a0 + Sz;
     if (a1 >= d.c) return;
@@ -842,14 +902,14 @@ trtri_merge_kernel(DevSym S, const int* __restrict__ list, const double* __restr
         // T[i,j] = sum_{k in [col0, a1)} L[i,k] * X[k,j]   (X11 lower: X[k,j] = 0 for k < j)
         const double* Ag = Lval + d.loff + row0 + (size_t)col0 * d.ld;
         const double* Bg = Xinv + d.xoff + col0 + (size_t)col0 * d.ldx;
-        gemm_mainloop<true>(sm, Ag, d.ld, mrows, Bg, d.ldx, BN, a1 - col0, acc);
+        gemm_mainloop<2, true>(sm, Ag, d.ld, mrows, Bg, d.ldx, BN, a1 - col0, acc);
         out = Twork + d.xoff;
     } else {
         // X21[i,j] = - sum_{k in [a1, row0 + mrows)} X[i,k] * T[k,j]   (X22 lower)
         const int kend = min(a2, row0 + BM);
         const double* Ag = Xinv + d.xoff + row0 + (size_t)a1 * d.ldx;
         const double* Bg = Twork + d.xoff + a1 + (size_t)col0 * d.ldx;
-        gemm_mainloop<true>(sm, Ag, d.ldx, mrows, Bg, d.ldx, BN, kend - a1, acc);
+        gemm_mainloop<2, true>(sm, Ag, d.ldx, mrows, Bg, d.ldx, BN, kend - a1, acc);
         out = Xinv + d.xoff;
     }
     if (!gemm_compute_warp()) return;
@@ -877,6 +937,10 @@ constexpr int WT = 512;
 constexpr int SLAB = 32;      // rows per CTA in the row-oriented products
 constexpr int TALL_N = 8192;  // fronts with at least this many rows take the finer-grained solve variants
 constexpr int KG = WT / 32;   // k-groups (warps)
+#ifndef OPB_TALL_WPC
+#define OPB_TALL_WPC 4
+#endif
+constexpr int TALL_WPC = OPB_TALL_WPC;   // warps per column of the backward products on tall fronts
 
 // children's update vectors into this supernode's right-hand side; a CTA owns a range of
 // destination rows, a thread one destination: it sums that destination's sources in ascending
@@ -1131,25 +1195,38 @@ inline size_t mid_smem(int panel) { return (size_t)(panel + INVBUF) * sizeof(dou
 
 }  // namespace
 
+int g_occ_small_tiles = -1;   // resident CTAs per SM of the 64-row-tile kernels (opb_get_info "occ_small_tiles")
+
 cudaError_t dense_configure() {
     cudaError_t e;
     e = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)diag_smem());
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(mid_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem(MIDL_PANEL));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(chol_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(chol_panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(front_cb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(trtri_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GemmSmem));
+    auto gemm_attr = [](const void* f, size_t smem) -> cudaError_t {
+        cudaError_t e2 = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e2 != cudaSuccess) return e2;
+        // the whole L1/shared array as shared memory: two 64-row-tile CTAs (2 x 100 KB) must fit on an SM
+        return cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    };
+    e = gemm_attr((const void*)chol_trsm_kernel<1>, sizeof(GemmSmemT<1>)); if (e != cudaSuccess) return e;
+    e = gemm_attr((const void*)chol_panel_update_kernel<1>, sizeof(GemmSmemT<1>)); if (e != cudaSuccess) return e;
+    e = gemm_attr((const void*)chol_panel_update_kernel<2>, sizeof(GemmSmem)); if (e != cudaSuccess) return e;
+    e = gemm_attr((const void*)front_cb_kernel<1>, sizeof(GemmSmemT<1>)); if (e != cudaSuccess) return e;
+    e = gemm_attr((const void*)front_cb_kernel<2>, sizeof(GemmSmem)); if (e != cudaSuccess) return e;
+    e = gemm_attr((const void*)trtri_merge_kernel, sizeof(GemmSmem)); if (e != cudaSuccess) return e;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, front_cb_kernel<1>, TileCfg<1>::THREADS, sizeof(GemmSmemT<1>)) == cudaSuccess)
+        g_occ_small_tiles = occ;
+    else cudaGetLastError();
+    return cudaSuccess;
 }
 
 void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
-                            double* CB, double* Xinv, DeltaState* st_d, int outer_block, const SideStream* side,
-                            KernelTimer* timer, cudaStream_t st) {
+                            double* CB, double* Xinv, DeltaState* st_d, int outer_block, int cb_small_k,
+                            const SideStream* side, KernelTimer* timer, cudaStream_t st) {
     if (!L.wide_count) return;
+    const bool upd_small_tiles = (cb_small_k & 1) == 0;     // odd cb_small_k (tuning): bulk panel updates in 128-row tiles
     KernelTimer* phase_timer = (timer && timer->phases) ? timer : nullptr;
     if (phase_timer) timer = nullptr;
     // medium fronts: panel in shared memory
@@ -1162,7 +1239,7 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
     if (L.count[FC_BIG]) {
         const int* list = d_sched + L.begin[FC_BIG];
         dim3 gea((L.maxN[FC_BIG] + EAP_RB - 1) / EAP_RB, L.count[FC_BIG]);
-        big_extend_add_panel_kernel<<<gea, 256, 0, st>>>(S, list, Lval, CB, st_d);
+        big_extend_add_panel_kernel<<<gea, EAP_T, 0, st>>>(S, list, Lval, CB, st_d);
         count_launch();
         if (phase_timer) phase_timer->put_mark(1, st);
         int sub = 1;                                            // WB blocks per outer block (power of two)
@@ -1173,6 +1250,20 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
             const int tb = cbeg / WB;
             if (cend <= cbeg || tb >= nsteps || L.step_count[tb] <= 0) return false;
             const int cnt2 = L.step_count[tb];
+            if (cend - cbeg <= WB || upd_small_tiles) {
+                // 64-row tiles, two CTAs per SM
+                const int nrow64 = (L.step_maxN[tb] - cbeg + 63) / 64;
+                const int ncol = (std::min(cend, L.maxC[FC_BIG]) - cbeg + BN - 1) / BN;
+                long long tiles = 0;
+                for (int J = 0; J < ncol && 2 * J < nrow64; J++) tiles += nrow64 - 2 * J;
+                if (tiles <= 0) return false;
+                dim3 gu((unsigned)tiles, cnt2);
+                if (timer) cudaEventRecord(timer->next(1), sx);
+                chol_panel_update_kernel<1><<<gu, TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), sx>>>(S, list, Lval, k0, klen, cbeg, cend, st_d);
+                if (timer) cudaEventRecord(timer->next(1), sx);
+                count_launch();
+                return true;
+            }
             const int nrow = (L.step_maxN[tb] - cbeg + BM - 1) / BM;
             const int ncol = (std::min(cend, L.maxC[FC_BIG]) - cbeg + BN - 1) / BN;
             long long tiles = 0;
@@ -1180,7 +1271,7 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
             if (tiles <= 0) return false;
             dim3 gu((unsigned)tiles, cnt2);
             if (timer) cudaEventRecord(timer->next(1), sx);
-            chol_panel_update_kernel<<<gu, GEMM_THREADS, sizeof(GemmSmem), sx>>>(S, list, Lval, k0, klen, cbeg, cend, st_d);
+            chol_panel_update_kernel<2><<<gu, GEMM_THREADS, sizeof(GemmSmem), sx>>>(S, list, Lval, k0, klen, cbeg, cend, st_d);
             if (timer) cudaEventRecord(timer->next(1), sx);
             count_launch();
             return true;
@@ -1206,9 +1297,9 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
                 count_launch();
                 const int rem = maxN - t * WB;
                 if (rem <= 0) continue;
-                const int nrow = (rem + BM - 1) / BM + 1;
+                const int nrow = (rem + 63) / 64 + 1;
                 dim3 gt(nrow, cnt);
-                chol_trsm_kernel<<<gt, GEMM_THREADS, sizeof(GemmSmem), C>>>(S, list, Lval, Xinv, t, st_d);
+                chol_trsm_kernel<1><<<gt, TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), C>>>(S, list, Lval, Xinv, t, st_d);
                 count_launch();
                 const int tb = t + 1;
                 if (tb >= nsteps || L.step_count[tb] <= 0) continue;       // no panel columns left
@@ -1260,9 +1351,9 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
             count_launch();
             const int rem = maxN - t * WB;     // rows from the start of the block (upper bound)
             if (rem <= 0) continue;
-            const int nrow = (rem + BM - 1) / BM + 1;
+            const int nrow = (rem + 63) / 64 + 1;
             dim3 gt(nrow, cnt);
-            chol_trsm_kernel<<<gt, GEMM_THREADS, sizeof(GemmSmem), C>>>(S, list, Lval, Xinv, t, st_d);
+            chol_trsm_kernel<1><<<gt, TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), C>>>(S, list, Lval, Xinv, t, st_d);
             count_launch();
             // Recursive (binary) schedule of the right-looking updates: with tb blocks finished and
             // 2^j the largest power of two dividing tb, the last 2^j blocks update the next 2^j
@@ -1298,26 +1389,32 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
     }
     // update blocks of all medium and big fronts, written once
     {
-        const long long nt = (L.wide_maxR + 1 + BM - 1) / BM + 1;
-        dim3 g((unsigned)(nt * (nt + 1) / 2), L.wide_count);
+        // short K (low levels): 64-row tiles, two CTAs per SM; otherwise 128 x 128 tiles
+        const int v = L.wide_maxC <= cb_small_k ? 0 : 1;
         if (phase_timer) phase_timer->put_mark(2, st);
-        if (timer) cudaEventRecord(timer->next(0), st);
-        front_cb_kernel<<<g, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, d_sched + L.wide_begin, Lval, CB, st_d);
-        if (timer) cudaEventRecord(timer->next(0), st);
-        count_launch();
+        if (L.cbt_count[v] > 0) {
+            const int2* tiles = reinterpret_cast<const int2*>(d_sched + L.cbt_begin[v]);
+            if (timer) cudaEventRecord(timer->next(0), st);
+            if (v == 0)
+                front_cb_kernel<1><<<L.cbt_count[v], TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), st>>>(
+                    S, d_sched + L.wide_begin, tiles, Lval, CB, st_d);
+            else
+                front_cb_kernel<2><<<L.cbt_count[v], GEMM_THREADS, sizeof(GemmSmem), st>>>(
+                    S, d_sched + L.wide_begin, tiles, Lval, CB, st_d);
+            if (timer) cudaEventRecord(timer->next(0), st);
+            count_launch();
+        }
     }
 }
 
 void launch_trtri(const DevSym& S, const TrtriPlan& T, const int* d_sched, const double* Lval,
                   double* Xinv, double* Twork, const DeltaState* st_d, cudaStream_t st) {
     const int* list = d_sched + T.list_begin;
-    for (size_t l = 0; l < T.level_count.size(); l++) {
-        const int cnt = T.level_count[l];
-        if (cnt <= 0) break;
-        const int nsub = 1 << l;
-        dim3 g((unsigned)(T.level_pairs[l] * nsub * nsub), cnt);
+    for (size_t l = 0; l < T.items_count.size(); l++) {
+        if (T.items_count[l] <= 0) continue;
+        const int2* items = reinterpret_cast<const int2*>(d_sched + T.items_begin[l]);
         for (int phase = 0; phase < 2; phase++) {
-            trtri_merge_kernel<<<g, GEMM_THREADS, sizeof(GemmSmem), st>>>(S, list, Lval, Xinv, Twork, (int)l, phase, st_d);
+            trtri_merge_kernel<<<T.items_count[l], GEMM_THREADS, sizeof(GemmSmem), st>>>(S, list, items, Lval, Xinv, Twork, (int)l, phase, st_d);
             count_launch();
         }
     }
@@ -1362,7 +1459,7 @@ void launch_solve_wide_bwd(const DevSym& S, const LevelPlan& L, const int* d_sch
     for (int blk = nblk - 1; blk >= 0; blk--) {
         const int cb = std::min(XB, L.maxC[FC_BIG] - blk * XB);
         if (L.maxN[FC_BIG] >= TALL_N) {
-            constexpr int WPC = 4;
+            constexpr int WPC = TALL_WPC;
             dim3 g1((cb + KG / WPC - 1) / (KG / WPC), cnt);
             wide_bwd_upd_kernel<WPC><<<g1, WT, 0, st>>>(S, list, Lval, x, xnew, u, blk);
             wide_bwd_tri_kernel<WPC><<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
@@ -1384,16 +1481,18 @@ cudaError_t preload_dense() {
     cudaError_t e;
     e = cudaFuncGetAttributes(&a, big_extend_add_panel_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, chol_diag_kernel); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, chol_panel_update_kernel); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, chol_trsm_kernel); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, front_cb_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, chol_panel_update_kernel<1>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, chol_panel_update_kernel<2>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, chol_trsm_kernel<1>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, front_cb_kernel<1>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, front_cb_kernel<2>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, mid_panel_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, trtri_merge_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_bwd_gather_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_bwd_tri_kernel<1>); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, wide_bwd_tri_kernel<4>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_bwd_tri_kernel<TALL_WPC>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_bwd_upd_kernel<1>); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, wide_bwd_upd_kernel<4>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, wide_bwd_upd_kernel<TALL_WPC>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_fwd_gather_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_fwd_tri_kernel<8>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_fwd_tri_kernel<SLAB>); if (e != cudaSuccess) return e;

@@ -361,10 +361,31 @@ cudaError_t factor_configure() {
 
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
-                          int outer_block, const ShardCtx* shard, const SideStream* side, KernelTimer* timer,
-                          cudaStream_t st) {
+                          int outer_block, int cb_small_k, const ShardCtx* shard, const SideStream* side,
+                          KernelTimer* timer, const std::vector<TrtriPlan>* trtri, double* Twork, cudaStream_t st) {
     bool prev_cross = false;
+    size_t next_trtri = 0;
+    bool aux_busy = false;
+    int lvl = -1;
+    // pivot-block inverses of the levels factorised so far: on the auxiliary stream when there is one
+    // and more levels follow (they hide behind those), otherwise in line
+    auto flush_trtri = [&](bool last) {
+        while (trtri && next_trtri < trtri->size() && ((*trtri)[next_trtri].after_level <= lvl || last)) {
+            const TrtriPlan& T = (*trtri)[next_trtri++];
+            if (side && side->aux && !last) {
+                cudaEventRecord(side->aux_fork, st);
+                cudaStreamWaitEvent(side->aux, side->aux_fork, 0);
+                launch_trtri(S, T, d_sched, Lval, Xinv, Twork, st_d, side->aux);
+                cudaEventRecord(side->aux_done, side->aux);
+                aux_busy = true;
+            } else {
+                launch_trtri(S, T, d_sched, Lval, Xinv, Twork, st_d, st);
+            }
+        }
+    };
     for (const LevelPlan& L : plan) {
+        flush_trtri(false);
+        lvl++;
         // Sharded instance: before a level with children on other ranks those children's update
         // blocks must be complete; AFTER such a level nobody may go on before every rank has
         // finished reading them, because the update-block arena reuses their memory from the
@@ -387,7 +408,7 @@ void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, c
         if (!L.wide_count) continue;
         if (mode == 0) {
             // Cholesky: panels in shared memory / blocked on the FP64 tensor pipe (kernels_dense.cu)
-            launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, outer_block, side, timer, st);
+            launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, outer_block, cb_small_k, side, timer, st);
             continue;
         }
         // LDL' fallback: scalar blocked path over every front that does not fit in shared memory
@@ -411,6 +432,8 @@ void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, c
         }
     }
     if (timer && timer->phases) timer->put_mark(3, st);
+    flush_trtri(true);
+    if (aux_busy) cudaStreamWaitEvent(st, side->aux_done, 0);
 }
 
 void launch_ldlt_inertia(const DevSym& S, const double* Lval, const int64_t* dpos, int n,

@@ -48,7 +48,7 @@ struct Bundle {
     std::vector<int> sched;
     std::vector<int64_t> Xoff;   // per supernode: offset of inv(L11) in Xinv (big supernodes) or -1
     int64_t x_total = 0;
-    TrtriPlan trtri;
+    std::vector<TrtriPlan> trtri;   // batches of pivot-block inverses, ascending after_level
     int n_tiny = 0, n_small = 0, n_big = 0;
     // one instance sharded over `world` GPUs: this bundle holds the schedule of `rank`
     int rank = 0, world = 1;
@@ -150,29 +150,64 @@ static void build_plan(Bundle& B) {
         L.solo_count = L.count[FC_T32] + L.count[FC_S64] + L.count[FC_S104] + L.count[FC_S152];
         L.wide_begin = L.begin[FC_MID];
         L.wide_count = L.all_count - L.solo_count;
+        // tile lists of the update-block kernel: big fronts first (descending pivot-column count:
+        // the long tiles start first), then the medium ones
+        for (int v = 0; v < 2; v++) {
+            if (B.sched.size() & 1) B.sched.push_back(0);          // int2 alignment
+            L.cbt_begin[v] = (int)B.sched.size();
+            for (int fc = FC_BIG; fc >= FC_MID; fc--)
+                for (int q = 0; q < L.count[fc]; q++) {
+                    const int pos = L.begin[fc] + q - L.wide_begin;
+                    const int s = B.sched[L.begin[fc] + q];
+                    const int c = cols(s), N = rows(s);
+                    if (N - c <= 0) continue;
+                    const long long nt = cb_tiles(v + 1, N, c & ~1);
+                    for (long long t = 0; t < nt; t++) { B.sched.push_back(pos); B.sched.push_back((int)t); }
+                }
+            L.cbt_count[v] = ((int)B.sched.size() - L.cbt_begin[v]) / 2;
+        }
         B.n_tiny += L.count[FC_T32];
         B.n_small += L.solo_count - L.count[FC_T32];
         B.n_big += L.wide_count;
     }
     // pivot-block inverses: every big supernode with more than one WB block takes part in the
-    // recursive merge; they are batched over the whole tree (independent of the levels)
-    TrtriPlan& T = B.trtri;
-    T = TrtriPlan();
-    std::vector<int> multi;
-    for (int s : all_big) if (cols(s) > WB) multi.push_back(s);
-    std::stable_sort(multi.begin(), multi.end(), [&](int a, int b) { return cols(a) > cols(b); });
-    T.count = (int)multi.size();
-    T.list_begin = (int)B.sched.size();
-    B.sched.insert(B.sched.end(), multi.begin(), multi.end());
-    if (!multi.empty()) {
+    // recursive merge.  Four batches -- everything below the top three levels, then each of the top
+    // three levels -- so that a batch can run on a low-priority stream while the levels above it are
+    // being factorised (only the root's batch has nothing left to hide behind).
+    B.trtri.clear();
+    const int nl = S.nlevels;
+    for (int g = 0; g < 4; g++) {
+        const int lo = g == 0 ? 0 : nl - 4 + g, hi = nl - 3 + g;      // levels [lo, hi)
+        if (hi <= 0 || lo < 0) continue;
+        TrtriPlan T;
+        T.after_level = hi - 1;
+        std::vector<int> multi;
+        for (int s : all_big) if (cols(s) > WB && S.level[s] >= lo && S.level[s] < hi) multi.push_back(s);
+        if (multi.empty()) continue;
+        std::stable_sort(multi.begin(), multi.end(), [&](int a, int b) { return cols(a) > cols(b); });
+        T.count = (int)multi.size();
+        T.list_begin = (int)B.sched.size();
+        B.sched.insert(B.sched.end(), multi.begin(), multi.end());
         const int maxc = cols(multi[0]);
         for (int l = 0; (WB << l) < std::min(maxc, XB); l++) {
-            const int Sz = WB << l;
-            int cnt = 0;
-            for (int s : multi) if (cols(s) > Sz) cnt++;
-            T.level_count.push_back(cnt);
-            T.level_pairs.push_back((maxc - Sz - 1) / (2 * Sz) + 1);
+            const int Sz = WB << l, nsub = 1 << l;
+            if (B.sched.size() & 1) B.sched.push_back(0);          // int2 alignment
+            T.items_begin.push_back((int)B.sched.size());
+            for (int q = 0; q < (int)multi.size(); q++) {
+                const int c = cols(multi[q]);
+                for (int pair = 0; (2 * pair + 1) * Sz < c; pair++) {
+                    const int a1 = (2 * pair + 1) * Sz, a2 = std::min(a1 + Sz, c);
+                    const int ni = (a2 - a1 + WB - 1) / WB;
+                    for (int I = 0; I < ni; I++)
+                        for (int J = 0; J < nsub; J++) {
+                            B.sched.push_back(q);
+                            B.sched.push_back(pair * nsub * nsub + I * nsub + J);
+                        }
+                }
+            }
+            T.items_count.push_back(((int)B.sched.size() - T.items_begin.back()) / 2);
         }
+        B.trtri.push_back(T);
     }
 }
 
@@ -189,6 +224,7 @@ struct opb_handle {
     std::vector<int64_t> user_perm;
     int attempts_per_sync = 2;
     int outer_block = OUTER_BLOCK;
+    int cb_small_k = CB_SMALL_K;
     double barrier_timeout_s = 20.0;     // sharded instance: a rank that waits longer reports an error
     std::shared_ptr<Bundle> B;
     bool cached_hit = false;
@@ -328,6 +364,9 @@ int opb_create(opb_handle** out, int device_id, unsigned flags) {
             }
             if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->side.rest, cudaStreamNonBlocking, least);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.rest_done, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->side.aux, cudaStreamNonBlocking, least);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.aux_fork, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.aux_done, cudaEventDisableTiming);
             h->side.deep = true;
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->side.fork, cudaEventDisableTiming);
@@ -363,6 +402,9 @@ int opb_destroy(opb_handle* h) {
             if (h->side.cls_done[i]) cudaEventDestroy(h->side.cls_done[i]);
         }
         if (h->side.rest) { cudaStreamSynchronize(h->side.rest); cudaStreamDestroy(h->side.rest); }
+        if (h->side.aux) { cudaStreamSynchronize(h->side.aux); cudaStreamDestroy(h->side.aux); }
+        if (h->side.aux_fork) cudaEventDestroy(h->side.aux_fork);
+        if (h->side.aux_done) cudaEventDestroy(h->side.aux_done);
         if (h->side.rest_done) cudaEventDestroy(h->side.rest_done);
         if (h->side.fork) cudaEventDestroy(h->side.fork);
         if (h->side.join) cudaEventDestroy(h->side.join);
@@ -398,6 +440,7 @@ int opb_set_option(opb_handle* h, const char* key, double v) {
     else if (k == "relax_small") h->opt.relax_small = v;
     else if (k == "attempts_per_sync") h->attempts_per_sync = std::max(1, (int)v);
     else if (k == "outer_block") { h->outer_block = std::max(WB, ((int)v / WB) * WB); h->drop_graphs(); }
+    else if (k == "cb_small_k") { h->cb_small_k = (int)v; h->drop_graphs(); }
     else if (k == "barrier_timeout_s") { h->barrier_timeout_s = v; h->sctx.timeout_clocks = (long long)(v * 2.0e9); h->drop_graphs(); }
     else if (k == "lookahead") { h->lookahead = v != 0; h->side.deep = v >= 2; h->drop_graphs(); }
     else if (k == "chain_priority") { h->side.chain_on_side = v != 0; h->drop_graphs(); }
@@ -699,9 +742,8 @@ static void enqueue_attempt_raw(opb_handle* h, KernelTimer* timer = nullptr, uns
     launch_scatter_fronts(h->Mval.p, B.d_amap.p, B.d_dpos.p, h->sdiag.p, h->Lval.p, B.S.nnzL,
                           B.Mp[B.S.n], B.S.n, h->d_state, 1, st);
     launch_factor_levels(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->Xinv.p, h->d_state, h->mode,
-                         h->outer_block, h->shard_ctx(), (h->lookahead && (!timer || timer->phases)) ? &h->side : nullptr, timer, st);
-    if (h->mode == OPB_MODE_CHOLESKY && B.trtri.count)
-        launch_trtri(h->dev, B.trtri, B.d_sched.p, h->Lval.p, h->Xinv.p, h->Twork.p, h->d_state, st);
+                         h->outer_block, h->cb_small_k, h->shard_ctx(), (h->lookahead && (!timer || timer->phases)) ? &h->side : nullptr, timer,
+                         h->mode == OPB_MODE_CHOLESKY ? &B.trtri : nullptr, h->Twork.p, st);
     // sharded: every rank learns about a failed pivot anywhere before the delta rule is applied
     if (h->sharded()) launch_shard_barrier(h->sctx, st);
     if (loop_handle) launch_ctl_end_loop(h->d_state, loop_handle, st);
@@ -1246,9 +1288,10 @@ int opb_get_info(opb_handle* h, const char* key, double* out) {
     else if (k == "n_big") *out = B.n_big;
     else if (k == "symbolic_cached") *out = h->cached_hit ? 1 : 0;
     else if (k == "loop_graph_active") { *out = h->g_loop.exec ? 1 : 0; h->err = "loop graph: " + h->loop_diag; }
+    else if (k == "occ_small_tiles") *out = g_occ_small_tiles;
     else if (k == "sum_rows") *out = (double)S.rowidx.size();
     else if (k == "x_total") *out = (double)B.x_total;
-    else if (k == "n_trtri") *out = B.trtri.count;
+    else if (k == "n_trtri") { int c = 0; for (const TrtriPlan& T : B.trtri) c += T.count; *out = c; }
     else if (k == "shard_rank") *out = B.rank;
     else if (k == "shard_world") *out = B.world;
     else if (k == "shard_load") *out = B.world > 1 ? B.shard.load[B.rank] : S.flops;

@@ -130,7 +130,18 @@ constexpr int MIDL_PANEL = 26000;     // doubles
 constexpr int NB = 32;                // block-column width of the LDL' big-front path
 constexpr int WB = 128;               // block width of the Cholesky big-front path (DMMA)
 constexpr int OUTER_BLOCK = 4096;     // default outer block of the panel update (WB times a power of two)
+constexpr int CB_SMALL_K = 1 << 30;      // levels whose fronts have at most this many pivot columns form their update blocks in 64-row tiles
 constexpr int XB = 2048;              // pivot blocks are inverted in diagonal blocks of this many columns
+
+// Tiles of the update-block kernel (BM rows x 128 columns over the lower triangle of the r x r block,
+// origin at front position ce = c & ~1).  WM = 2 (BM = 128): tile (I, J), I >= J, linear index
+// I(I+1)/2 + J.  WM = 1 (BM = 64): row tile I meets column tile J when I >= 2J; the row tiles 2a and
+// 2a+1 hold a+1 tiles each, a(a+1) tiles precede them.
+__host__ __device__ inline long long cb_tiles(int WM, int N, int ce) {
+    if (WM == 2) { const long long nt = (N - ce + 127) / 128; return nt * (nt + 1) / 2; }
+    const long long n64 = (N - ce + 63) / 64, a = n64 >> 1;
+    return a * (a + 1) + ((n64 & 1) ? a + 1 : 0);
+}
 
 // Per-level schedule built on the host from Symbolic.
 struct LevelPlan {
@@ -140,6 +151,9 @@ struct LevelPlan {
     int solo_count = 0;                        // classes T32 .. S152 (a prefix of the level)
     int wide_begin = 0, wide_count = 0;        // classes MID .. BIG (the rest)
     int wide_maxN = 0, wide_maxC = 0, wide_maxR = 0;
+    // exact tile lists of the update-block kernel, as (position in the wide list, tile) pairs inside
+    // d_sched: [0] 64-row tiles, [1] 128-row tiles; biggest pivot blocks first
+    int cbt_begin[2] = {0, 0}, cbt_count[2] = {0, 0};
     // big fronts are sorted by pivot-column count (descending); outer step t of the blocked
     // factorisation touches the first step_count[t] of them
     std::vector<int> step_count, step_maxN;
@@ -188,6 +202,9 @@ struct SideStream {
     bool deep = false;
     cudaStream_t cls[LA_CLASSES] = {nullptr}, rest = nullptr;
     cudaEvent_t cls_done[LA_CLASSES] = {nullptr}, rest_done = nullptr;
+    // pivot-block inverses of finished levels run here (lowest priority) while the levels above are factorised
+    cudaStream_t aux = nullptr;
+    cudaEvent_t aux_fork = nullptr, aux_done = nullptr;
 };
 
 // Optional per-kernel timing of one factorisation attempt (opb_profile_factor): CUDA events
@@ -221,25 +238,28 @@ struct KernelTimer {
 };
 
 // ---- kernels_factor.cu
+struct TrtriPlan;
 cudaError_t factor_configure();
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
-                          int outer_block, const ShardCtx* shard, const SideStream* side, KernelTimer* timer,
-                          cudaStream_t st);
+                          int outer_block, int cb_small_k, const ShardCtx* shard, const SideStream* side,
+                          KernelTimer* timer, const std::vector<TrtriPlan>* trtri, double* Twork, cudaStream_t st);
 
 // ---- kernels_dense.cu  (Cholesky of big fronts on the FP64 tensor pipe, pivot-block inverses,
 //                         multi-CTA triangular solves for big supernodes)
 struct TrtriPlan {
+    int after_level = 0;              // the batch may start once this elimination-tree level is factorised
     int count = 0;                    // big supernodes with more than one WB block (sorted by c descending)
     int list_begin = 0;               // position in d_sched
-    std::vector<int> level_count;     // merge level l: number of participating supernodes
-    std::vector<int> level_pairs;     // merge level l: max number of block pairs per supernode
+    // merge level l: exact work list inside d_sched, (position in the list, pair * nsub^2 + I * nsub + J) pairs
+    std::vector<int> items_begin, items_count;
 };
 cudaError_t dense_configure();
+extern int g_occ_small_tiles;
 // medium + big fronts of one level (Cholesky)
 void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
-                            double* CB, double* Xinv, DeltaState* st_d, int outer_block, const SideStream* side,
-                            KernelTimer* timer, cudaStream_t st);
+                            double* CB, double* Xinv, DeltaState* st_d, int outer_block, int cb_small_k,
+                            const SideStream* side, KernelTimer* timer, cudaStream_t st);
 void launch_trtri(const DevSym& S, const TrtriPlan& T, const int* d_sched, const double* Lval,
                   double* Xinv, double* Twork, const DeltaState* st_d, cudaStream_t st);
 void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,

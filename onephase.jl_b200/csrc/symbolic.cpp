@@ -905,7 +905,7 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
         int cnt = 0;
         if (p >= 0) {
             const int pc = S.sfirst[p + 1] - S.sfirst[p], pN = pc + (int)(S.rowptr[p + 1] - S.rowptr[p]);
-            cnt = (pN - (pc & ~1) + CB_TILE - 1) / CB_TILE + 1;
+            cnt = (pN - (pc & ~1) + CB_TILE - 1) / CB_TILE + 2;     // one spare cut: a 128-column tile ends at an even cut
         }
         S.tcut_ptr[s + 1] = S.tcut_ptr[s] + cnt;
     }

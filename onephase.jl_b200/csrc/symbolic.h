@@ -12,7 +12,7 @@ namespace opb {
 // Leading dimension of a supernode panel with N = c + r rows: padded to an even
 // count so that every panel column starts on a 16-byte boundary (TMA bulk copies).
 inline int64_t panel_ld(int64_t N) { return (N + 1) & ~(int64_t)1; }
-constexpr int CB_TILE = 128;   // tile edge of the update-block kernel (kernels_dense.cu: BM = BN)
+constexpr int CB_TILE = 64;    // granularity of the tile-cut table (kernels_dense.cu: tiles of 64 / 128 rows, 128 columns)
 
 struct SymOptions {
     int nd_leaf = 96;          // nested dissection stops at parts of this size
@@ -67,7 +67,7 @@ struct Symbolic {
     std::vector<int> gch;
     // tile cuts of every update block inside its parent's update block: supernode s (rows rel[.])
     // crosses the parent's CB_TILE-row tile boundary k (front position (c_p & ~1) + k * CB_TILE) at
-    // row position tcut[tcut_ptr[s] + k], k = 0 .. tiles(parent); lets the update-block kernel find
+    // row position tcut[tcut_ptr[s] + k], k = 0 .. tiles(parent) + 1; lets the update-block kernel find
     // the child entries of a tile with four loads instead of four binary searches
     std::vector<int> tcut_ptr, tcut;
     std::vector<int64_t> amap;           // per M_L entry: destination offset in L storage

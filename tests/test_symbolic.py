@@ -223,7 +223,7 @@ def test_update_block_storage_reuses_memory_without_overlap(pkg, gen, kw):
 
 
 def test_tile_cut_table(pkg):
-    """tcut (symbolic.cpp): row position at which every update block crosses the 128-row tile
+    """tcut (symbolic.cpp): row position at which every update block crosses the 64-row tile
     boundaries of its parent's update block == a binary search in `rel` (what front_cb_kernel did
     per tile before the table existed)."""
     for prob in [problems.sparse_qp(600, 300, win=5, seed=2), problems.pde_control(9, seed=4), problems.elec(60, seed=3)]:
@@ -239,8 +239,8 @@ def test_tile_cut_table(pkg):
                 continue
             c = sfirst[p + 1] - sfirst[p]; N = c + rowptr[p + 1] - rowptr[p]
             ce = c & ~1
-            nt = (N - ce + 127) // 128
-            assert tp[s + 1] - tp[s] == nt + 1
-            want = np.searchsorted(rel[rowptr[s]:rowptr[s + 1]], ce + 128 * np.arange(nt + 1), side="left")
+            nt = (N - ce + 63) // 64
+            assert tp[s + 1] - tp[s] == nt + 2
+            want = np.searchsorted(rel[rowptr[s]:rowptr[s + 1]], ce + 64 * np.arange(nt + 2), side="left")
             assert np.array_equal(tc[tp[s]:tp[s + 1]], want)
         h.close()

@@ -20,10 +20,10 @@ def main():
     pars = pkg.Class_parameters()
     it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=0.0)
     k = pkg.pick_KKT_solver(pars)
+    k.initialize(it)
     for o in opts:
         key, val = o.split("=")
         k._h.set_option(key, float(val))
-    k.initialize(it)
     k.form_system(it)
     h = k._h
     sf = np.array(h.symbolic("sfirst")); rp = np.array(h.symbolic("rowptr")); lev = np.array(h.symbolic("level"))
@@ -31,6 +31,7 @@ def main():
     for rep in range(2):
         P = h.profile_levels(0.0)
     T = P["levels"]
+    print("resident CTAs per SM of the 64-row-tile kernels:", h.info("occ_small_tiles"))
     print("workload %s  total %.2f ms  fill %.2f  trtri %.2f   (columns: ms before the big panels | big panels | update blocks)"
           % (wl, P["total_ms"], P["fill_ms"], P["trtri_ms"]))
     print("%3s %6s %7s %7s %10s %10s %8s %8s %8s %7s %7s" % ("lvl", "fronts", "max c", "max N", "panel Gf", "cb Gf", "pre", "panel", "cb", "pan TF", "cb TF"))
