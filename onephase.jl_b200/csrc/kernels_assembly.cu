@@ -12,16 +12,20 @@ namespace opb {
 
 namespace {
 
-__global__ void sigma_kernel(const double* __restrict__ y, const double* __restrict__ s,
-                             double* __restrict__ sigma, int m) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < m) sigma[k] = y[k] / s[k];
-}
-
-__global__ void scale_T_kernel(const double* __restrict__ Jv, const int* __restrict__ Jrow,
-                               const double* __restrict__ sigma, double* __restrict__ T, int64_t nnzJ) {
-    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < nnzJ) T[p] = __dmul_rn(Jv[p], sigma[Jrow[p]]);
+// One pass over J's entries: sigma = y ./ s, T = J .* sigma[row] (rounded separately: eval.jl:85-87), the
+// CSR copy of J's values for the J*x products, and the reset of the diagonal-minimum scratch
+__global__ void prep_kernel(const double* __restrict__ Jv, const int* __restrict__ Jrow, const int* __restrict__ Rpos,
+                            const double* __restrict__ y, const double* __restrict__ s, double* __restrict__ sigma,
+                            double* __restrict__ T, double* __restrict__ Rval, int64_t nnzJ, int m,
+                            unsigned long long* scratch) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) { scratch[0] = 0xffffffffffffffffull; scratch[1] = 0ull; scratch[2] = 0ull; }
+    if (p < m) sigma[p] = y[p] / s[p];
+    if (p < nnzJ) {
+        const int r = Jrow[p];
+        T[p] = __dmul_rn(Jv[p], y[r] / s[r]);
+        Rval[p] = Jv[Rpos[p]];
+    }
 }
 
 __global__ void assemble_M_kernel(const int64_t* __restrict__ pair_ptr, const int* __restrict__ pairA,
@@ -53,14 +57,10 @@ __device__ __forceinline__ double sortable_dbl(unsigned long long b) {
     return __longlong_as_double((long long)b);
 }
 
-// scratch[0] = sortable min bits, scratch[1] = NaN flag
-__global__ void diag_reset_kernel(unsigned long long* scratch) {
-    scratch[0] = 0xffffffffffffffffull;
-    scratch[1] = 0ull;
-}
-
+// schur_diag = diag(Q) and its minimum (diag_min, kkt_system_solver.jl:291-294; NaN wins); the last CTA
+// to finish publishes the result (scratch[2] = ticket counter, reset by prep_kernel)
 __global__ void diag_extract_kernel(const int64_t* __restrict__ Mp, const double* __restrict__ Mval,
-                                    double* __restrict__ sdiag, unsigned long long* scratch, int n) {
+                                    double* __restrict__ sdiag, unsigned long long* scratch, DeltaState* st, int n) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long key = 0xffffffffffffffffull;
     unsigned nanf = 0;
@@ -79,18 +79,17 @@ __global__ void diag_extract_kernel(const int64_t* __restrict__ Mp, const double
         if (key != 0xffffffffffffffffull) atomicMin(&scratch[0], key);
         if (nanf) atomicOr(&scratch[1], 1ull);
     }
-}
-
-__global__ void diag_finish_kernel(const unsigned long long* scratch, DeltaState* st) {
-    double v = sortable_dbl(scratch[0]);
-    if (scratch[1]) v = __longlong_as_double(0x7ff8000000000000ll);
-    st->diag_min = v;
-}
-
-__global__ void gather_kernel(const double* __restrict__ src, const int* __restrict__ pos,
-                              double* __restrict__ dst, int64_t nnz) {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nnz) dst[q] = src[pos[q]];
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&scratch[2], 1ull) == (unsigned long long)(gridDim.x - 1);
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        double v = sortable_dbl(atomicMin(&scratch[0], 0xffffffffffffffffull));
+        if (atomicOr(&scratch[1], 0ull)) v = __longlong_as_double(0x7ff8000000000000ll);
+        st->diag_min = v;
+    }
 }
 
 __global__ void zero_kernel(double* __restrict__ p, int64_t n, const DeltaState* st) {
@@ -196,11 +195,16 @@ void launch_diag_JtDJ(const int64_t* Jp, const int64_t* Ji, const double* Jx, co
     count_launch();
 }
 
-void launch_sigma_T(const double* Jv, const int* Jrow, const double* y, const double* s,
-                    double* sigma, double* T, int64_t nnzJ, int m, cudaStream_t st) {
-    if (m > 0) sigma_kernel<<<nblk(m, 256), 256, 0, st>>>(y, s, sigma, m);
-    count_launch();
-    if (nnzJ > 0) scale_T_kernel<<<nblk(nnzJ, 256), 256, 0, st>>>(Jv, Jrow, sigma, T, nnzJ);
+static unsigned long long* diag_scratch(DeltaState* st_d) {
+    // scratch lives right behind the DeltaState (allocated with 128 spare bytes): [0] sortable minimum
+    // bits, [1] NaN flag, [2] ticket counter
+    return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(st_d) + ((sizeof(DeltaState) + 15) / 16) * 16);
+}
+
+void launch_prep(const double* Jv, const int* Jrow, const int* Rpos, const double* y, const double* s,
+                 double* sigma, double* T, double* Rval, int64_t nnzJ, int m, DeltaState* st_d, cudaStream_t st) {
+    const int64_t cnt = nnzJ > m ? nnzJ : m;
+    prep_kernel<<<nblk(cnt > 0 ? cnt : 1, 256), 256, 0, st>>>(Jv, Jrow, Rpos, y, s, sigma, T, Rval, nnzJ, m, diag_scratch(st_d));
     count_launch();
 }
 
@@ -211,24 +215,10 @@ void launch_assemble_M(const int64_t* pair_ptr, const int* pairA, const int* pai
     count_launch();
 }
 
-static unsigned long long* g_unused = nullptr;
-
 void launch_diag_extract(const int64_t* Mp, const double* Mval, double* sdiag, DeltaState* st_d,
                          int n, cudaStream_t st) {
-    // scratch lives right behind the DeltaState (allocated with 64 spare bytes)
-    unsigned long long* scratch = reinterpret_cast<unsigned long long*>(
-        reinterpret_cast<char*>(st_d) + ((sizeof(DeltaState) + 15) / 16) * 16);
-    (void)g_unused;
-    diag_reset_kernel<<<1, 1, 0, st>>>(scratch);
-    count_launch();
-    diag_extract_kernel<<<nblk(n, 256), 256, 0, st>>>(Mp, Mval, sdiag, scratch, n);
-    count_launch();
-    diag_finish_kernel<<<1, 1, 0, st>>>(scratch, st_d);
-    count_launch();
-}
-
-void launch_csr_gather(const double* src, const int* pos, double* dst, int64_t nnz, cudaStream_t st) {
-    if (nnz > 0) gather_kernel<<<nblk(nnz, 256), 256, 0, st>>>(src, pos, dst, nnz);
+    unsigned long long* scratch = diag_scratch(st_d);
+    diag_extract_kernel<<<nblk(n > 0 ? n : 1, 256), 256, 0, st>>>(Mp, Mval, sdiag, scratch, st_d, n);
     count_launch();
 }
 
@@ -266,13 +256,9 @@ void launch_ctl_single(DeltaState* st_d, double delta, int mode, cudaStream_t st
 cudaError_t preload_assembly() {
     cudaFuncAttributes a;
     cudaError_t e;
-    e = cudaFuncGetAttributes(&a, sigma_kernel); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, scale_T_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, prep_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, assemble_M_kernel); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, diag_reset_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, diag_extract_kernel); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, diag_finish_kernel); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, gather_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, zero_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, scatter_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, ctl_begin_kernel); if (e != cudaSuccess) return e;

@@ -725,11 +725,10 @@ static int need_device(opb_handle* h) {
 static int stage_form(opb_handle* h) {
     Bundle& B = *h->B;
     cudaStream_t st = h->stream;
-    launch_sigma_T(h->Jv.p, B.d_Jrow.p, h->y.p, h->s.p, h->sigma.p, h->T.p, B.P.nnzJ, B.P.m, st);
+    launch_prep(h->Jv.p, B.d_Jrow.p, B.d_Rpos.p, h->y.p, h->s.p, h->sigma.p, h->T.p, h->Rval.p, B.P.nnzJ, B.P.m, h->d_state, st);
     launch_assemble_M(B.d_pair_ptr.p, B.d_pairA.p, B.d_pairB.p, B.d_hmap.p, h->T.p, h->Jv.p, h->Hv.p,
                       h->Mval.p, B.Mp[B.S.n], st);
     launch_diag_extract(B.d_Mp.p, h->Mval.p, h->sdiag.p, h->d_state, B.S.n, st);
-    launch_csr_gather(h->Jv.p, B.d_Rpos.p, h->Rval.p, B.P.nnzJ, st);
     CK(cudaGetLastError());
     h->ready = opb_handle::SYSTEM_FORMED;
     return OPB_OK;

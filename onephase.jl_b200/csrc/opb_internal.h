@@ -164,14 +164,13 @@ struct LevelPlan {
 };
 
 // ---- kernels_assembly.cu
-void launch_sigma_T(const double* Jv, const int* Jrow, const double* y, const double* s,
-                    double* sigma, double* T, int64_t nnzJ, int m, cudaStream_t st);
+void launch_prep(const double* Jv, const int* Jrow, const int* Rpos, const double* y, const double* s,
+                 double* sigma, double* T, double* Rval, int64_t nnzJ, int m, DeltaState* st_d, cudaStream_t st);
 void launch_assemble_M(const int64_t* pair_ptr, const int* pairA, const int* pairB, const int* hmap,
                        const double* T, const double* Jv, const double* Hv, double* Mval,
                        int64_t nnzM, cudaStream_t st);
 void launch_diag_extract(const int64_t* Mp, const double* Mval, double* sdiag, DeltaState* st_d,
                          int n, cudaStream_t st);
-void launch_csr_gather(const double* src, const int* pos, double* dst, int64_t nnz, cudaStream_t st);
 void launch_scatter_fronts(const double* Mval, const int64_t* amap, const int64_t* dpos,
                            const double* sdiag, double* Lval, int64_t nnzL, int64_t nnzM, int n,
                            const DeltaState* st_d, int use_sdiag, cudaStream_t st);
