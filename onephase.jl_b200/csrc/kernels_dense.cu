@@ -142,14 +142,16 @@ __device__ __forceinline__ void gemm_issue(GemmSmemT<WM>& sm, int stage, int kb,
 }
 
 // one k-step (4 columns) of the warp tile: 12 fragment loads, 32 DMMAs
-template <int WM, bool B_KC, bool TAIL>
+// SCALE (LDL' mode): the A fragment of column k is multiplied by d_k on its way into the DMMAs, so that
+// the product is (L D) L' without a scaled copy of the panel (8 extra multiplies per 32 DMMAs)
+template <int WM, bool B_KC, bool TAIL, bool SCALE = false>
 __device__ __forceinline__ void gemm_kstep(const double* As, const double* Bs, int kk, bool kvalid,
-                                           double (&acc)[8][4][2]) {
+                                           double (&acc)[8][4][2], double dkv = 1.0) {
     constexpr int LDM = TileCfg<WM>::LDM;
     double av[8], bv[4];
 #pragma unroll
     for (int mt = 0; mt < 8; mt++) {
-        const double v = As[kk * LDM + mt * 8];
+        const double v = SCALE ? As[kk * LDM + mt * 8] * dkv : As[kk * LDM + mt * 8];
         av[mt] = (!TAIL || kvalid) ? v : 0.0;
     }
 #pragma unroll
@@ -172,10 +174,11 @@ struct NoHook { __device__ __forceinline__ void operator()() const {} };
 // L2 prefetch of the children's update-block entries the epilogue is about to merge)
 constexpr int HOOK_LEAD = 8;
 
-template <int WM, bool B_KC, class Hook = NoHook>
+template <int WM, bool B_KC, class Hook = NoHook, bool SCALE = false>
 __device__ __forceinline__ void gemm_mainloop(GemmSmemT<WM>& sm, const double* Ag, int lda, int mrows,
                                               const double* Bg, int ldb, int nrows, int K,
-                                              double (&acc)[8][4][2], Hook hook = Hook()) {
+                                              double (&acc)[8][4][2], Hook hook = Hook(),
+                                              const double* __restrict__ dk = nullptr) {
     constexpr int CW = TileCfg<WM>::CWARPS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -209,11 +212,17 @@ __device__ __forceinline__ void gemm_mainloop(GemmSmemT<WM>& sm, const double* A
             const double* Bs = sm.B[stage] + boff;
             const int nk = K - kb * BK;
             if (nk >= BK) {
+                double dv[BK / 4];
 #pragma unroll
-                for (int ks = 0; ks < BK / 4; ks++) gemm_kstep<WM, B_KC, false>(As, Bs, ks * 4 + q, true, acc);
+                for (int ks = 0; ks < BK / 4; ks++) dv[ks] = SCALE ? dk[kb * BK + ks * 4 + q] : 1.0;
+#pragma unroll
+                for (int ks = 0; ks < BK / 4; ks++) gemm_kstep<WM, B_KC, false, SCALE>(As, Bs, ks * 4 + q, true, acc, dv[ks]);
             } else {
 #pragma unroll 1
-                for (int ks = 0; ks * 4 < nk; ks++) gemm_kstep<WM, B_KC, true>(As, Bs, ks * 4 + q, ks * 4 + q < nk, acc);
+                for (int ks = 0; ks * 4 < nk; ks++) {
+                    const bool kv = ks * 4 + q < nk;
+                    gemm_kstep<WM, B_KC, true, SCALE>(As, Bs, ks * 4 + q, kv, acc, (SCALE && kv) ? dk[kb * BK + ks * 4 + q] : 1.0);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[stage]);
@@ -273,7 +282,10 @@ constexpr int INVBUF = 32 * INVLD;           // doubles
 // and finalises the matching eight rows of X (lane = column); then the whole CTA applies the
 // rank-8 update to the trailing columns of the block and to the later rows of X.  Two block
 // barriers per eight columns; the register code is 8 x 8 unrolled, i.e. small.
+// LDLT = true: unit lower L with D on the diagonal (julia.jl:47-90: ldlt without pivoting; a zero or NaN
+// pivot fails the attempt), X = inverse of the unit lower factor.
 constexpr int PW = 8;
+template <bool LDLT = false>
 __device__ bool cta_potrf32_inv(double* P, int ld, int j0, int w, double* invbuf, int* s_fail) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int i = tid & 31, q = tid >> 5, nq = nthr >> 5;
@@ -295,14 +307,27 @@ __device__ bool cta_potrf32_inv(double* P, int ld, int j0, int w, double* invbuf
             for (int t = 0; t < PW; t++) {
                 const int j = jp + t;
                 const double d = __shfl_sync(FULL, p[t], j & 31);
-                if (!(d > 0.0)) ok = false;          // pivot <= 0 or NaN (julia.jl:39-41)
-                rs[t] = rsqrt(d);                    // = 1 / L[j,j]
-                const double lt = (i >= j) ? p[t] * rs[t] : 0.0;     // lane j: d * rsqrt(d) = sqrt(d)
-                p[t] = lt;
+                if (LDLT) {
+                    if (j < w && (d == 0.0 || d != d)) ok = false;     // zero or NaN pivot
+                    rs[t] = 1.0;                                      // unit diagonal
+                    // lane j keeps d (stored on the diagonal), the lanes below it hold L[i,j] = a / d
+                    const double lt = (i > j) ? p[t] / d : ((i == j) ? d : 0.0);
+                    p[t] = lt;
 #pragma unroll
-                for (int u = t + 1; u < PW; u++) {
-                    const double lu = __shfl_sync(FULL, lt, (jp + u) & 31);
-                    p[u] -= lt * lu;                 // rows above jp+u hold junk that is never stored
+                    for (int u = t + 1; u < PW; u++) {
+                        const double lu = __shfl_sync(FULL, lt, (jp + u) & 31);      // L[jp+u, j]
+                        if (i > j) p[u] -= lt * (d * lu);
+                    }
+                } else {
+                    if (!(d > 0.0)) ok = false;          // pivot <= 0 or NaN (julia.jl:39-41)
+                    rs[t] = rsqrt(d);                    // = 1 / L[j,j]
+                    const double lt = (i >= j) ? p[t] * rs[t] : 0.0;     // lane j: d * rsqrt(d) = sqrt(d)
+                    p[t] = lt;
+#pragma unroll
+                    for (int u = t + 1; u < PW; u++) {
+                        const double lu = __shfl_sync(FULL, lt, (jp + u) & 31);
+                        p[u] -= lt * lu;                 // rows above jp+u hold junk that is never stored
+                    }
                 }
             }
             if (!ok) { if (i == 0) *s_fail = 1; }
@@ -338,11 +363,19 @@ __device__ bool cta_potrf32_inv(double* P, int ld, int j0, int w, double* invbuf
             double li[PW];
 #pragma unroll
             for (int t = 0; t < PW; t++) li[t] = B[i + (size_t)(jp + t) * ld];
+            if (LDLT) {
+#pragma unroll
+                for (int t = 0; t < PW; t++) li[t] *= B[(jp + t) + (size_t)(jp + t) * ld];     // (L D)[i, jp+t]
+            }
             for (int k = i1 + q; k <= i; k += nq) {
                 double acc = 0.0;
 #pragma unroll
                 for (int t = 0; t < PW; t++) acc += li[t] * B[k + (size_t)(jp + t) * ld];
                 B[i + (size_t)k * ld] -= acc;
+            }
+            if (LDLT) {
+#pragma unroll
+                for (int t = 0; t < PW; t++) li[t] = B[i + (size_t)(jp + t) * ld];
             }
             for (int jc = q; jc < i1; jc += nq) {
                 double acc = 0.0;
@@ -361,16 +394,19 @@ __device__ __forceinline__ double* xs_block(double* Xs, int I, int J) { return X
 // Warp-level FP64 tensor-core product on shared-memory operands (DMMA m8n8k4), 16 x 16 tile:
 //   acc += A[m0.., 0..K) * B^T, A element (m,k) at A[m + k*lda]; B element (n,k) at
 //   B[n + k*ldb] (B_KC = false) or B[k + n*ldb] (B_KC = true).  Rows >= M / N read as zero.
+// dk != nullptr (LDL'): column k of A is scaled by dk[k * dstride]
 template <bool B_KC>
 __device__ __forceinline__ void warp_tile16(double (&acc)[2][2][2], const double* A, int lda, int m0, int M,
-                                            const double* B, int ldb, int n0, int N, int K) {
+                                            const double* B, int ldb, int n0, int N, int K,
+                                            const double* dk = nullptr, int dstride = 0) {
     const int lane = threadIdx.x & 31, q = lane & 3, g = lane >> 2;
     const bool ma = m0 + g < M, mb = m0 + 8 + g < M, na = n0 + g < N, nb = n0 + 8 + g < N;
     for (int k0 = 0; k0 < K; k0 += 4) {
         const int kk = k0 + q;
         const bool kv = kk < K;
-        const double a0 = (kv && ma) ? A[(m0 + g) + (size_t)kk * lda] : 0.0;
-        const double a1 = (kv && mb) ? A[(m0 + 8 + g) + (size_t)kk * lda] : 0.0;
+        const double sc = (dk && kv) ? dk[(size_t)kk * dstride] : 1.0;
+        const double a0 = (kv && ma) ? A[(m0 + g) + (size_t)kk * lda] * sc : 0.0;
+        const double a1 = (kv && mb) ? A[(m0 + 8 + g) + (size_t)kk * lda] * sc : 0.0;
         double b0, b1;
         if (B_KC) {
             b0 = (kv && na) ? B[kk + (size_t)(n0 + g) * ldb] : 0.0;
@@ -385,10 +421,10 @@ __device__ __forceinline__ void warp_tile16(double (&acc)[2][2][2], const double
         dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
     }
 }
-// MODE 0: C = acc, 1: C += acc, 2: C -= acc, 3: C = -acc
+// MODE 0: C = acc, 1: C += acc, 2: C -= acc, 3: C = -acc; cs != nullptr: column n divided by cs[n * cstride]
 template <int MODE>
 __device__ __forceinline__ void warp_tile16_store(const double (&acc)[2][2][2], double* C, int ldc, int m0, int M,
-                                                  int n0, int N) {
+                                                  int n0, int N, const double* cs = nullptr, int cstride = 0) {
     const int lane = threadIdx.x & 31, q = lane & 3, g = lane >> 2;
 #pragma unroll
     for (int a = 0; a < 2; a++)
@@ -399,7 +435,7 @@ __device__ __forceinline__ void warp_tile16_store(const double (&acc)[2][2][2], 
                 const int m = m0 + 8 * a + g, n = n0 + 8 * b + 2 * q + e;
                 if (m < M && n < N) {
                     double* p = C + m + (size_t)n * ldc;
-                    const double v = acc[a][b][e];
+                    const double v = cs ? acc[a][b][e] / cs[(size_t)n * cstride] : acc[a][b][e];
                     if (MODE == 0) *p = v; else if (MODE == 1) *p += v; else if (MODE == 2) *p -= v; else *p = -v;
                 }
             }
@@ -407,7 +443,7 @@ __device__ __forceinline__ void warp_tile16_store(const double (&acc)[2][2][2], 
 
 // P: shared-memory panel, column-major (ld), n rows, c pivot columns (top c x c = pivot block).
 // invbuf: INVBUF doubles; s_fail: one shared int.
-template <bool PROF = false>
+template <bool PROF = false, bool LDLT = false>
 __device__ bool panel_chol_smem(double* P, int ld, int n, int c, double* invbuf, double* Xs, int* s_fail,
                                 long long* stamps = nullptr) {
     int ns = 0;
@@ -416,7 +452,7 @@ __device__ bool panel_chol_smem(double* P, int ld, int n, int c, double* invbuf,
     for (int j0 = 0; j0 < c; j0 += 32) {
         const int w = min(32, c - j0);
         OPB_STAMP();
-        if (!cta_potrf32_inv(P, ld, j0, w, invbuf, s_fail)) return false;
+        if (!cta_potrf32_inv<LDLT>(P, ld, j0, w, invbuf, s_fail)) return false;
         if (Xs) {
             double* xb = xs_block(Xs, j0 >> 5, j0 >> 5);
             for (int e = tid; e < INVBUF; e += nthr) xb[e] = invbuf[e];
@@ -433,8 +469,10 @@ __device__ bool panel_chol_smem(double* P, int ld, int n, int c, double* invbuf,
                 warp_tile16<false>(acc0, P + (size_t)j0 * ld, ld, m0, n, invbuf, INVLD, 0, w, w);
                 if (w > 16) warp_tile16<false>(acc1, P + (size_t)j0 * ld, ld, m0, n, invbuf, INVLD, 16, w, w);
                 __syncwarp();
-                warp_tile16_store<0>(acc0, P + (size_t)j0 * ld, ld, m0, n, 0, w);
-                if (w > 16) warp_tile16_store<0>(acc1, P + (size_t)j0 * ld, ld, m0, n, 16, w);
+                // LDL': L = A inv(Ld)' D^-1  (the pivots sit on the diagonal of the block)
+                const double* dsc = LDLT ? P + j0 + (size_t)j0 * ld : nullptr;
+                warp_tile16_store<0>(acc0, P + (size_t)j0 * ld, ld, m0, n, 0, w, dsc, ld + 1);
+                if (w > 16) warp_tile16_store<0>(acc1, P + (size_t)j0 * ld, ld, m0, n, 16, w, dsc, ld + 1);
             }
         }
         __syncthreads();
@@ -447,7 +485,8 @@ __device__ bool panel_chol_smem(double* P, int ld, int n, int c, double* invbuf,
                 const int mt = it % ntm, nt = it / ntm;
                 if (mt < nt) continue;
                 double acc[2][2][2] = {};
-                warp_tile16<false>(acc, Ablk, ld, i1 + 16 * mt, n, Ablk, ld, i1 + 16 * nt, c, w);
+                warp_tile16<false>(acc, Ablk, ld, i1 + 16 * mt, n, Ablk, ld, i1 + 16 * nt, c, w,
+                                   LDLT ? P + j0 + (size_t)j0 * ld : nullptr, ld + 1);
                 warp_tile16_store<2>(acc, P, ld, i1 + 16 * mt, n, i1 + 16 * nt, c);
             }
         }
@@ -497,7 +536,7 @@ constexpr int XS_BLOCKS = 10;        // lower 32 x 32 blocks of a 128 x 128 tria
 // diagonal block of outer step t of a big front: Cholesky + inverse
 __global__ void __launch_bounds__(PT)
 chol_diag_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval, double* __restrict__ Xinv,
-                 int t, DeltaState* st) {
+                 int t, int ldlt, DeltaState* st) {
     extern __shared__ double D[];          // LDD * WB + INVBUF + XS_BLOCKS * INVBUF
     __shared__ int s_fail;
     if (stop_requested(st)) return;
@@ -514,7 +553,9 @@ chol_diag_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
         D[i + j * LDD] = (i >= j) ? base[i + (size_t)j * d.ld] : 0.0;
     }
     __syncthreads();
-    if (!panel_chol_smem(D, LDD, b, b, invbuf, Xs, &s_fail)) {
+    const bool ok = ldlt ? panel_chol_smem<false, true>(D, LDD, b, b, invbuf, Xs, &s_fail)
+                         : panel_chol_smem<false, false>(D, LDD, b, b, invbuf, Xs, &s_fail);
+    if (!ok) {
         if (tid == 0) st->fail = 1;
         return;
     }
@@ -526,6 +567,8 @@ chol_diag_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
             X[i + (size_t)j * d.ldx] = xs_block(Xs, i >> 5, j >> 5)[(i & 31) + (j & 31) * INVLD];
         }
     }
+    // LDL': the pivots as a contiguous vector (the tile engine scales its A operand with it)
+    if (ldlt && tid < b) S.dvec[d.first + j0 + tid] = D[tid + tid * LDD];
 }
 
 // medium fronts: the whole N x c panel lives in shared memory.  Children's update blocks are
@@ -533,7 +576,7 @@ chol_diag_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
 // block of the front is produced later by front_cb_kernel.
 __global__ void __launch_bounds__(PT)
 mid_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval,
-                 const double* __restrict__ CB, DeltaState* st) {
+                 const double* __restrict__ CB, int ldlt, DeltaState* st) {
     extern __shared__ double P[];          // N * c + INVBUF
     __shared__ int s_fail;
     if (stop_requested(st)) return;
@@ -561,7 +604,9 @@ mid_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
         }
         __syncthreads();
     }
-    if (!panel_chol_smem(P, N, N, c, invbuf, nullptr, &s_fail)) {
+    const bool ok = ldlt ? panel_chol_smem<false, true>(P, N, N, c, invbuf, nullptr, &s_fail)
+                         : panel_chol_smem<false, false>(P, N, N, c, invbuf, nullptr, &s_fail);
+    if (!ok) {
         if (tid == 0) st->fail = 1;
         return;
     }
@@ -569,6 +614,7 @@ mid_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
         const int i = idx % N, j = idx / N;
         if (i >= j) panel[i + (size_t)j * d.ld] = P[idx];      // the strictly upper part holds scratch
     }
+    if (ldlt) for (int j = tid; j < c; j += PT) S.dvec[d.first + j] = P[j + (size_t)j * N];
 }
 
 // big fronts: add the children's update blocks into the panel columns only.  A CTA owns EAP_RB
@@ -629,7 +675,7 @@ big_extend_add_panel_kernel(DevSym S, const int* __restrict__ list, double* __re
 template <int WM>
 __global__ void __launch_bounds__(TileCfg<WM>::THREADS, 3 - WM)
 chol_trsm_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval,
-                 const double* __restrict__ Xinv, int t, DeltaState* st) {
+                 const double* __restrict__ Xinv, int t, int ldlt, DeltaState* st) {
     constexpr int BM_ = TileCfg<WM>::BM;
     extern __shared__ __align__(16) unsigned char smraw[];
     GemmSmemT<WM>& sm = *reinterpret_cast<GemmSmemT<WM>*>(smraw);
@@ -656,7 +702,8 @@ chol_trsm_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int n = acc_col(nt, e);
-                if (n < b) Lval[d.loff + i + (size_t)(j0 + n) * d.ld] = acc[mt][nt][e];
+                // LDL': L21 = A21 inv(L_kk)' D_kk^-1
+                if (n < b) Lval[d.loff + i + (size_t)(j0 + n) * d.ld] = ldlt ? acc[mt][nt][e] / S.dvec[d.first + j0 + n] : acc[mt][nt][e];
             }
     }
 }
@@ -670,7 +717,7 @@ chol_trsm_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
 // cbeg and k0 are multiples of WB.  (The update block of the front is formed once, at the end,
 // by front_cb_kernel.)
 // WM = 1: 64-row tiles, two CTAs per SM.
-template <int WM>
+template <int WM, bool LDLT = false>
 __global__ void __launch_bounds__(TileCfg<WM>::THREADS, 3 - WM)
 chol_panel_update_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval,
                          int k0, int klen, int cbeg, int cend, DeltaState* st) {
@@ -708,7 +755,9 @@ chol_panel_update_kernel(DevSym S, const int* __restrict__ list, double* __restr
     const double* Ag = Lval + d.loff + ri + (size_t)k0 * d.ld;
     const double* Bg = Lval + d.loff + rj + (size_t)k0 * d.ld;
     double acc[8][4][2];
-    gemm_mainloop<WM, false>(sm, Ag, d.ld, min(BM_, d.N - ri), Bg, d.ld, min(BN, d.N - rj), kl, acc);
+    // LDL': L[i,k] -= sum_p (L[i,p] d_p) L[k,p]
+    gemm_mainloop<WM, false, NoHook, LDLT>(sm, Ag, d.ld, min(BM_, d.N - ri), Bg, d.ld, min(BN, d.N - rj), kl, acc,
+                                           NoHook(), S.dvec + d.first + k0);
     if (!gemm_compute_warp<WM>()) return;
 #pragma unroll
     for (int nt = 0; nt < 4; nt++)
@@ -772,7 +821,7 @@ struct CbPrefetch {
     }
 };
 
-template <int WM>
+template <int WM, bool LDLT = false>
 __global__ void __launch_bounds__(TileCfg<WM>::THREADS, 3 - WM)
 front_cb_kernel(DevSym S, const int* __restrict__ list, const int2* __restrict__ tiles,
                 const double* __restrict__ Lval, double* __restrict__ CB, DeltaState* st) {
@@ -805,8 +854,8 @@ front_cb_kernel(DevSym S, const int* __restrict__ list, const int2* __restrict__
     const double* Ag = Lval + d.loff + ri;
     const double* Bg = Lval + d.loff + rj;
     double acc[8][4][2];
-    gemm_mainloop<WM, false>(sm, Ag, d.ld, min(BM_, d.N - ri), Bg, d.ld, min(BN, d.N - rj), d.c, acc,
-                             CbPrefetch{S, CB, d.s, r64, WM, J});
+    gemm_mainloop<WM, false, CbPrefetch, LDLT>(sm, Ag, d.ld, min(BM_, d.N - ri), Bg, d.ld, min(BN, d.N - rj), d.c, acc,
+                                               CbPrefetch{S, CB, d.s, r64, WM, J}, S.dvec + d.first);
     // the stage buffers are free now: reuse them as the BM_ x 128 tile (ld BM_ + 1)
     double* T = reinterpret_cast<double*>(smraw);
     static_assert((size_t)TLD_ * BN * sizeof(double) <= sizeof(GemmSmemT<WM>) - 2 * STAGES * sizeof(unsigned long long),
@@ -1064,13 +1113,18 @@ wide_fwd_upd_kernel(DevSym S, const int* __restrict__ list, const double* __rest
 }
 
 __global__ void __launch_bounds__(WT)
-wide_bwd_gather_kernel(DevSym S, const int* __restrict__ list, const double* __restrict__ x,
-                       double* __restrict__ u) {
+wide_bwd_gather_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ x,
+                       double* __restrict__ u, int ldlt) {
     const int s = list[blockIdx.y];
     const int64_t rp = S.rowptr[s];
     const int r = (int)(S.rowptr[s + 1] - rp);
     const int t = blockIdx.x * WT + threadIdx.x;
     if (t < r) u[rp + t] = x[S.rowidx[rp + t]];
+    // LDL': x = L^-T D^-1 y -- the pivots are applied to the whole pivot block before its backward sweep
+    if (ldlt) {
+        const int first = S.sfirst[s];
+        if (t < S.sfirst[s + 1] - first) x[first + t] /= S.dvec[first + t];
+    }
 }
 
 // xnew[k] = xs[k] - sum_{i >= b1} L[i,k] * f[i]  for the columns k of block blk, where f is the
@@ -1210,20 +1264,24 @@ cudaError_t dense_configure() {
         return cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     };
     e = gemm_attr((const void*)chol_trsm_kernel<1>, sizeof(GemmSmemT<1>)); if (e != cudaSuccess) return e;
-    e = gemm_attr((const void*)chol_panel_update_kernel<1>, sizeof(GemmSmemT<1>)); if (e != cudaSuccess) return e;
-    e = gemm_attr((const void*)chol_panel_update_kernel<2>, sizeof(GemmSmem)); if (e != cudaSuccess) return e;
-    e = gemm_attr((const void*)front_cb_kernel<1>, sizeof(GemmSmemT<1>)); if (e != cudaSuccess) return e;
-    e = gemm_attr((const void*)front_cb_kernel<2>, sizeof(GemmSmem)); if (e != cudaSuccess) return e;
+    e = gemm_attr((const void*)chol_panel_update_kernel<1, false>, sizeof(GemmSmemT<1>)); if (e != cudaSuccess) return e;
+    e = gemm_attr((const void*)chol_panel_update_kernel<2, false>, sizeof(GemmSmem)); if (e != cudaSuccess) return e;
+    e = gemm_attr((const void*)front_cb_kernel<1, false>, sizeof(GemmSmemT<1>)); if (e != cudaSuccess) return e;
+    e = gemm_attr((const void*)front_cb_kernel<2, false>, sizeof(GemmSmem)); if (e != cudaSuccess) return e;
+    e = gemm_attr((const void*)chol_panel_update_kernel<1, true>, sizeof(GemmSmemT<1>)); if (e != cudaSuccess) return e;
+    e = gemm_attr((const void*)chol_panel_update_kernel<2, true>, sizeof(GemmSmem)); if (e != cudaSuccess) return e;
+    e = gemm_attr((const void*)front_cb_kernel<1, true>, sizeof(GemmSmemT<1>)); if (e != cudaSuccess) return e;
+    e = gemm_attr((const void*)front_cb_kernel<2, true>, sizeof(GemmSmem)); if (e != cudaSuccess) return e;
     e = gemm_attr((const void*)trtri_merge_kernel, sizeof(GemmSmem)); if (e != cudaSuccess) return e;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, front_cb_kernel<1>, TileCfg<1>::THREADS, sizeof(GemmSmemT<1>)) == cudaSuccess)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, front_cb_kernel<1, false>, TileCfg<1>::THREADS, sizeof(GemmSmemT<1>)) == cudaSuccess)
         g_occ_small_tiles = occ;
     else cudaGetLastError();
     return cudaSuccess;
 }
 
 void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
-                            double* CB, double* Xinv, DeltaState* st_d, int outer_block, int cb_small_k,
+                            double* CB, double* Xinv, DeltaState* st_d, int ldlt, int outer_block, int cb_small_k,
                             const SideStream* side, KernelTimer* timer, cudaStream_t st) {
     if (!L.wide_count) return;
     const bool upd_small_tiles = (cb_small_k & 1) == 0;     // odd cb_small_k (tuning): bulk panel updates in 128-row tiles
@@ -1232,7 +1290,7 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
     // medium fronts: panel in shared memory
     for (int fc = FC_MID; fc <= FC_MIDL; fc++) {
         if (!L.count[fc]) continue;
-        mid_panel_kernel<<<L.count[fc], PT, mid_smem(L.maxPanel[fc]), st>>>(S, d_sched + L.begin[fc], Lval, CB, st_d);
+        mid_panel_kernel<<<L.count[fc], PT, mid_smem(L.maxPanel[fc]), st>>>(S, d_sched + L.begin[fc], Lval, CB, ldlt, st_d);
         count_launch();
     }
     // big fronts: blocked right-looking factorisation of the panel columns
@@ -1259,7 +1317,8 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
                 if (tiles <= 0) return false;
                 dim3 gu((unsigned)tiles, cnt2);
                 if (timer) cudaEventRecord(timer->next(1), sx);
-                chol_panel_update_kernel<1><<<gu, TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), sx>>>(S, list, Lval, k0, klen, cbeg, cend, st_d);
+                if (ldlt) chol_panel_update_kernel<1, true><<<gu, TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), sx>>>(S, list, Lval, k0, klen, cbeg, cend, st_d);
+                else chol_panel_update_kernel<1, false><<<gu, TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), sx>>>(S, list, Lval, k0, klen, cbeg, cend, st_d);
                 if (timer) cudaEventRecord(timer->next(1), sx);
                 count_launch();
                 return true;
@@ -1271,7 +1330,8 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
             if (tiles <= 0) return false;
             dim3 gu((unsigned)tiles, cnt2);
             if (timer) cudaEventRecord(timer->next(1), sx);
-            chol_panel_update_kernel<2><<<gu, GEMM_THREADS, sizeof(GemmSmem), sx>>>(S, list, Lval, k0, klen, cbeg, cend, st_d);
+            if (ldlt) chol_panel_update_kernel<2, true><<<gu, GEMM_THREADS, sizeof(GemmSmem), sx>>>(S, list, Lval, k0, klen, cbeg, cend, st_d);
+            else chol_panel_update_kernel<2, false><<<gu, GEMM_THREADS, sizeof(GemmSmem), sx>>>(S, list, Lval, k0, klen, cbeg, cend, st_d);
             if (timer) cudaEventRecord(timer->next(1), sx);
             count_launch();
             return true;
@@ -1293,13 +1353,13 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
                 const int cnt = L.step_count[t];
                 if (cnt <= 0) break;
                 const int maxN = L.step_maxN[t];
-                chol_diag_kernel<<<cnt, PT, diag_smem(), C>>>(S, list, Lval, Xinv, t, st_d);
+                chol_diag_kernel<<<cnt, PT, diag_smem(), C>>>(S, list, Lval, Xinv, t, ldlt, st_d);
                 count_launch();
                 const int rem = maxN - t * WB;
                 if (rem <= 0) continue;
                 const int nrow = (rem + 63) / 64 + 1;
                 dim3 gt(nrow, cnt);
-                chol_trsm_kernel<1><<<gt, TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), C>>>(S, list, Lval, Xinv, t, st_d);
+                chol_trsm_kernel<1><<<gt, TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), C>>>(S, list, Lval, Xinv, t, ldlt, st_d);
                 count_launch();
                 const int tb = t + 1;
                 if (tb >= nsteps || L.step_count[tb] <= 0) continue;       // no panel columns left
@@ -1347,13 +1407,13 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
             const int cnt = L.step_count[t];
             if (cnt <= 0) break;
             const int maxN = L.step_maxN[t];
-            chol_diag_kernel<<<cnt, PT, diag_smem(), C>>>(S, list, Lval, Xinv, t, st_d);
+            chol_diag_kernel<<<cnt, PT, diag_smem(), C>>>(S, list, Lval, Xinv, t, ldlt, st_d);
             count_launch();
             const int rem = maxN - t * WB;     // rows from the start of the block (upper bound)
             if (rem <= 0) continue;
             const int nrow = (rem + 63) / 64 + 1;
             dim3 gt(nrow, cnt);
-            chol_trsm_kernel<1><<<gt, TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), C>>>(S, list, Lval, Xinv, t, st_d);
+            chol_trsm_kernel<1><<<gt, TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), C>>>(S, list, Lval, Xinv, t, ldlt, st_d);
             count_launch();
             // Recursive (binary) schedule of the right-looking updates: with tb blocks finished and
             // 2^j the largest power of two dividing tb, the last 2^j blocks update the next 2^j
@@ -1395,12 +1455,11 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
         if (L.cbt_count[v] > 0) {
             const int2* tiles = reinterpret_cast<const int2*>(d_sched + L.cbt_begin[v]);
             if (timer) cudaEventRecord(timer->next(0), st);
-            if (v == 0)
-                front_cb_kernel<1><<<L.cbt_count[v], TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), st>>>(
-                    S, d_sched + L.wide_begin, tiles, Lval, CB, st_d);
-            else
-                front_cb_kernel<2><<<L.cbt_count[v], GEMM_THREADS, sizeof(GemmSmem), st>>>(
-                    S, d_sched + L.wide_begin, tiles, Lval, CB, st_d);
+            const int* wl = d_sched + L.wide_begin;
+            if (v == 0 && !ldlt) front_cb_kernel<1, false><<<L.cbt_count[v], TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), st>>>(S, wl, tiles, Lval, CB, st_d);
+            else if (v == 0) front_cb_kernel<1, true><<<L.cbt_count[v], TileCfg<1>::THREADS, sizeof(GemmSmemT<1>), st>>>(S, wl, tiles, Lval, CB, st_d);
+            else if (!ldlt) front_cb_kernel<2, false><<<L.cbt_count[v], GEMM_THREADS, sizeof(GemmSmem), st>>>(S, wl, tiles, Lval, CB, st_d);
+            else front_cb_kernel<2, true><<<L.cbt_count[v], GEMM_THREADS, sizeof(GemmSmem), st>>>(S, wl, tiles, Lval, CB, st_d);
             if (timer) cudaEventRecord(timer->next(0), st);
             count_launch();
         }
@@ -1448,12 +1507,12 @@ void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sch
 }
 
 void launch_solve_wide_bwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
-                           const double* Xinv, double* x, double* xnew, double* u, cudaStream_t st) {
+                           const double* Xinv, double* x, double* xnew, double* u, int ldlt, cudaStream_t st) {
     const int cnt = L.count[FC_BIG];
     if (!cnt) return;
     const int* list = d_sched + L.begin[FC_BIG];
     dim3 g0((L.maxN[FC_BIG] + WT) / WT, cnt);
-    wide_bwd_gather_kernel<<<g0, WT, 0, st>>>(S, list, x, u);
+    wide_bwd_gather_kernel<<<g0, WT, 0, st>>>(S, list, x, u, ldlt);
     count_launch();
     const int nblk = (L.maxC[FC_BIG] + XB - 1) / XB;
     for (int blk = nblk - 1; blk >= 0; blk--) {
@@ -1481,11 +1540,15 @@ cudaError_t preload_dense() {
     cudaError_t e;
     e = cudaFuncGetAttributes(&a, big_extend_add_panel_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, chol_diag_kernel); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, chol_panel_update_kernel<1>); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, chol_panel_update_kernel<2>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, chol_panel_update_kernel<1, false>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, chol_panel_update_kernel<2, false>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, chol_panel_update_kernel<1, true>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, chol_panel_update_kernel<2, true>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, chol_trsm_kernel<1>); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, front_cb_kernel<1>); if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a, front_cb_kernel<2>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, front_cb_kernel<1, false>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, front_cb_kernel<2, false>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, front_cb_kernel<1, true>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, front_cb_kernel<2, true>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, mid_panel_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, trtri_merge_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, wide_bwd_gather_kernel); if (e != cudaSuccess) return e;

@@ -299,15 +299,16 @@ cudaError_t solve_configure() { return cudaSuccess; }
 void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                   const double* Lval, const double* Xinv, double* x, double* xnew, double* u, int mode,
                   const ShardCtx* shard, const int* colowner, const SideStream* side, cudaStream_t st) {
-    // Cholesky: BIG supernodes take the multi-CTA path through inv(L11) (kernels_dense.cu), the
-    // other classes (front or panel fits in shared memory) are solved by one CTA each;
-    // LDL': every supernode is solved by one CTA.
+    // BIG supernodes take the multi-CTA path through inv(L11) (kernels_dense.cu), the other classes
+    // (front or panel fits in shared memory) are solved by one CTA each; LDL': L11 is unit lower and
+    // the pivots are applied once per supernode at the start of its backward step.  (With the
+    // scalar LDL' path of option "ldlt_scalar" every supernode is solved by one CTA.)
     // Sharded instance: a rank runs the supernodes it owns.  Forward, a level whose supernodes
     // have children on other ranks waits at a barrier and reads those children's update vectors
     // from the owners' HBM; backward, the owner of a top supernode pushes its part of the solution
     // to every peer before the ranks below continue, and at the end every rank publishes the
     // columns it owns.
-    const bool wide = (mode == 0);
+    const bool wide = (mode == 0) || !g_ldlt_scalar;     // LDL' on the tensor path has inv(L11) too
     // The supernodes of one level are independent of each other: where a level has both
     // CTA-per-supernode classes (latency-bound) and BIG supernodes (bandwidth-bound), the two
     // groups run concurrently on two streams and meet again before the next level.
@@ -333,7 +334,7 @@ void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int
         if (par) { cudaEventRecord(side->fork, st); cudaStreamWaitEvent(s2, side->fork, 0); }
         launch_small_classes(false, S, L, d_sched, Lval, x, u, mode, s2);
         launch_cta_classes(false, S, L, d_sched, solo, Lval, x, u, mode, s2);
-        if (wide) launch_solve_wide_bwd(S, L, d_sched, Lval, Xinv, x, xnew, u, st);
+        if (wide) launch_solve_wide_bwd(S, L, d_sched, Lval, Xinv, x, xnew, u, mode, st);
         if (par) { cudaEventRecord(side->join, s2); cudaStreamWaitEvent(st, side->join, 0); }
         if (shard) {
             launch_push_supernodes(S, d_sched + L.push_begin, L.push_count, L.push_maxc, x, st);

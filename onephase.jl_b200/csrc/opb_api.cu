@@ -232,7 +232,7 @@ struct opb_handle {
     enum Ready { NOT_READY, SYSTEM_FORMED, FACTORED } ready = NOT_READY;
     int mode = OPB_MODE_CHOLESKY;
     DBuf<double> Jv, Hv, y, s, sigma, T, Rval, Mval, sdiag, Lval, CB;
-    DBuf<double> dual_r, primal_r, comp_r, b, res, dx, dy, ds, tm, xw, xw2, uw, userval, Xinv, Twork;
+    DBuf<double> dual_r, primal_r, comp_r, b, res, dx, dy, ds, tm, xw, xw2, uw, userval, Xinv, Twork, Dvec;
     DBuf<unsigned long long> red;
     DBuf<int64_t> scr_i0, scr_i1;        // scratch of opb_eval_diag_JtDJ
     DBuf<double> scr_d0, scr_d1, scr_d2;
@@ -389,7 +389,7 @@ int opb_destroy(opb_handle* h) {
         if (h->stream) cudaStreamSynchronize(h->stream);
         DBuf<double>* bufs[] = {&h->Jv, &h->Hv, &h->y, &h->s, &h->sigma, &h->T, &h->Rval, &h->Mval, &h->sdiag,
                                 &h->Lval, &h->CB, &h->dual_r, &h->primal_r, &h->comp_r, &h->b, &h->res,
-                                &h->dx, &h->dy, &h->ds, &h->tm, &h->xw, &h->xw2, &h->uw, &h->userval, &h->Xinv, &h->Twork};
+                                &h->dx, &h->dy, &h->ds, &h->tm, &h->xw, &h->xw2, &h->uw, &h->userval, &h->Xinv, &h->Twork, &h->Dvec};
         for (auto* b : bufs) b->release();
         h->red.release();
         h->scr_i0.release(); h->scr_i1.release(); h->scr_d0.release(); h->scr_d1.release(); h->scr_d2.release();
@@ -440,6 +440,7 @@ int opb_set_option(opb_handle* h, const char* key, double v) {
     else if (k == "relax_small") h->opt.relax_small = v;
     else if (k == "attempts_per_sync") h->attempts_per_sync = std::max(1, (int)v);
     else if (k == "outer_block") { h->outer_block = std::max(WB, ((int)v / WB) * WB); h->drop_graphs(); }
+    else if (k == "ldlt_scalar") { g_ldlt_scalar = v != 0; h->drop_graphs(); }
     else if (k == "cb_small_k") { h->cb_small_k = (int)v; h->drop_graphs(); }
     else if (k == "barrier_timeout_s") { h->barrier_timeout_s = v; h->sctx.timeout_clocks = (long long)(v * 2.0e9); h->drop_graphs(); }
     else if (k == "lookahead") { h->lookahead = v != 0; h->side.deep = v >= 2; h->drop_graphs(); }
@@ -613,7 +614,9 @@ static int alloc_numeric(opb_handle* h) {
         CK(h->dual_r.alloc(n)); CK(h->primal_r.alloc(m)); CK(h->comp_r.alloc(m));
         CK(h->dy.alloc(m)); CK(h->ds.alloc(m)); CK(h->tm.alloc(m));
     }
+    CK(h->Dvec.alloc(n));
     h->dev = B.dev;
+    h->dev.dvec = h->Dvec.p;
     if (h->sharded()) {
         // own buffers; the peers' are attached by opb_shard_attach (again after every new structure)
         h->dev.cb_peer[h->shard_rank] = h->CB.p; h->dev.u_peer[h->shard_rank] = h->uw.p;
@@ -742,7 +745,7 @@ static void enqueue_attempt_raw(opb_handle* h, KernelTimer* timer = nullptr, uns
                           B.Mp[B.S.n], B.S.n, h->d_state, 1, st);
     launch_factor_levels(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->Xinv.p, h->d_state, h->mode,
                          h->outer_block, h->cb_small_k, h->shard_ctx(), (h->lookahead && (!timer || timer->phases)) ? &h->side : nullptr, timer,
-                         h->mode == OPB_MODE_CHOLESKY ? &B.trtri : nullptr, h->Twork.p, st);
+                         (h->mode == OPB_MODE_CHOLESKY || !g_ldlt_scalar) ? &B.trtri : nullptr, h->Twork.p, st);
     // sharded: every rank learns about a failed pivot anywhere before the delta rule is applied
     if (h->sharded()) launch_shard_barrier(h->sctx, st);
     if (loop_handle) launch_ctl_end_loop(h->d_state, loop_handle, st);

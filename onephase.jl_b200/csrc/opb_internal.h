@@ -55,6 +55,7 @@ struct DevSym {
     const int* child_list;
     const int* perm;   // perm[new] = old
     const int64_t* Xoff;  // per supernode: offset of inv(L11) (c x c, ld = ld_of(c)) in Xinv, or -1
+    double* dvec;         // LDL' mode: the pivots D as a vector over the permuted columns (per handle)
     const int64_t* gptr;  // forward-solve gather lists (symbolic.h)
     const int64_t* gsrc;
     const int* gch;
@@ -239,6 +240,7 @@ struct KernelTimer {
 // ---- kernels_factor.cu
 struct TrtriPlan;
 cudaError_t factor_configure();
+extern bool g_ldlt_scalar;
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
                           int outer_block, int cb_small_k, const ShardCtx* shard, const SideStream* side,
@@ -257,14 +259,14 @@ cudaError_t dense_configure();
 extern int g_occ_small_tiles;
 // medium + big fronts of one level (Cholesky)
 void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
-                            double* CB, double* Xinv, DeltaState* st_d, int outer_block, int cb_small_k,
+                            double* CB, double* Xinv, DeltaState* st_d, int ldlt, int outer_block, int cb_small_k,
                             const SideStream* side, KernelTimer* timer, cudaStream_t st);
 void launch_trtri(const DevSym& S, const TrtriPlan& T, const int* d_sched, const double* Lval,
                   double* Xinv, double* Twork, const DeltaState* st_d, cudaStream_t st);
 void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
                            const double* Xinv, double* x, double* xnew, double* u, cudaStream_t st);
 void launch_solve_wide_bwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
-                           const double* Xinv, double* x, double* xnew, double* u, cudaStream_t st);
+                           const double* Xinv, double* x, double* xnew, double* u, int ldlt, cudaStream_t st);
 void launch_ldlt_inertia(const DevSym& S, const double* Lval, const int64_t* dpos, int n,
                          DeltaState* st_d, cudaStream_t st);
 

@@ -152,12 +152,42 @@ def test_ldlt_quasidefinite_chain(pkg, orc):
 
 def test_ldlt_quasidefinite_reaches_big_front_kernels(pkg, orc):
     """The KKT matrix of a 3-D grid problem: top separators far beyond the 152-row shared-memory
-    fronts, so the blocked LDL' kernels (big_potrf / big_trsm / big_update) and the CTA solves
-    of wide supernodes run."""
+    fronts, so the blocked LDL' path of the big fronts runs -- the tensor-core tile engine with the
+    pivots applied inside it, the diagonal-block / panel kernels in their LDL' variant, the pivot-block
+    inverses and the multi-CTA solves."""
     p = problems.pde_control(9, seed=1)
     K = _kkt_matrix(p, 1e-6)
     ok, info = _ldlt_compare(pkg, orc, K, p.n, p.m, expect=1)
     assert info["n_big"] >= 1 and info["max_front"] > 152, info
+
+
+def test_ldlt_tensor_path_matches_the_scalar_path(pkg):
+    """The two LDL' implementations of the big fronts (tile engine, default; scalar 32-column blocks,
+    option ldlt_scalar) on a quasi-definite matrix with multi-block pivot blocks: same completion /
+    inertia flags, pivots to 1e-9, solutions to 1e-10, both with a small residual."""
+    p = problems.pde_control(12, seed=3)
+    K = _kkt_matrix(p, 1e-6)
+    b = np.random.default_rng(5).standard_normal(K.shape[0])
+    Kf = K + sp.tril(K, -1).T
+    out = []
+    for scalar in (0, 1):
+        s = _solver(pkg, "symmetric")
+        s._h.set_option("ldlt_scalar", scalar)
+        ok = s.ls_factor(K, p.n, p.m)
+        h = s._h
+        D = h.L_values()[h.symbolic("dpos")]
+        x = s.ls_solve(b)
+        res = np.abs(Kf @ x - b).max() / max(np.abs(b).max(), np.abs(Kf).max() * np.abs(x).max())
+        assert res <= 1e-10, (scalar, res)
+        out.append((ok, D, x, h.info("n_big"), h.info("n_trtri")))
+        s._h.set_option("ldlt_scalar", 0)
+        s.finalize()
+    (ok0, D0, x0, nbig, ntr), (ok1, D1, x1, _, _) = out
+    assert ok0 == ok1 == 1
+    assert nbig >= 1 and ntr >= 1, (nbig, ntr)       # pivot blocks of more than 128 columns took part
+    assert np.array_equal(np.sign(D0), np.sign(D1))
+    assert np.allclose(D0, D1, rtol=1e-9, atol=0.0)
+    assert np.linalg.norm(x0 - x1) <= REL_TOL * np.linalg.norm(x1)
 
 
 def test_ldlt_dense_front(pkg, orc):
