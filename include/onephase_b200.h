@@ -68,7 +68,11 @@ int opb_set_stream(opb_handle* h, void* cuda_stream);
  * update on a side stream, 2 [default] = deep look-ahead: every update cut into pieces by the step at which
  * its columns are next touched, one prioritised stream per piece class), "chain_priority" (0/1: the
  * latency chain of that factorisation runs on the highest-priority stream, default 1),
- * "barrier_timeout_s" (sharded instance: seconds a rank waits for its peers, default 20). */
+ * "barrier_timeout_s" (sharded instance: seconds a rank waits for its peers, default 20), "cb_small_k" (tuning: levels
+ * whose fronts have at most this many pivot columns form their update blocks in 64-row tiles, default all; an odd
+ * value runs the bulk panel updates in 128-row tiles), "ldlt_scalar" (0/1: LDL' of the big fronts on the first,
+ * scalar path instead of the tensor-core tile engine; for A/B runs), "loop_graph" (0/1: the delta loop as one
+ * CUDA-graph WHILE node, default 1), "solve_overlap" (0/1). */
 int opb_set_option(opb_handle* h, const char* key, double value);
 /* Optional fill-reducing permutation supplied by the caller (0-based, perm[new] = old). */
 int opb_set_permutation(opb_handle* h, int64_t n, const int64_t* perm);

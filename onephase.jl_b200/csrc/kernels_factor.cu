@@ -359,8 +359,6 @@ cudaError_t factor_configure() {
                                 (int)small_smem(FC_MAXN[FC_T32]));
 }
 
-bool g_ldlt_scalar = false;    // option "ldlt_scalar": the first (scalar, K = 32) LDL' path of the big fronts
-
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
                           int outer_block, int cb_small_k, const ShardCtx* shard, const SideStream* side,
@@ -408,10 +406,10 @@ void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, c
             count_launch();
         }
         if (!L.wide_count) continue;
-        if (mode == 0 || !g_ldlt_scalar) {
+        if (mode != FMODE_LDLT_SCALAR) {
             // panels in shared memory / blocked on the FP64 tensor pipe (kernels_dense.cu); LDL': the same
             // schedule with the pivots D applied inside the tile engine
-            launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, mode, outer_block, cb_small_k, side, timer, st);
+            launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, mode == FMODE_LDLT ? 1 : 0, outer_block, cb_small_k, side, timer, st);
             continue;
         }
         // LDL' fallback: scalar blocked path over every front that does not fit in shared memory

@@ -297,7 +297,7 @@ __global__ void permute_out_kernel(const double* __restrict__ x, const int* __re
 cudaError_t solve_configure() { return cudaSuccess; }
 
 void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
-                  const double* Lval, const double* Xinv, double* x, double* xnew, double* u, int mode,
+                  const double* Lval, const double* Xinv, double* x, double* xnew, double* u, int fmode,
                   const ShardCtx* shard, const int* colowner, const SideStream* side, cudaStream_t st) {
     // BIG supernodes take the multi-CTA path through inv(L11) (kernels_dense.cu), the other classes
     // (front or panel fits in shared memory) are solved by one CTA each; LDL': L11 is unit lower and
@@ -308,7 +308,8 @@ void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int
     // from the owners' HBM; backward, the owner of a top supernode pushes its part of the solution
     // to every peer before the ranks below continue, and at the end every rank publishes the
     // columns it owns.
-    const bool wide = (mode == 0) || !g_ldlt_scalar;     // LDL' on the tensor path has inv(L11) too
+    const bool wide = fmode != FMODE_LDLT_SCALAR;      // LDL' on the tensor path has inv(L11) too
+    const int mode = fmode == FMODE_CHOLESKY ? 0 : 1;   // what the kernels distinguish: Cholesky / LDL'
     // The supernodes of one level are independent of each other: where a level has both
     // CTA-per-supernode classes (latency-bound) and BIG supernodes (bandwidth-bound), the two
     // groups run concurrently on two streams and meet again before the next level.

@@ -225,6 +225,8 @@ struct opb_handle {
     int attempts_per_sync = 2;
     int outer_block = OUTER_BLOCK;
     int cb_small_k = CB_SMALL_K;
+    bool ldlt_scalar = false;            // option "ldlt_scalar"
+    int fmode() const { return mode == OPB_MODE_CHOLESKY ? FMODE_CHOLESKY : (ldlt_scalar ? FMODE_LDLT_SCALAR : FMODE_LDLT); }
     double barrier_timeout_s = 20.0;     // sharded instance: a rank that waits longer reports an error
     std::shared_ptr<Bundle> B;
     bool cached_hit = false;
@@ -440,7 +442,7 @@ int opb_set_option(opb_handle* h, const char* key, double v) {
     else if (k == "relax_small") h->opt.relax_small = v;
     else if (k == "attempts_per_sync") h->attempts_per_sync = std::max(1, (int)v);
     else if (k == "outer_block") { h->outer_block = std::max(WB, ((int)v / WB) * WB); h->drop_graphs(); }
-    else if (k == "ldlt_scalar") { g_ldlt_scalar = v != 0; h->drop_graphs(); }
+    else if (k == "ldlt_scalar") { h->ldlt_scalar = v != 0; h->drop_graphs(); }
     else if (k == "cb_small_k") { h->cb_small_k = (int)v; h->drop_graphs(); }
     else if (k == "barrier_timeout_s") { h->barrier_timeout_s = v; h->sctx.timeout_clocks = (long long)(v * 2.0e9); h->drop_graphs(); }
     else if (k == "lookahead") { h->lookahead = v != 0; h->side.deep = v >= 2; h->drop_graphs(); }
@@ -743,9 +745,9 @@ static void enqueue_attempt_raw(opb_handle* h, KernelTimer* timer = nullptr, uns
     launch_ctl_begin(h->d_state, st);
     launch_scatter_fronts(h->Mval.p, B.d_amap.p, B.d_dpos.p, h->sdiag.p, h->Lval.p, B.S.nnzL,
                           B.Mp[B.S.n], B.S.n, h->d_state, 1, st);
-    launch_factor_levels(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->Xinv.p, h->d_state, h->mode,
+    launch_factor_levels(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->CB.p, h->Xinv.p, h->d_state, h->fmode(),
                          h->outer_block, h->cb_small_k, h->shard_ctx(), (h->lookahead && (!timer || timer->phases)) ? &h->side : nullptr, timer,
-                         (h->mode == OPB_MODE_CHOLESKY || !g_ldlt_scalar) ? &B.trtri : nullptr, h->Twork.p, st);
+                         h->fmode() != FMODE_LDLT_SCALAR ? &B.trtri : nullptr, h->Twork.p, st);
     // sharded: every rank learns about a failed pivot anywhere before the delta rule is applied
     if (h->sharded()) launch_shard_barrier(h->sctx, st);
     if (loop_handle) launch_ctl_end_loop(h->d_state, loop_handle, st);
@@ -1058,7 +1060,7 @@ int opb_direction_resident(opb_handle* h, int n_refine) {
         launch_schur_rhs(D, st);
         for (int it = 0; it < n_refine; it++) {
             launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, D.n, st);
-            launch_solve(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode,
+            launch_solve(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->fmode(),
                          h->shard_ctx(), B.d_colowner.p, h->solve_overlap ? &h->side : nullptr, st);
             launch_permute_out_add(h->xw.p, B.d_perm.p, h->dx.p, D.n, 1, st);
             // the reference also evaluates the residual after the last correction but only
@@ -1144,7 +1146,7 @@ int opb_solve_resident(opb_handle* h, int nsolves) {
     for (int k = 0; k < nsolves; k++)
         run_captured(h, h->g_solve, h->mode, [&] {
             launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, B.S.n, h->stream);
-            launch_solve(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode,
+            launch_solve(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->fmode(),
                          h->shard_ctx(), B.d_colowner.p, h->solve_overlap ? &h->side : nullptr, h->stream);
             launch_permute_out_add(h->xw.p, B.d_perm.p, h->b.p, B.S.n, 0, h->stream);
         });
@@ -1233,7 +1235,7 @@ int opb_ls_solve(opb_handle* h, const double* rhs, double* sol) {
     cudaStream_t st = h->stream;
     CK(cudaMemcpyAsync(h->res.p, rhs, n * sizeof(double), cudaMemcpyHostToDevice, st));
     launch_permute_in(h->res.p, B.d_perm.p, h->xw.p, n, st);
-    launch_solve(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->mode,
+    launch_solve(h->dev, B.plan, B.d_sched.p, h->Lval.p, h->Xinv.p, h->xw.p, h->xw2.p, h->uw.p, h->fmode(),
                          h->shard_ctx(), B.d_colowner.p, h->solve_overlap ? &h->side : nullptr, st);
     launch_permute_out_add(h->xw.p, B.d_perm.p, h->b.p, n, 0, st);
     CK(cudaGetLastError());

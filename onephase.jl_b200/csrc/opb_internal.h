@@ -237,10 +237,12 @@ struct KernelTimer {
     }
 };
 
+// host-side factorisation mode of the launchers: the kernels (DeltaState::mode) only distinguish 0 / 1
+enum { FMODE_CHOLESKY = 0, FMODE_LDLT = 1, FMODE_LDLT_SCALAR = 2 };   // 2: option "ldlt_scalar", the first (scalar, K = 32) LDL' path
+
 // ---- kernels_factor.cu
 struct TrtriPlan;
 cudaError_t factor_configure();
-extern bool g_ldlt_scalar;
 void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, const int* d_sched,
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
                           int outer_block, int cb_small_k, const ShardCtx* shard, const SideStream* side,
