@@ -970,14 +970,17 @@ int opb_profile_factor(opb_handle* h, double delta, double* total_ms, double* cb
     if (cb_ms) *cb_ms = sum[0];
     if (update_ms) *update_ms = sum[1];
     // algorithmic flops of the two kernels over the fronts they serve (MID, MIDL and BIG classes):
-    // update block r^2 c (lower half, multiply-add), panel updates N c^2 - 2 c^3 / 3 (BIG only)
+    // update block r^2 c (lower half, multiply-add), panel updates of the BIG fronts
     double fcb = 0.0, fup = 0.0;
     const Symbolic& S = h->B->S;
     for (int s = 0; s < S.nsuper; s++) {
         const double c = S.sfirst[s + 1] - S.sfirst[s], r = (double)(S.rowptr[s + 1] - S.rowptr[s]), N = c + r;
         if (N <= SMALL_N) continue;
         fcb += r * r * c;
-        if (!(c <= WB && N * c <= MIDL_PANEL)) fup += N * c * c - 2.0 * c * c * c / 3.0;
+        // BIG fronts: panel flops N c^2 - 2 c^3 / 3, minus what other kernels execute -- the TRSMs
+        // (rows below each 128-column block times 128^2) and the diagonal blocks (128^3 / 3 each)
+        if (!(c <= WB && N * c <= MIDL_PANEL))
+            fup += N * c * c - 2.0 * c * c * c / 3.0 - WB * (N * c - 0.5 * c * c) - c * (double)WB * WB / 3.0;
     }
     if (cb_flops) *cb_flops = fcb;
     if (update_flops) *update_flops = fup;

@@ -22,6 +22,12 @@ def test_reference_arm_prints_the_contract_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["higher_is_better"] is False and d["unit"] == "ms/iter"
     assert d["config"]["workload"] == "c3_small" and d["value"] > 0
+    # the arm runs the workload it names: the FULL generator arguments of the table, not the bounded sample
+    sys.path.insert(0, ROOT)
+    import bench
+    gen, kw, _ = bench.WORKLOADS["c3_small"]
+    assert d["same_config"] is True and d["config"]["generator"] == gen and d["config"]["generator_args"] == kw
+    assert d["config"]["n"] == kw["n"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "supernodal" in cb["sample"]
