@@ -444,6 +444,18 @@ def measure_sharded(pkg, torch, dist, args, local, world, workload):
     steps = max(2, min(args.steps, 5))
     inst.e2e_step()
     dist.barrier(); torch.cuda.synchronize()
+    # correctness of the sharded solve, evaluated on the host from the INPUTS (rank 0): the last direction of the
+    # step must satisfy the Schur system  (J' S J + H + delta I) dx = dual_r + J'(S primal_r + comp_r / s)
+    schur_res = None
+    if dist.get_rank() == 0:
+        import scipy.sparse as sp
+        r = prob.rhs[N_DIRECTIONS - 1]
+        sig = prob.y / prob.s
+        Hs = prob.H + sp.tril(prob.H, -1).T
+        dx = inst.k.dir.x
+        b = r[0] + prob.J.T @ (r[1] * sig + r[2] / prob.s)
+        Mdx = prob.J.T @ (sig * (prob.J @ dx)) + Hs @ dx + float(inst.k._delta) * dx
+        schur_res = float(np.abs(Mdx - b).max() / np.abs(b).max())
     t0 = time.perf_counter()
     for _ in range(steps):
         inst.e2e_step()
@@ -461,7 +473,8 @@ def measure_sharded(pkg, torch, dist, args, local, world, workload):
     dist.all_reduce(loads)
     out = {"workload": workload, "n_gpus": world, "ms_per_iter": float(t[0]), "e2e_ms_per_iter": float(t[1]),
            "factor_ms": float(t[2]) / max(nf_res, 1), "solve_pair_ms": float(t[3]), "num_fac": nf_res,
-           "N_err": float(kkt_err[5]), "scaling": "strong",
+           "N_err": float(kkt_err[5]), "schur_residual_host_check": schur_res, "scaling": "strong",
+           "split_fronts": int(h.info("shard_split")),
            "rank_flops": [float(v) for v in loads], "top_flops": h.info("shard_top_flops"),
            "barrier_levels": int(h.info("shard_barriers")),
            "how": "subtree-to-GPU mapping by factorisation flops; update blocks, forward update vectors and the "

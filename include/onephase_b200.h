@@ -59,7 +59,8 @@ int opb_set_stream(opb_handle* h, void* cuda_stream);
 
 /* Options.  Symbolic (before opb_set_structure): "ordering" (4 auto = fewer flops of 0 and 3
  * [default], 0 level-structure nested dissection + minimum-degree leaves, 1 natural,
- * 3 METIS_NodeND), "nd_leaf", "nd_balance" (a separator level must leave at least this fraction
+ * 3 METIS_NodeND), "shard_split_flops" (sharded instance: update blocks of top fronts with at least this many
+ * flops are split over the ranks of their range, default 2e10), "nd_leaf", "nd_balance" (a separator level must leave at least this fraction
  * of the part on either side, default 0.30), "metis_max_n", "relax" (0/1), "relax_small".
  * Numeric (any time): "attempts_per_sync" (delta-loop attempts enqueued per host
  * synchronisation, default 2), "graphs" (0/1: replay the launch sequences from CUDA graphs),
@@ -188,9 +189,12 @@ int opb_sync_state(opb_handle* h, double* delta_out, int* num_fac_out, int* stat
  *                     rank's peer-visible buffers (CUDA IPC handles); exchange them between the
  *                     ranks by any means (the Python host uses torch.distributed.all_gather)
  *   opb_shard_attach  map the buffers of rank `peer` from its blob
- * Extra info keys: shard_rank, shard_world, shard_load (flops owned by this rank),
+ * The update blocks of the top separators are formed by all ranks of the separator's range: the owner
+ * factorises the panel, the other ranks pull it over NVLink and store their share of the tiles into the owner's
+ * update-block arena.
+ * Extra info keys: shard_rank, shard_world, shard_load (flops owned by this rank), shard_split (split fronts),
  * shard_top_flops, shard_barriers; symbolic arrays: owner, top. */
-#define OPB_SHARD_BLOB_BYTES 320
+#define OPB_SHARD_BLOB_BYTES 384
 int opb_shard_init(opb_handle* h, int rank, int world);
 int opb_shard_export(opb_handle* h, unsigned char* blob);
 int opb_shard_attach(opb_handle* h, int peer, const unsigned char* blob);

@@ -210,7 +210,7 @@ end
 # ---------------------------------------------------------------------------------------------
 # One instance over several GPUs (include/onephase_b200.h, opb_shard_*): one Julia process per GPU,
 # every process making the same calls with the same data.  `allgather(blob)::Vector{Vector{UInt8}}`
-# is any transport the host program has (MPI.Allgather, Distributed.jl, a file): only these 320
+# is any transport the host program has (MPI.Allgather, Distributed.jl, a file): only these 384
 # bytes per rank travel through it, the numeric data moves between the GPUs inside the kernels.
 #   shard_init!(kkt_solver, rank, world)        before the first form_system!
 #   shard_attach!(kkt_solver, allgather)        after every opb_set_structure (form_system! calls it)
@@ -221,7 +221,7 @@ function shard_init!(kkt_solver::Schur_B200_KKT_solver, rank::Integer, world::In
 end
 
 function shard_attach!(kkt_solver::Schur_B200_KKT_solver, allgather::Function)
-    blob = Vector{UInt8}(undef, 320)
+    blob = Vector{UInt8}(undef, 384)
     opb_check(kkt_solver._h, ccall((:opb_shard_export, LIBOPB), Cint, (Ptr{Cvoid}, Ptr{UInt8}),
                                    kkt_solver._h.ptr, blob))
     blobs = allgather(blob)

@@ -33,7 +33,7 @@ EXPORTS = [
     "opb_shard_init", "opb_shard_export", "opb_shard_attach", "opb_profile_factor", "opb_eval_diag_JtDJ",
     "opb_system_rhs", "opb_step_bounds", "opb_get_direction", "opb_profile_levels",
 ]
-SHARD_BLOB_BYTES = 320
+SHARD_BLOB_BYTES = 384
 
 
 class OPBError(RuntimeError):

@@ -621,10 +621,14 @@ mid_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lv
 // consecutive front rows; a warp walks the child's columns for 32 of the child's rows (coalesced along
 // the rows on both sides) with EAP_Q independent read-modify-writes in flight per lane -- the kernel is
 // a chain of DRAM round trips, so its speed is the number of them in flight.
-constexpr int EAP_RB = 32, EAP_T = 256, EAP_W = EAP_T / 32, EAP_Q = 4;
+// Two shapes: 256 threads x 4 in flight for levels with many fronts (small CTAs start faster), 512 x 8 for the
+// few huge fronts at the top of the tree (root of C5 100^3: 3.3 -> 2.0 ms).
+constexpr int EAP_RB = 32;
+template <int EAP_T, int EAP_Q>
 __global__ void __launch_bounds__(EAP_T)
 big_extend_add_panel_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval,
                             const double* __restrict__ CB, DeltaState* st) {
+    constexpr int EAP_W = EAP_T / 32;
     if (stop_requested(st)) return;
     const Front d = get_front(S, list[blockIdx.y]);
     const int row0 = blockIdx.x * EAP_RB;
@@ -908,7 +912,8 @@ front_cb_kernel(DevSym S, const int* __restrict__ list, const int2* __restrict__
         }
         __syncthreads();
     }
-    double* out = CB + d.cboff;
+    // sharded instance: the tiles of a split front go into the OWNER's arena (peer stores over NVLink)
+    double* out = (S.owner ? S.cb_peer[S.owner[d.s]] : CB) + d.cboff;
     for (int idx = tid; idx < BM_ * BN; idx += NTHR) {
         const int i = ri + idx % BM_, kk = rj + idx / BM_;
         if (i < d.N && kk >= d.c && kk < d.N && i >= kk)
@@ -1282,22 +1287,26 @@ cudaError_t dense_configure() {
 
 void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
                             double* CB, double* Xinv, DeltaState* st_d, int ldlt, int outer_block, int cb_small_k,
-                            const SideStream* side, KernelTimer* timer, cudaStream_t st) {
-    if (!L.wide_count) return;
+                            const SideStream* side, KernelTimer* timer, int phase, cudaStream_t st) {
+    // phase 0: the whole level; 1: panels only; 2: update blocks only (sharded instance, levels with
+    // split fronts: the helpers' tiles come in between, see launch_factor_levels)
+    const bool do_panels = phase != 2 && L.wide_count > 0, do_cb = phase != 1;
+    if (!do_panels && !(do_cb && (L.cbt_count[0] > 0 || L.cbt_count[1] > 0))) return;
     const bool upd_small_tiles = (cb_small_k & 1) == 0;     // odd cb_small_k (tuning): bulk panel updates in 128-row tiles
     KernelTimer* phase_timer = (timer && timer->phases) ? timer : nullptr;
     if (phase_timer) timer = nullptr;
     // medium fronts: panel in shared memory
-    for (int fc = FC_MID; fc <= FC_MIDL; fc++) {
+    for (int fc = FC_MID; do_panels && fc <= FC_MIDL; fc++) {
         if (!L.count[fc]) continue;
         mid_panel_kernel<<<L.count[fc], PT, mid_smem(L.maxPanel[fc]), st>>>(S, d_sched + L.begin[fc], Lval, CB, ldlt, st_d);
         count_launch();
     }
     // big fronts: blocked right-looking factorisation of the panel columns
-    if (L.count[FC_BIG]) {
+    if (do_panels && L.count[FC_BIG]) {
         const int* list = d_sched + L.begin[FC_BIG];
         dim3 gea((L.maxN[FC_BIG] + EAP_RB - 1) / EAP_RB, L.count[FC_BIG]);
-        big_extend_add_panel_kernel<<<gea, EAP_T, 0, st>>>(S, list, Lval, CB, st_d);
+        if (L.count[FC_BIG] <= 4) big_extend_add_panel_kernel<512, 8><<<gea, 512, 0, st>>>(S, list, Lval, CB, st_d);
+        else big_extend_add_panel_kernel<256, 4><<<gea, 256, 0, st>>>(S, list, Lval, CB, st_d);
         count_launch();
         if (phase_timer) phase_timer->put_mark(1, st);
         int sub = 1;                                            // WB blocks per outer block (power of two)
@@ -1448,7 +1457,7 @@ void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sc
         }
     }
     // update blocks of all medium and big fronts, written once
-    {
+    if (do_cb) {
         // short K (low levels): 64-row tiles, two CTAs per SM; otherwise 128 x 128 tiles
         const int v = L.wide_maxC <= cb_small_k ? 0 : 1;
         if (phase_timer) phase_timer->put_mark(2, st);
@@ -1538,7 +1547,8 @@ void launch_solve_wide_bwd(const DevSym& S, const LevelPlan& L, const int* d_sch
 cudaError_t preload_dense() {
     cudaFuncAttributes a;
     cudaError_t e;
-    e = cudaFuncGetAttributes(&a, big_extend_add_panel_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, big_extend_add_panel_kernel<256, 4>); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, big_extend_add_panel_kernel<512, 8>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, chol_diag_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, chol_panel_update_kernel<1, false>); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, chol_panel_update_kernel<2, false>); if (e != cudaSuccess) return e;

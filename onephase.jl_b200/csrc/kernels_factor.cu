@@ -405,13 +405,25 @@ void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, c
                 S, d_sched + L.begin[fc], Lval, CB, st_d);
             count_launch();
         }
-        if (!L.wide_count) continue;
         if (mode != FMODE_LDLT_SCALAR) {
             // panels in shared memory / blocked on the FP64 tensor pipe (kernels_dense.cu); LDL': the same
             // schedule with the pivots D applied inside the tile engine
-            launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, mode == FMODE_LDLT ? 1 : 0, outer_block, cb_small_k, side, timer, st);
+            const int ldlt = mode == FMODE_LDLT ? 1 : 0;
+            if (shard && L.split) {
+                // Sharded instance, level with split fronts: the owners factorise the panels; then every rank
+                // of a split front's range pulls the panel over NVLink and forms its share of the update
+                // block's tiles, storing them into the owner's arena; nobody goes on before all tiles are in.
+                launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, ldlt, outer_block, cb_small_k, side, timer, 1, st);
+                launch_shard_barrier(*shard, st);
+                launch_pull_panels(S, d_sched + L.help_begin, L.help_count, L.help_maxN, Lval, st_d, st);
+                launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, ldlt, outer_block, cb_small_k, side, timer, 2, st);
+                launch_shard_barrier(*shard, st);
+            } else {
+                launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, ldlt, outer_block, cb_small_k, side, timer, 0, st);
+            }
             continue;
         }
+        if (!L.wide_count) continue;
         // LDL' fallback: scalar blocked path over every front that does not fit in shared memory
         const int* list = d_sched + L.wide_begin;
         dim3 gea((L.wide_maxN + EA_RB - 1) / EA_RB, L.wide_count);

@@ -86,7 +86,41 @@ push_owned_kernel(DevSym S, const int* __restrict__ colowner, const double* __re
         if (p != S.rank) S.x_peer[p][k] = v;
 }
 
+// split fronts of other ranks: the rows below the pivot block of the finished panel, from the owner's HBM
+// into this rank's copy of the factor storage (same offsets: every rank keeps the global layout)
+constexpr int PULL_ROWS = 256, PULL_COLS = 64;
+__global__ void __launch_bounds__(PULL_ROWS)
+pull_panels_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ Lval, const DeltaState* st) {
+    if (*(volatile const int*)&st->done | *(volatile const int*)&st->fail) return;
+    const int s = list[blockIdx.z];
+    const int c = S.sfirst[s + 1] - S.sfirst[s];
+    const int N = c + (int)(S.rowptr[s + 1] - S.rowptr[s]);
+    const int ld = ld_of(N);
+    const int i = (c & ~1) + blockIdx.x * PULL_ROWS + threadIdx.x;
+    const int j0 = blockIdx.y * PULL_COLS;
+    if (i >= N || j0 >= c) return;
+    const double* __restrict__ src = S.l_peer[S.owner[s]] + S.Loff[s] + i;
+    double* __restrict__ dst = Lval + S.Loff[s] + i;
+    const int j1 = min(c, j0 + PULL_COLS);
+    int j = j0;
+    for (; j + 4 <= j1; j += 4) {
+        const double v0 = src[(size_t)j * ld], v1 = src[(size_t)(j + 1) * ld];
+        const double v2 = src[(size_t)(j + 2) * ld], v3 = src[(size_t)(j + 3) * ld];
+        dst[(size_t)j * ld] = v0; dst[(size_t)(j + 1) * ld] = v1; dst[(size_t)(j + 2) * ld] = v2; dst[(size_t)(j + 3) * ld] = v3;
+    }
+    for (; j < j1; j++) dst[(size_t)j * ld] = src[(size_t)j * ld];
+}
+
 }  // namespace
+
+void launch_pull_panels(const DevSym& S, const int* list, int count, int maxN, double* Lval, const DeltaState* st_d,
+                        cudaStream_t st) {
+    if (count <= 0 || maxN <= 0) return;
+    // columns: every front has at most maxN of them
+    dim3 g((maxN + PULL_ROWS - 1) / PULL_ROWS, (maxN + PULL_COLS - 1) / PULL_COLS, count);
+    pull_panels_kernel<<<g, PULL_ROWS, 0, st>>>(S, list, Lval, st_d);
+    count_launch();
+}
 
 void launch_shard_barrier(const ShardCtx& C, cudaStream_t st) {
     shard_barrier_kernel<<<1, 32, 0, st>>>(C);
@@ -113,6 +147,7 @@ cudaError_t preload_shard() {
     e = cudaFuncGetAttributes(&a, shard_barrier_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, push_supernodes_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, push_owned_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, pull_panels_kernel); if (e != cudaSuccess) return e;
     return cudaSuccess;
 }
 

@@ -97,10 +97,14 @@ static void build_plan(Bundle& B) {
         LevelPlan& L = B.plan[l];
         std::vector<int> cls[NFC];
         std::vector<int> push;
-        if (sharded) L.barrier_before = B.shard.level_barrier[l];
+        if (sharded) { L.barrier_before = B.shard.level_barrier[l]; L.split = B.shard.level_split[l]; }
+        std::vector<int> helped;          // split fronts of other ranks this rank forms update-block tiles of
         for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
             const int s = S.level_list[t];
-            if (sharded && B.shard.owner[s] != B.rank) continue;      // another rank's supernode
+            if (sharded && B.shard.owner[s] != B.rank) {              // another rank's supernode
+                if (B.shard.split[s] && B.shard.ra[s] <= B.rank && B.rank < B.shard.rb[s]) helped.push_back(s);
+                continue;
+            }
             const int c = cols(s), N = rows(s);
             if (sharded && B.shard.top[s]) { push.push_back(s); L.push_maxc = std::max(L.push_maxc, c); }
             int fc;
@@ -144,6 +148,12 @@ static void build_plan(Bundle& B) {
                 }
         }
         L.all_count = (int)B.sched.size() - L.all_begin;
+        // helped fronts sit right behind the level's wide list, so the update-block kernel addresses
+        // them through the same list pointer (positions wide_count .. wide_count + help_count - 1)
+        L.help_begin = (int)B.sched.size();
+        L.help_count = (int)helped.size();
+        B.sched.insert(B.sched.end(), helped.begin(), helped.end());
+        for (int s : helped) L.help_maxN = std::max(L.help_maxN, rows(s));
         L.push_begin = (int)B.sched.size();
         L.push_count = (int)push.size();
         B.sched.insert(B.sched.end(), push.begin(), push.end());
@@ -155,15 +165,19 @@ static void build_plan(Bundle& B) {
         for (int v = 0; v < 2; v++) {
             if (B.sched.size() & 1) B.sched.push_back(0);          // int2 alignment
             L.cbt_begin[v] = (int)B.sched.size();
+            auto add_tiles = [&](int pos, int s) {
+                const int c = cols(s), N = rows(s);
+                if (N - c <= 0) return;
+                const long long nt = cb_tiles(v + 1, N, c & ~1);
+                // split front (sharded instance): tile t belongs to rank ra + t mod (rb - ra)
+                const bool sp = sharded && B.shard.split[s];
+                const int G = sp ? B.shard.rb[s] - B.shard.ra[s] : 1, me = sp ? B.rank - B.shard.ra[s] : 0;
+                for (long long t = me; t < nt; t += G) { B.sched.push_back(pos); B.sched.push_back((int)t); }
+            };
             for (int fc = FC_BIG; fc >= FC_MID; fc--)
-                for (int q = 0; q < L.count[fc]; q++) {
-                    const int pos = L.begin[fc] + q - L.wide_begin;
-                    const int s = B.sched[L.begin[fc] + q];
-                    const int c = cols(s), N = rows(s);
-                    if (N - c <= 0) continue;
-                    const long long nt = cb_tiles(v + 1, N, c & ~1);
-                    for (long long t = 0; t < nt; t++) { B.sched.push_back(pos); B.sched.push_back((int)t); }
-                }
+                for (int q = 0; q < L.count[fc]; q++)
+                    add_tiles(L.begin[fc] + q - L.wide_begin, B.sched[L.begin[fc] + q]);
+            for (int q = 0; q < L.help_count; q++) add_tiles(L.help_begin + q - L.wide_begin, B.sched[L.help_begin + q]);
             L.cbt_count[v] = ((int)B.sched.size() - L.cbt_begin[v]) / 2;
         }
         B.n_tiny += L.count[FC_T32];
@@ -267,12 +281,12 @@ struct opb_handle {
     ShardCtx sctx{};
     unsigned long long* d_flags = nullptr;   // [2][MAX_SHARD] flags, [16] epoch, [17] error
     bool peer_ok[MAX_SHARD] = {false};
-    void* peer_ipc[MAX_SHARD][4] = {{nullptr}};
+    void* peer_ipc[MAX_SHARD][5] = {{nullptr}};
     std::string peer_blob[MAX_SHARD];
     bool sharded() const { return shard_world > 1; }
     const ShardCtx* shard_ctx() const { return shard_world > 1 ? &sctx : nullptr; }
     void close_peer(int p) {
-        for (int k = 0; k < 4; k++) if (peer_ipc[p][k]) { cudaIpcCloseMemHandle(peer_ipc[p][k]); peer_ipc[p][k] = nullptr; }
+        for (int k = 0; k < 5; k++) if (peer_ipc[p][k]) { cudaIpcCloseMemHandle(peer_ipc[p][k]); peer_ipc[p][k] = nullptr; }
         peer_ok[p] = false; peer_blob[p].clear();
     }
 
@@ -440,6 +454,7 @@ int opb_set_option(opb_handle* h, const char* key, double v) {
     else if (k == "relax") h->opt.relax_enable = (int)v;
     else if (k == "metis_max_n") h->opt.metis_max_n = (int)v;
     else if (k == "relax_small") h->opt.relax_small = v;
+    else if (k == "shard_split_flops") h->opt.shard_split_flops = v;
     else if (k == "attempts_per_sync") h->attempts_per_sync = std::max(1, (int)v);
     else if (k == "outer_block") { h->outer_block = std::max(WB, ((int)v / WB) * WB); h->drop_graphs(); }
     else if (k == "ldlt_scalar") { h->ldlt_scalar = v != 0; h->drop_graphs(); }
@@ -462,10 +477,11 @@ int opb_set_permutation(opb_handle* h, int64_t n, const int64_t* perm) {
 }
 
 // ---- one instance over several GPUs ---------------------------------------
-// blob layout: [0] pid, [8] CB, [16] u, [24] x, [32] flags (raw device pointers, valid inside the
-// exporting process), [64 + 64 k] cudaIpcMemHandle_t of the same four buffers
+// blob layout: [0] pid, [8] CB, [16] u, [24] x, [32] flags, [40] L (raw device pointers, valid inside the
+// exporting process), [64 + 64 k] cudaIpcMemHandle_t of the same five buffers
+constexpr int NPEERBUF = 5;
 static_assert(sizeof(cudaIpcMemHandle_t) == 64, "blob layout");
-static_assert(OPB_SHARD_BLOB_BYTES >= 64 + 4 * 64, "blob layout");
+static_assert(OPB_SHARD_BLOB_BYTES >= 64 + NPEERBUF * 64, "blob layout");
 
 int opb_shard_init(opb_handle* h, int rank, int world) {
     if (!h) return OPB_ERR_INVALID;
@@ -496,9 +512,9 @@ int opb_shard_export(opb_handle* h, unsigned char* blob) {
     cudaSetDevice(h->device);
     memset(blob, 0, OPB_SHARD_BLOB_BYTES);
     const uint64_t pid = (uint64_t)getpid();
-    void* ptrs[4] = {h->CB.p, h->uw.p, h->xw.p, h->d_flags};
+    void* ptrs[NPEERBUF] = {h->CB.p, h->uw.p, h->xw.p, h->d_flags, h->Lval.p};
     memcpy(blob, &pid, 8);
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < NPEERBUF; k++) {
         memcpy(blob + 8 + 8 * k, &ptrs[k], 8);
         cudaIpcMemHandle_t ih;
         CK(cudaIpcGetMemHandle(&ih, ptrs[k]));
@@ -515,7 +531,7 @@ int opb_shard_attach(opb_handle* h, int peer, const unsigned char* blob) {
     cudaSetDevice(h->device);
     h->drop_graphs();
     const std::string nb(reinterpret_cast<const char*>(blob), OPB_SHARD_BLOB_BYTES);
-    void* ptrs[4];
+    void* ptrs[NPEERBUF];
     uint64_t pid;
     memcpy(&pid, blob, 8);
     if (pid == (uint64_t)getpid()) {
@@ -525,13 +541,17 @@ int opb_shard_attach(opb_handle* h, int peer, const unsigned char* blob) {
         // until the barrier times out, so same-process peers use plain launches.  (Between
         // processes the ranks' contexts are independent and the graphs stay on.)
         h->use_graphs = false;
+        // ... and the two-stream look-ahead instead of the deep one: every stream of every virtual rank
+        // needs its own hardware queue (a barrier kernel spinning in a shared queue blocks the peer it
+        // waits for), and ten streams per handle exhaust the connections of one context
+        h->side.deep = false;
         h->close_peer(peer);
-        for (int k = 0; k < 4; k++) memcpy(&ptrs[k], blob + 8 + 8 * k, 8);
+        for (int k = 0; k < NPEERBUF; k++) memcpy(&ptrs[k], blob + 8 + 8 * k, 8);
     } else if (h->peer_blob[peer] == nb && h->peer_ipc[peer][0]) {
-        for (int k = 0; k < 4; k++) ptrs[k] = h->peer_ipc[peer][k];     // same allocations as before
+        for (int k = 0; k < NPEERBUF; k++) ptrs[k] = h->peer_ipc[peer][k];     // same allocations as before
     } else {
         h->close_peer(peer);
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < NPEERBUF; k++) {
             cudaIpcMemHandle_t ih;
             memcpy(&ih, blob + 64 + 64 * k, 64);
             CK(cudaIpcOpenMemHandle(&ptrs[k], ih, cudaIpcMemLazyEnablePeerAccess));
@@ -543,6 +563,7 @@ int opb_shard_attach(opb_handle* h, int peer, const unsigned char* blob) {
     h->dev.u_peer[peer] = static_cast<double*>(ptrs[1]);
     h->dev.x_peer[peer] = static_cast<double*>(ptrs[2]);
     h->sctx.flags_peer[peer] = static_cast<unsigned long long*>(ptrs[3]);
+    h->dev.l_peer[peer] = static_cast<double*>(ptrs[4]);
     h->peer_ok[peer] = true;
     return OPB_OK;
 }
@@ -623,6 +644,7 @@ static int alloc_numeric(opb_handle* h) {
         // own buffers; the peers' are attached by opb_shard_attach (again after every new structure)
         h->dev.cb_peer[h->shard_rank] = h->CB.p; h->dev.u_peer[h->shard_rank] = h->uw.p;
         h->dev.x_peer[h->shard_rank] = h->xw.p;
+        h->dev.l_peer[h->shard_rank] = h->Lval.p;
         for (int p = 0; p < h->shard_world; p++) if (p != h->shard_rank) h->peer_ok[p] = false;
     }
     return OPB_OK;
@@ -630,10 +652,10 @@ static int alloc_numeric(opb_handle* h) {
 
 static std::string cache_key(const opb_handle* h, uint64_t h1, uint64_t h2) {
     const SymOptions& o = h->opt;
-    char buf[200];
-    snprintf(buf, sizeof buf, "%d|%d|%.4f|%d|%d|%d|%.3f|%d|%d/%d|%016llx|%016llx", h->device, o.nd_leaf, o.nd_balance, o.ordering,
+    char buf[240];
+    snprintf(buf, sizeof buf, "%d|%d|%.4f|%d|%d|%d|%.3f|%d|%d/%d|%.3g|%016llx|%016llx", h->device, o.nd_leaf, o.nd_balance, o.ordering,
              o.metis_max_n, o.relax_enable, o.relax_small, h->user_perm.empty() ? 0 : 1, h->shard_rank, h->shard_world,
-             (unsigned long long)h1, (unsigned long long)h2);
+             o.shard_split_flops, (unsigned long long)h1, (unsigned long long)h2);
     return buf;
 }
 
@@ -668,7 +690,7 @@ static int finish_structure(opb_handle* h, std::shared_ptr<Bundle> B, const std:
     }
     B->rank = h->shard_rank; B->world = h->shard_world;
     if (B->world > 1) {
-        shard_map(B->S, B->world, B->shard);
+        shard_map(B->S, B->world, h->opt.shard_split_flops, B->shard);
         B->colowner.resize(B->S.n);
         for (int j = 0; j < B->S.n; j++) B->colowner[j] = B->shard.owner[B->S.col2super[j]];
     }
@@ -1303,7 +1325,9 @@ int opb_get_info(opb_handle* h, const char* key, double* out) {
     else if (k == "shard_world") *out = B.world;
     else if (k == "shard_load") *out = B.world > 1 ? B.shard.load[B.rank] : S.flops;
     else if (k == "shard_top_flops") *out = B.world > 1 ? B.shard.top_flops : 0.0;
-    else if (k == "shard_barriers") { int c = 0; for (const LevelPlan& L : B.plan) c += L.barrier_before; *out = c; }
+    else if (k == "shard_barriers") { int c = 0; for (const LevelPlan& L : B.plan) c += L.barrier_before + 2 * L.split; *out = c; }
+    else if (k == "shard_split") { int c = 0; if (B.world > 1) for (char f : B.shard.split) c += f; *out = c; }
+    else if (k == "shard_helped") { int c = 0; for (const LevelPlan& L : B.plan) c += L.help_count; *out = c; }
     else return h->fail(OPB_ERR_INVALID, "unknown info key " + k);
     return OPB_OK;
 }
@@ -1338,6 +1362,9 @@ int64_t opb_get_symbolic(opb_handle* h, const char* name, int64_t* out, int64_t 
     if (k == "tcut_ptr") return copy_out(S.tcut_ptr, out, cap);
     if (k == "tcut") return copy_out(S.tcut, out, cap);
     if (k == "owner") { if (B.world > 1) return copy_out(B.shard.owner, out, cap); return copy_out(std::vector<int>(S.nsuper, 0), out, cap); }
+    if (k == "split") { std::vector<int> t(S.nsuper, 0); if (B.world > 1) for (int q = 0; q < S.nsuper; q++) t[q] = B.shard.split[q]; return copy_out(t, out, cap); }
+    if (k == "range_a") { if (B.world > 1) return copy_out(B.shard.ra, out, cap); return copy_out(std::vector<int>(S.nsuper, 0), out, cap); }
+    if (k == "range_b") { if (B.world > 1) return copy_out(B.shard.rb, out, cap); return copy_out(std::vector<int>(S.nsuper, 1), out, cap); }
     if (k == "top") { std::vector<int> t(S.nsuper, 0); if (B.world > 1) for (int q = 0; q < S.nsuper; q++) t[q] = B.shard.top[q]; return copy_out(t, out, cap); }
     return h->fail(OPB_ERR_INVALID, "unknown symbolic array " + k);
 }

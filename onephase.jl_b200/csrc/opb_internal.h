@@ -65,6 +65,7 @@ struct DevSym {
     const int* owner;     // per supernode: rank that owns it
     int rank, world;
     double* cb_peer[MAX_SHARD];   // update-block buffer of every rank (peer-mapped; [rank] = own)
+    double* l_peer[MAX_SHARD];    // factor storage of every rank (helpers pull the panels of split fronts)
     double* u_peer[MAX_SHARD];    // forward-solve update vectors of every rank
     double* x_peer[MAX_SHARD];    // solution vector of every rank (top supernodes are pushed to all)
 };
@@ -162,6 +163,9 @@ struct LevelPlan {
     // child on another rank); push_count = top supernodes of this rank on the level, whose solution
     // is pushed to every peer in the backward sweep
     int barrier_before = 0, push_count = 0, push_begin = 0, push_maxc = 0;
+    // sharded instance: the level has split fronts (ShardMap::split): two more barriers, and the split
+    // fronts of other ranks whose update-block tiles this rank forms (positions right behind the wide list)
+    int split = 0, help_begin = 0, help_count = 0, help_maxN = 0;
 };
 
 // ---- kernels_assembly.cu
@@ -262,7 +266,7 @@ extern int g_occ_small_tiles;
 // medium + big fronts of one level (Cholesky)
 void launch_wide_chol_level(const DevSym& S, const LevelPlan& L, const int* d_sched, double* Lval,
                             double* CB, double* Xinv, DeltaState* st_d, int ldlt, int outer_block, int cb_small_k,
-                            const SideStream* side, KernelTimer* timer, cudaStream_t st);
+                            const SideStream* side, KernelTimer* timer, int phase, cudaStream_t st);
 void launch_trtri(const DevSym& S, const TrtriPlan& T, const int* d_sched, const double* Lval,
                   double* Xinv, double* Twork, const DeltaState* st_d, cudaStream_t st);
 void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
@@ -284,6 +288,7 @@ cudaError_t preload_shard();
 void launch_shard_barrier(const ShardCtx& C, cudaStream_t st);
 void launch_push_supernodes(const DevSym& S, const int* list, int count, int maxc, const double* x, cudaStream_t st);
 void launch_push_owned(const DevSym& S, const int* colowner, const double* x, cudaStream_t st);
+void launch_pull_panels(const DevSym& S, const int* list, int count, int maxN, double* Lval, const DeltaState* st_d, cudaStream_t st);
 
 // ---- kernels_solve.cu
 cudaError_t solve_configure();

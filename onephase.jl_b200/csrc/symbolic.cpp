@@ -947,13 +947,16 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
     return true;
 }
 
-void shard_map(const Symbolic& S, int world, ShardMap& out) {
+void shard_map(const Symbolic& S, int world, double split_flops, ShardMap& out) {
     const int NS = S.nsuper;
     out = ShardMap();
     out.world = std::max(1, world);
     out.owner.assign(NS, 0);
     out.top.assign(NS, 0);
     out.level_barrier.assign(std::max(1, S.nlevels), 0);
+    out.level_split.assign(std::max(1, S.nlevels), 0);
+    out.split.assign(NS, 0);
+    out.ra.assign(NS, 0); out.rb.assign(NS, 1);
     out.load.assign(out.world, 0.0);
     // factorisation flops of every supernode and of the subtree below it (children have smaller
     // indices: the supernodes are numbered in postorder)
@@ -1013,6 +1016,7 @@ void shard_map(const Symbolic& S, int world, ShardMap& out) {
                 expansions++;
                 out.owner[hnode] = T.a;
                 out.top[hnode] = 1;
+                out.ra[hnode] = T.a; out.rb[hnode] = T.b;
                 T.roots.erase(T.roots.begin() + pick);
                 for (int k = S.child_ptr[hnode]; k < S.child_ptr[hnode + 1]; k++) T.roots.push_back(S.child_list[k]);
             }
@@ -1024,6 +1028,17 @@ void shard_map(const Symbolic& S, int world, ShardMap& out) {
         }
     }
     for (int s = 0; s < NS; s++) {
+        // update blocks worth splitting: r^2 c above split_flops (default 2e10: a millisecond of one GPU)
+        const double c = S.sfirst[s + 1] - S.sfirst[s], r = (double)(S.rowptr[s + 1] - S.rowptr[s]);
+        if (out.top[s] && out.rb[s] - out.ra[s] >= 2 && r > 0 && r * r * c >= split_flops) {
+            out.split[s] = 1;
+            out.level_split[S.level[s]] = 1;
+        } else if (!out.top[s]) { out.ra[s] = out.owner[s]; out.rb[s] = out.owner[s] + 1; }
+        if (out.split[s]) {
+            const double fcb = r * r * c;
+            out.load[out.owner[s]] += w[s] - fcb;
+            for (int q = out.ra[s]; q < out.rb[s]; q++) out.load[q] += fcb / (out.rb[s] - out.ra[s]);
+        } else
         out.load[out.owner[s]] += w[s];
         if (out.top[s]) out.top_flops += w[s];
         const int p = S.sparent[s];

@@ -23,6 +23,7 @@ struct SymOptions {
     double relax_small = 8;    // always merge a last child when merged width <= this
     double relax_z16 = 0.8, relax_z32 = 0.3, relax_z64 = 0.1, relax_zinf = 0.05;
     int relax_enable = 1;
+    double shard_split_flops = 2e10;   // sharded instance: update blocks of top fronts with at least this many flops (r^2 c) are split over the ranks of their range
 };
 
 // Pattern of M_L = tril(J' D J + H) with full diagonal, and the gather map
@@ -106,10 +107,17 @@ struct ShardMap {
     std::vector<int> owner;              // per supernode: rank that factorises and solves it
     std::vector<char> top;               // per supernode: descendants live on more than one rank
     std::vector<char> level_barrier;     // per level: some supernode of the level has a child on another rank
+    // Top supernodes whose update block is formed by ALL ranks of the range the supernode was expanded
+    // in (`split`): rank range [ra, rb), tile t of the update block belongs to rank ra + t mod (rb - ra).
+    // The owner factorises the panel; the helpers pull it over NVLink and store their tiles into the
+    // owner's update-block arena.  level_split: the level has such a supernode (every rank runs the
+    // two extra barriers of that level).
+    std::vector<char> split, level_split;
+    std::vector<int> ra, rb;
     std::vector<double> load;            // per rank: flops of the supernodes it owns
     double top_flops = 0;                // flops of the top supernodes
 };
-void shard_map(const Symbolic& S, int world, ShardMap& out);
+void shard_map(const Symbolic& S, int world, double split_flops, ShardMap& out);
 
 uint64_t pattern_hash(int64_t n, const int64_t* p, const int64_t* i, int64_t nnz);
 

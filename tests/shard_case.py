@@ -6,7 +6,7 @@ CUDA_DEVICE_MAX_CONNECTIONS raised, keeps every handle's stream on its own hardw
 one CUDA context two streams that share a queue serialise, and a rank waiting in a barrier kernel
 would then block the very peer it waits for (between processes, the real deployment, every rank
 has its own context and queues).  Prints one JSON line.
-    python tests/shard_case.py GEN WORLD [key=value ...] [--delta-prev X] [--iters K]"""
+    python tests/shard_case.py GEN WORLD [key=value ...] [--delta-prev X] [--iters K] [--opt LIBOPTION=VALUE]"""
 import faulthandler
 import json
 import os
@@ -25,7 +25,7 @@ import __graft_entry__ as g  # noqa: E402
 
 def main():
     gen, world = sys.argv[1], int(sys.argv[2])
-    kw, delta_prev, iters = {}, 0.0, 2
+    kw, delta_prev, iters, opts = {}, 0.0, 2, {}
     args = sys.argv[3:]
     while args:
         a = args.pop(0)
@@ -33,6 +33,9 @@ def main():
             delta_prev = float(args.pop(0))
         elif a == "--iters":
             iters = int(args.pop(0))
+        elif a == "--opt":
+            ok_, ov_ = args.pop(0).split("=")
+            opts[ok_] = float(ov_)
         else:
             k, v = a.split("=")
             kw[k] = float(v) if "." in v else int(v)
@@ -46,6 +49,8 @@ def main():
         k.initialize(it)
         if shard is not None:
             k._h.set_option("barrier_timeout_s", 5.0)
+            for ok_, ov_ in opts.items():
+                k._h.set_option(ok_, ov_)
         out = []
         for _ in range(iters):
             k.form_system(it)
@@ -80,6 +85,9 @@ def main():
     for t in ts:
         t.join(timeout=90)
     report = {"gen": gen, "world": world, "errors": errors, "ref": [list(r[:3]) for r in ref], "ranks": []}
+    if not errors and keep[0] is not None:
+        report["split_fronts"] = int(keep[0]._h.info("shard_split"))
+        report["helped"] = [int(k._h.info("shard_helped")) for k in keep if k is not None]
     ok = not errors and all(r is not None for r in res)
     if ok:
         for r in range(world):

@@ -67,6 +67,32 @@ def test_mapping_properties(pkg, gen, kw, world):
         assert h.info("n_tiny") + h.info("n_small") + h.info("n_big") == int((owner == r).sum())
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_split_fronts_are_top_fronts_with_a_rank_range(pkg, world):
+    """ShardMap::split: only top supernodes with rows below the pivot block, the owner is the first rank of
+    the range, non-top supernodes have the one-rank range of their owner; every rank derives the same flags."""
+    prob = problems.pde_control(12, seed=1)
+    seen = None
+    for rank in range(world):
+        h = pkg.Handle(-1)
+        h.set_option("shard_split_flops", 0.0)
+        h.shard_init(rank, world)
+        h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
+        owner = np.array(h.symbolic("owner")); top = np.array(h.symbolic("top")); split = np.array(h.symbolic("split"))
+        ra = np.array(h.symbolic("range_a")); rb = np.array(h.symbolic("range_b"))
+        r = np.diff(np.array(h.symbolic("rowptr")))
+        assert np.all(top[split == 1] == 1) and np.all(r[split == 1] > 0)
+        assert np.all(ra <= owner) and np.all(owner < rb) and np.all(rb <= world)
+        assert np.all(ra[split == 1] == owner[split == 1]) and np.all((rb - ra)[split == 1] >= 2)
+        assert np.all((rb - ra)[top == 0] == 1)
+        # threshold 0: every top front with rows below its pivot block and a range of >= 2 ranks is split
+        assert np.array_equal(split == 1, (top == 1) & (r > 0) & (rb - ra >= 2))
+        cur = (owner.tolist(), split.tolist(), ra.tolist(), rb.tolist())
+        assert seen is None or seen == cur
+        seen = cur
+        h.close()
+
+
 def test_mapping_balances_subtrees(pkg):
     prob = problems.sparse_qp(20000, 10000, seed=0)
     hs = _maps(pkg, prob, 4)
@@ -159,6 +185,20 @@ def test_virtual_ranks_match_single_gpu(gen, kw, world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])      # virtual ranks share one context: more handles than hardware queues stall in the barriers
+@pytest.mark.parametrize("gen,kw", [("sparse_qp", ["n=20000", "m_gen=10000"]), ("pde_control", ["N=16"])])
+def test_virtual_ranks_split_update_blocks(gen, kw, world):
+    """The update blocks of the top separators formed by ALL ranks of the separator's range (the owner
+    factorises the panel, the helpers pull it and store their tiles into the owner's arena): with the
+    split threshold at zero every top front with rows below its pivot block is split; same delta
+    sequence, directions <= 1e-12 against one GPU."""
+    rep = _case(gen, world, *kw, "--opt", "shard_split_flops=0")
+    if world >= 4:       # with two ranks the only top front may be the root (no update block)
+        assert rep["split_fronts"] >= 1 and sum(rep["helped"]) >= 1, rep
+    assert all(r["worst_rel_diff"] <= 1e-12 for r in rep["ranks"])
+
+
+@pytest.mark.gpu
 def test_virtual_ranks_delta_loop_failure_is_seen_by_every_rank():
     # indefinite Hessian: attempts fail on SOME rank (near the accepted delta only in the top
     # separator); every rank must take the same delta decisions (fail bit exchanged at the
@@ -177,7 +217,7 @@ def test_sharded_handle_requires_attached_peers(pkg):
     h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
     with pytest.raises(pkg.OPBError):
         h.form(prob.J.data, prob.H.data, prob.y, prob.s)
-    assert len(h.shard_export()) == 320
+    assert len(h.shard_export()) == 384
 
 
 # --------------------------------------------------------------------------- several GPUs, one process each
