@@ -104,10 +104,13 @@ front_small_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ 
         const int rc = (int)(S.rowptr[ch + 1] - rp);
         const int* __restrict__ relc = S.rel + rp;
         const double* __restrict__ cb = child_cb(S, CB, ch);
-        for (int j = 0; j < rc; j++) {
-            const int pj = relc[j];
-            for (int i = j + tid; i < rc; i += THREADS)
-                F[relc[i] + (size_t)pj * N] += cb[i + (size_t)j * rc];
+        // one flat loop over the child's block (not column by column: a column is a few dozen entries, and
+        // a dependent round of global loads per column made this the longest phase of a small front);
+        // distinct (i, j) of one child land on distinct entries of F
+#pragma unroll 4
+        for (int idx = tid; idx < rc * rc; idx += THREADS) {
+            const int i = idx % rc, j = idx / rc;
+            if (i >= j) F[relc[i] + (size_t)relc[j] * N] += cb[idx];
         }
         __syncthreads();
     }
@@ -363,7 +366,7 @@ void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, c
                           double* Lval, double* CB, double* Xinv, DeltaState* st_d, int mode,
                           int outer_block, int cb_small_k, const ShardCtx* shard, const SideStream* side,
                           KernelTimer* timer, const std::vector<TrtriPlan>* trtri, double* Twork, cudaStream_t st) {
-    bool prev_cross = false;
+    unsigned prev_mask = 0;       // group of the previous level when it read peers' update blocks (see below)
     size_t next_trtri = 0;
     bool aux_busy = false;
     int lvl = -1;
@@ -391,8 +394,9 @@ void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, c
         // finished reading them, because the update-block arena reuses their memory from the
         // next level on (symbolic.cpp, level-lifetime allocator).  The barrier that ends the
         // attempt covers the last level.
-        if (shard && (L.barrier_before || prev_cross)) launch_shard_barrier(*shard, st);
-        prev_cross = L.barrier_before != 0;
+        if (shard && prev_mask) launch_shard_barrier(*shard, prev_mask, st);
+        if (shard && L.barrier_before && L.barrier_mask) launch_shard_barrier(*shard, L.barrier_mask, st);
+        prev_mask = (L.barrier_before || L.split) ? L.barrier_mask : 0u;
         if (timer && timer->phases) timer->put_mark(0, st);
         if (L.count[FC_T32]) {
             front_small_kernel<64><<<L.count[FC_T32], 64, small_smem(L.maxN[FC_T32]), st>>>(
@@ -414,10 +418,11 @@ void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, c
                 // of a split front's range pulls the panel over NVLink and forms its share of the update
                 // block's tiles, storing them into the owner's arena; nobody goes on before all tiles are in.
                 launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, ldlt, outer_block, cb_small_k, side, timer, 1, st);
-                launch_shard_barrier(*shard, st);
+                launch_shard_barrier(*shard, L.barrier_mask, st);
                 launch_pull_panels(S, d_sched + L.help_begin, L.help_count, L.help_maxN, Lval, st_d, st);
                 launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, ldlt, outer_block, cb_small_k, side, timer, 2, st);
-                launch_shard_barrier(*shard, st);
+                launch_shard_barrier(*shard, L.barrier_mask, st);
+                prev_mask = 0;      // that barrier already covers "nobody goes on while a peer still reads" 
             } else {
                 launch_wide_chol_level(S, L, d_sched, Lval, CB, Xinv, st_d, ldlt, outer_block, cb_small_k, side, timer, 0, st);
             }

@@ -35,18 +35,18 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 
 __global__ void __launch_bounds__(32)
-shard_barrier_kernel(ShardCtx C) {
+shard_barrier_kernel(ShardCtx C, unsigned mask) {
     DeltaState* st = C.state;
-    __shared__ unsigned long long s_epoch;
     const int lane = threadIdx.x;
-    if (lane == 0) { s_epoch = *C.epoch + 1; *C.epoch = s_epoch; }
-    __syncwarp();
-    const unsigned long long e = s_epoch;
-    const int slot = (int)(e & 1) * MAX_SHARD;
     const int myfail = *(volatile int*)&st->fail ? 1 : 0;
     __threadfence_system();                      // everything this rank wrote before the barrier
     int peerfail = 0;
-    if (lane < C.world && lane != C.rank) {
+    if (lane < C.world && lane != C.rank && ((mask >> lane) & 1u)) {
+        // pairwise epoch: this rank and peer `lane` have met e - 1 times before (any subset of the ranks
+        // may take part in a barrier, so there is no common count)
+        const unsigned long long e = C.epoch[lane] + 1;
+        C.epoch[lane] = e;
+        const int slot = (int)(e & 1) * MAX_SHARD;
         st_release_sys(C.flags_peer[lane] + slot + C.rank, (e << 1) | (unsigned long long)myfail);
         const long long t0 = clock64();
         unsigned long long v;
@@ -122,8 +122,10 @@ void launch_pull_panels(const DevSym& S, const int* list, int count, int maxN, d
     count_launch();
 }
 
-void launch_shard_barrier(const ShardCtx& C, cudaStream_t st) {
-    shard_barrier_kernel<<<1, 32, 0, st>>>(C);
+void launch_shard_barrier(const ShardCtx& C, unsigned mask, cudaStream_t st) {
+    mask &= (1u << C.world) - 1u;
+    if (!((mask >> C.rank) & 1u) || !(mask & ~(1u << C.rank))) return;      // not taking part / nobody else
+    shard_barrier_kernel<<<1, 32, 0, st>>>(C, mask);
     count_launch();
 }
 

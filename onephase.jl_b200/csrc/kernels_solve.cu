@@ -316,7 +316,7 @@ void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int
     if (shard) side = nullptr;
     for (size_t l = 0; l < plan.size(); l++) {
         const LevelPlan& L = plan[l];
-        if (shard && L.barrier_before) launch_shard_barrier(*shard, st);
+        if (shard && L.barrier_before) launch_shard_barrier(*shard, L.barrier_mask, st);
         // warp per supernode for the tiny class, CTA per supernode above
         const int solo = (wide ? L.all_count - L.count[FC_BIG] : L.all_count) - L.count[FC_T32];
         const bool par = side && wide && L.count[FC_BIG] > 0 && (solo + L.count[FC_T32]) > 0;
@@ -339,12 +339,12 @@ void launch_solve(const DevSym& S, const std::vector<LevelPlan>& plan, const int
         if (par) { cudaEventRecord(side->join, s2); cudaStreamWaitEvent(st, side->join, 0); }
         if (shard) {
             launch_push_supernodes(S, d_sched + L.push_begin, L.push_count, L.push_maxc, x, st);
-            if (L.barrier_before) launch_shard_barrier(*shard, st);
+            if (L.barrier_before) launch_shard_barrier(*shard, L.barrier_mask, st);
         }
     }
     if (shard) {
         launch_push_owned(S, colowner, x, st);
-        launch_shard_barrier(*shard, st);
+        launch_shard_barrier(*shard, shard_all(*shard), st);
     }
 }
 

@@ -97,7 +97,10 @@ static void build_plan(Bundle& B) {
         LevelPlan& L = B.plan[l];
         std::vector<int> cls[NFC];
         std::vector<int> push;
-        if (sharded) { L.barrier_before = B.shard.level_barrier[l]; L.split = B.shard.level_split[l]; }
+        if (sharded) {
+            L.barrier_before = B.shard.level_barrier[l]; L.split = B.shard.level_split[l];
+            L.barrier_mask = B.shard.level_mask[(size_t)l * B.world + B.rank];
+        }
         std::vector<int> helped;          // split fronts of other ranks this rank forms update-block tiles of
         for (int t = S.level_ptr[l]; t < S.level_ptr[l + 1]; t++) {
             const int s = S.level_list[t];
@@ -279,7 +282,7 @@ struct opb_handle {
     int shard_rank = 0, shard_world = 1;
     DevSym dev{};                        // B->dev plus this handle's peer pointers
     ShardCtx sctx{};
-    unsigned long long* d_flags = nullptr;   // [2][MAX_SHARD] flags, [16] epoch, [17] error
+    unsigned long long* d_flags = nullptr;   // [2][MAX_SHARD] flags, [16 .. 24) pairwise epochs, [24] error
     bool peer_ok[MAX_SHARD] = {false};
     void* peer_ipc[MAX_SHARD][5] = {{nullptr}};
     std::string peer_blob[MAX_SHARD];
@@ -498,7 +501,7 @@ int opb_shard_init(opb_handle* h, int rank, int world) {
         h->sctx.flags_local = h->d_flags;
         h->sctx.flags_peer[rank] = h->d_flags;
         h->sctx.epoch = h->d_flags + 2 * MAX_SHARD;
-        h->sctx.error = reinterpret_cast<int*>(h->d_flags + 2 * MAX_SHARD + 1);
+        h->sctx.error = reinterpret_cast<int*>(h->d_flags + 3 * MAX_SHARD);
         h->sctx.state = h->d_state;
         h->sctx.timeout_clocks = (long long)(h->barrier_timeout_s * 2.0e9);
     }
@@ -771,7 +774,7 @@ static void enqueue_attempt_raw(opb_handle* h, KernelTimer* timer = nullptr, uns
                          h->outer_block, h->cb_small_k, h->shard_ctx(), (h->lookahead && (!timer || timer->phases)) ? &h->side : nullptr, timer,
                          h->fmode() != FMODE_LDLT_SCALAR ? &B.trtri : nullptr, h->Twork.p, st);
     // sharded: every rank learns about a failed pivot anywhere before the delta rule is applied
-    if (h->sharded()) launch_shard_barrier(h->sctx, st);
+    if (h->sharded()) launch_shard_barrier(h->sctx, shard_all(h->sctx), st);
     if (loop_handle) launch_ctl_end_loop(h->d_state, loop_handle, st);
     else launch_ctl_end(h->d_state, st);
 }
@@ -836,14 +839,14 @@ static int read_state(opb_handle* h) {
         h->loop_pending = 0;
     }
     if (shard_err) {
-        unsigned long long f[2 * MAX_SHARD + 2] = {0};
+        unsigned long long f[32] = {0};
         cudaMemcpy(f, h->d_flags, sizeof f, cudaMemcpyDeviceToHost);
-        char buf[512];
-        int o = snprintf(buf, sizeof buf, "sharded instance: a peer GPU did not reach the barrier (timeout); rank %d/%d epoch %llu, peers' (epoch,fail):",
-                         h->shard_rank, h->shard_world, f[2 * MAX_SHARD]);
-        for (int sl = 0; sl < 2; sl++)
-            for (int p = 0; p < h->shard_world && o < 480; p++)
-                o += snprintf(buf + o, sizeof buf - o, " s%d[%d]=(%llu,%llu)", sl, p, f[sl * MAX_SHARD + p] >> 1, f[sl * MAX_SHARD + p] & 1);
+        char buf[640];
+        int o = snprintf(buf, sizeof buf, "sharded instance: a peer GPU did not reach the barrier (timeout); rank %d/%d, per peer (own epoch | peer's flags (epoch,fail) in slots 0/1):",
+                         h->shard_rank, h->shard_world);
+        for (int p = 0; p < h->shard_world && o < 600; p++)
+            o += snprintf(buf + o, sizeof buf - o, " [%d] %llu | (%llu,%llu) (%llu,%llu)", p, f[2 * MAX_SHARD + p],
+                          f[p] >> 1, f[p] & 1, f[MAX_SHARD + p] >> 1, f[MAX_SHARD + p] & 1);
         return h->fail(OPB_ERR_INTERNAL, buf);
     }
     return OPB_OK;
@@ -1012,7 +1015,6 @@ int opb_profile_factor(opb_handle* h, double delta, double* total_ms, double* cb
 int opb_profile_levels(opb_handle* h, double delta, double* out, int cap, int* nlevels_out, double* total_ms) {
     int rc = need_device(h); if (rc) return rc;
     if (!h->B || h->ready == opb_handle::NOT_READY) return h->fail(OPB_ERR_STATE, "kkt solver not ready to factor (form_system first)");
-    if (h->sharded()) return h->fail(OPB_ERR_INVALID, "opb_profile_levels is not available on a sharded handle");
     h->mode = OPB_MODE_CHOLESKY;
     cudaStream_t st = h->stream;
     KernelTimer& T = h->ktimer;
@@ -1325,7 +1327,7 @@ int opb_get_info(opb_handle* h, const char* key, double* out) {
     else if (k == "shard_world") *out = B.world;
     else if (k == "shard_load") *out = B.world > 1 ? B.shard.load[B.rank] : S.flops;
     else if (k == "shard_top_flops") *out = B.world > 1 ? B.shard.top_flops : 0.0;
-    else if (k == "shard_barriers") { int c = 0; for (const LevelPlan& L : B.plan) c += L.barrier_before + 2 * L.split; *out = c; }
+    else if (k == "shard_barriers") { int c = 0; for (const LevelPlan& L : B.plan) if (L.barrier_mask) c += L.barrier_before + 2 * L.split; *out = c; }
     else if (k == "shard_split") { int c = 0; if (B.world > 1) for (char f : B.shard.split) c += f; *out = c; }
     else if (k == "shard_helped") { int c = 0; for (const LevelPlan& L : B.plan) c += L.help_count; *out = c; }
     else return h->fail(OPB_ERR_INVALID, "unknown info key " + k);
@@ -1362,6 +1364,11 @@ int64_t opb_get_symbolic(opb_handle* h, const char* name, int64_t* out, int64_t 
     if (k == "tcut_ptr") return copy_out(S.tcut_ptr, out, cap);
     if (k == "tcut") return copy_out(S.tcut, out, cap);
     if (k == "owner") { if (B.world > 1) return copy_out(B.shard.owner, out, cap); return copy_out(std::vector<int>(S.nsuper, 0), out, cap); }
+    if (k == "level_mask") {      // per level: the ranks THIS rank synchronises with (bit mask, 0 = none)
+        std::vector<int> t(S.nlevels, 0);
+        if (B.world > 1) for (int l = 0; l < S.nlevels; l++) t[l] = (int)B.shard.level_mask[(size_t)l * B.world + B.rank];
+        return copy_out(t, out, cap);
+    }
     if (k == "split") { std::vector<int> t(S.nsuper, 0); if (B.world > 1) for (int q = 0; q < S.nsuper; q++) t[q] = B.shard.split[q]; return copy_out(t, out, cap); }
     if (k == "range_a") { if (B.world > 1) return copy_out(B.shard.ra, out, cap); return copy_out(std::vector<int>(S.nsuper, 0), out, cap); }
     if (k == "range_b") { if (B.world > 1) return copy_out(B.shard.rb, out, cap); return copy_out(std::vector<int>(S.nsuper, 1), out, cap); }

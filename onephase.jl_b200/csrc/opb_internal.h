@@ -89,12 +89,13 @@ __device__ __forceinline__ double gather_dest(const DevSym& S, const double* u, 
 }
 
 // Cross-GPU barrier state of a sharded handle: every rank owns 2 x MAX_SHARD flag words that
-// its peers write over NVLink ((epoch << 1) | fail, slot = epoch & 1) and a local epoch counter.
+// its peers write over NVLink ((epoch << 1) | fail, slot = epoch & 1) and MAX_SHARD local epoch counters
+// (one per peer: a barrier may involve a subset of the ranks, so the counts are kept pair by pair).
 struct ShardCtx {
     int rank, world;
     unsigned long long* flags_local;            // [2][MAX_SHARD]
     unsigned long long* flags_peer[MAX_SHARD];  // the same array on every rank
-    unsigned long long* epoch;                  // local barrier counter
+    unsigned long long* epoch;                  // local counters, one per peer: barriers done together with that peer
     int* error;                                 // local: set to 1 when a wait timed out
     long long timeout_clocks;                   // a wait gives up after this many SM clocks
     DeltaState* state;                          // local controller state (fail bit exchanged at every barrier)
@@ -163,6 +164,7 @@ struct LevelPlan {
     // child on another rank); push_count = top supernodes of this rank on the level, whose solution
     // is pushed to every peer in the backward sweep
     int barrier_before = 0, push_count = 0, push_begin = 0, push_maxc = 0;
+    unsigned barrier_mask = 0;                 // ... with these ranks (bit mask incl. this rank; 0: nobody to wait for)
     // sharded instance: the level has split fronts (ShardMap::split): two more barriers, and the split
     // fronts of other ranks whose update-block tiles this rank forms (positions right behind the wide list)
     int split = 0, help_begin = 0, help_count = 0, help_maxN = 0;
@@ -285,7 +287,8 @@ cudaError_t preload_dense();
 cudaError_t preload_shard();
 
 // ---- kernels_shard.cu  (cross-GPU barrier over peer-mapped flags, solution pushes)
-void launch_shard_barrier(const ShardCtx& C, cudaStream_t st);
+void launch_shard_barrier(const ShardCtx& C, unsigned mask, cudaStream_t st);      // mask: participating ranks
+inline unsigned shard_all(const ShardCtx& C) { return (1u << C.world) - 1u; }
 void launch_push_supernodes(const DevSym& S, const int* list, int count, int maxc, const double* x, cudaStream_t st);
 void launch_push_owned(const DevSym& S, const int* colowner, const double* x, cudaStream_t st);
 void launch_pull_panels(const DevSym& S, const int* list, int count, int maxN, double* Lval, const DeltaState* st_d, cudaStream_t st);

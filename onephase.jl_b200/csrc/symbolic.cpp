@@ -1044,6 +1044,26 @@ void shard_map(const Symbolic& S, int world, double split_flops, ShardMap& out) 
         const int p = S.sparent[s];
         if (p >= 0 && out.owner[p] != out.owner[s]) out.level_barrier[S.level[p]] = 1;
     }
+    // synchronisation groups per level (union-find over the ranks)
+    const int nl = std::max(1, S.nlevels), Wd = out.world;
+    out.level_mask.assign((size_t)nl * Wd, 0u);
+    std::vector<int> uf((size_t)nl * Wd);
+    for (int l = 0; l < nl; l++) for (int r = 0; r < Wd; r++) uf[(size_t)l * Wd + r] = r;
+    auto find = [&](int l, int r) { int* u = uf.data() + (size_t)l * Wd; while (u[r] != r) { u[r] = u[u[r]]; r = u[r]; } return r; };
+    auto unite = [&](int l, int a, int b) { a = find(l, a); b = find(l, b); if (a != b) uf[(size_t)l * Wd + std::max(a, b)] = std::min(a, b); };
+    for (int s = 0; s < NS; s++) {
+        const int p = S.sparent[s];
+        if (p >= 0 && out.owner[p] != out.owner[s]) unite(S.level[p], out.owner[p], out.owner[s]);
+        if (out.split[s]) for (int q = out.ra[s] + 1; q < out.rb[s]; q++) unite(S.level[s], out.ra[s], q);
+    }
+    for (int l = 0; l < nl; l++) {
+        std::vector<unsigned> comp(Wd, 0u);
+        for (int r = 0; r < Wd; r++) comp[find(l, r)] |= 1u << r;
+        for (int r = 0; r < Wd; r++) {
+            const unsigned m = comp[find(l, r)];
+            out.level_mask[(size_t)l * Wd + r] = (m & (m - 1)) ? m : 0u;      // a component of one rank needs no barrier
+        }
+    }
 }
 
 }  // namespace opb

@@ -112,6 +112,11 @@ struct ShardMap {
     // The owner factorises the panel; the helpers pull it over NVLink and store their tiles into the
     // owner's update-block arena.  level_split: the level has such a supernode (every rank runs the
     // two extra barriers of that level).
+    // level_mask[l * world + r]: the ranks rank r synchronises with at level l (bit mask incl. r itself, 0 = no
+    // barrier for r): the connected component of r under "owner of a supernode of the level <-> owner of one
+    // of its children" and "ranks of a split front's range".  Ranks whose subtrees are private at a level do
+    // not wait for anybody there.
+    std::vector<unsigned> level_mask;
     std::vector<char> split, level_split;
     std::vector<int> ra, rb;
     std::vector<double> load;            // per rank: flops of the supernodes it owns

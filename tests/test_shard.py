@@ -54,7 +54,11 @@ def test_mapping_properties(pkg, gen, kw, world):
             barrier_levels.add(int(level[p]))
         if not top[p]:
             assert owner[p] == owner[s] and not top[s], "below the top the tree is private to one rank"
-    assert hs[0].info("shard_barriers") == len(barrier_levels)
+    # a rank takes part in the barrier of a level only when it is connected to a cross-rank edge there
+    nb = [h.info("shard_barriers") for h in hs]
+    assert all(0 <= b <= len(barrier_levels) for b in nb) and (not barrier_levels or max(nb) >= 1)
+    for l in barrier_levels:
+        assert sum(1 for h in hs if h.symbolic("level_mask")[l] != 0) >= 2
     # loads = flops of the (amalgamated) supernode panels each rank owns
     sf = hs[0].symbolic("sfirst"); rp = hs[0].symbolic("rowptr")
     c = np.diff(sf).astype(float); N = c + np.diff(rp)
@@ -91,6 +95,45 @@ def test_split_fronts_are_top_fronts_with_a_rank_range(pkg, world):
         assert seen is None or seen == cur
         seen = cur
         h.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_barrier_groups_are_consistent(pkg, world):
+    """ShardMap::level_mask: at every level the ranks fall into groups that synchronise among themselves
+    only -- every rank of a group holds the same mask, the owners of a supernode and of its children on
+    other ranks share a group at the supernode's level, and so do the ranks of a split front's range."""
+    prob = problems.pde_control(12, seed=1)
+    masks, meta = [], None
+    for rank in range(world):
+        h = pkg.Handle(-1)
+        h.set_option("shard_split_flops", 0.0)
+        h.shard_init(rank, world)
+        h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
+        masks.append(np.array(h.symbolic("level_mask")))
+        if meta is None:
+            meta = [np.array(h.symbolic(k)) for k in ("owner", "sparent", "level", "split", "range_a", "range_b")]
+        h.close()
+    owner, par, level, split, ra, rb = meta
+    nl = len(masks[0])
+    for l in range(nl):
+        for r in range(world):
+            m = int(masks[r][l])
+            if m == 0:
+                continue
+            assert (m >> r) & 1 and m != (1 << r)
+            for q in range(world):
+                if (m >> q) & 1:
+                    assert int(masks[q][l]) == m, (l, r, q)
+    for s in range(len(par)):
+        p = par[s]
+        if p >= 0 and owner[p] != owner[s]:
+            m = int(masks[owner[p]][level[p]])
+            assert (m >> owner[s]) & 1 and (m >> owner[p]) & 1
+        if split[s]:
+            m = int(masks[owner[s]][level[s]])
+            assert all((m >> q) & 1 for q in range(ra[s], rb[s]))
+    # private subtrees do not wait for anybody at the low levels
+    assert all(int(masks[r][0]) == 0 for r in range(world))
 
 
 def test_mapping_balances_subtrees(pkg):

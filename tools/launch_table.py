@@ -13,7 +13,7 @@ def table(path, first=0, last=None):
     for r in rows[hi + 1:]:
         if len(r) <= vi:
             continue
-        name = r[ki].split("(")[0].replace("opb::", "").replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
+        name = r[ki].split("(")[0].replace("void ", "").strip().rsplit(">::", 1)[-1].replace("opb::", "")
         try:
             v = float(r[vi].replace(",", ""))
         except ValueError:

@@ -17,9 +17,20 @@ def main():
     pkg = g.package()
     gen, kw = bench.WORKLOADS[wl][0], bench.WORKLOADS[wl][1]
     prob = getattr(g.problems(), gen)(**kw)
-    pars = pkg.Class_parameters()
+    # under torchrun: ONE instance sharded over the ranks, every rank prints its own table
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, shard, dev = 0, None, 0
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        dev = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+        rank = dist.get_rank()
+        shard = pkg.DistShard()
+    pars = pkg.Class_parameters(device=dev)
     it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=0.0)
-    k = pkg.pick_KKT_solver(pars)
+    k = pkg.pick_KKT_solver(pars, shard=shard)
     k.initialize(it)
     for o in opts:
         key, val = o.split("=")
@@ -31,7 +42,24 @@ def main():
     for rep in range(2):
         P = h.profile_levels(0.0)
     T = P["levels"]
-    print("resident CTAs per SM of the 64-row-tile kernels:", h.info("occ_small_tiles"))
+    if world > 1:
+        import io
+        import contextlib
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            report(wl, h, P, T, lev, c, r, N, "rank %d of %d: " % (rank, world))
+        for q in range(world):
+            dist.barrier()
+            if q == rank:
+                sys.stdout.write(buf.getvalue()); sys.stdout.flush()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+    report(wl, h, P, T, lev, c, r, N, "")
+
+
+def report(wl, h, P, T, lev, c, r, N, tag):
+    print(tag + "resident CTAs per SM of the 64-row-tile kernels:", h.info("occ_small_tiles"))
     print("workload %s  total %.2f ms  fill %.2f  trtri %.2f   (columns: ms before the big panels | big panels | update blocks)"
           % (wl, P["total_ms"], P["fill_ms"], P["trtri_ms"]))
     print("%3s %6s %7s %7s %10s %10s %8s %8s %8s %7s %7s" % ("lvl", "fronts", "max c", "max N", "panel Gf", "cb Gf", "pre", "panel", "cb", "pan TF", "cb TF"))
