@@ -397,6 +397,8 @@ void launch_factor_levels(const DevSym& S, const std::vector<LevelPlan>& plan, c
         if (shard && prev_mask) launch_shard_barrier(*shard, prev_mask, st);
         if (shard && L.barrier_before && L.barrier_mask) launch_shard_barrier(*shard, L.barrier_mask, st);
         prev_mask = (L.barrier_before || L.split) ? L.barrier_mask : 0u;
+        // children on other ranks (complete now): bulk copies of their update blocks into this rank's arena
+        if (shard && L.pullcb_count) launch_pull_cb(S, d_sched + L.pullcb_begin, L.pullcb_count, L.pullcb_maxR, CB, st_d, st);
         if (timer && timer->phases) timer->put_mark(0, st);
         if (L.count[FC_T32]) {
             front_small_kernel<64><<<L.count[FC_T32], 64, small_smem(L.maxN[FC_T32]), st>>>(

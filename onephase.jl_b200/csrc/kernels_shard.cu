@@ -111,7 +111,37 @@ pull_panels_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ 
     for (; j < j1; j++) dst[(size_t)j * ld] = src[(size_t)j * ld];
 }
 
+// update blocks of children on other ranks: the lower triangle of the r x r block from the owner's arena into
+// this rank's arena, same offset
+__global__ void __launch_bounds__(PULL_ROWS)
+pull_cb_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ CB, const DeltaState* st) {
+    if (*(volatile const int*)&st->done | *(volatile const int*)&st->fail) return;
+    const int s = list[blockIdx.z];
+    const int r = (int)(S.rowptr[s + 1] - S.rowptr[s]);
+    const int i = blockIdx.x * PULL_ROWS + threadIdx.x;
+    const int j0 = blockIdx.y * PULL_COLS;
+    if (i >= r || j0 >= r || j0 > i) return;
+    const double* __restrict__ src = S.cb_peer[S.owner[s]] + S.CBoff[s] + i;
+    double* __restrict__ dst = CB + S.CBoff[s] + i;
+    const int j1 = min(min(r, j0 + PULL_COLS), i + 1);       // lower triangle: columns <= row
+    int j = j0;
+    for (; j + 4 <= j1; j += 4) {
+        const double v0 = src[(size_t)j * r], v1 = src[(size_t)(j + 1) * r];
+        const double v2 = src[(size_t)(j + 2) * r], v3 = src[(size_t)(j + 3) * r];
+        dst[(size_t)j * r] = v0; dst[(size_t)(j + 1) * r] = v1; dst[(size_t)(j + 2) * r] = v2; dst[(size_t)(j + 3) * r] = v3;
+    }
+    for (; j < j1; j++) dst[(size_t)j * r] = src[(size_t)j * r];
+}
+
 }  // namespace
+
+void launch_pull_cb(const DevSym& S, const int* list, int count, int maxR, double* CB, const DeltaState* st_d,
+                    cudaStream_t st) {
+    if (count <= 0 || maxR <= 0) return;
+    dim3 g((maxR + PULL_ROWS - 1) / PULL_ROWS, (maxR + PULL_COLS - 1) / PULL_COLS, count);
+    pull_cb_kernel<<<g, PULL_ROWS, 0, st>>>(S, list, CB, st_d);
+    count_launch();
+}
 
 void launch_pull_panels(const DevSym& S, const int* list, int count, int maxN, double* Lval, const DeltaState* st_d,
                         cudaStream_t st) {
@@ -150,6 +180,7 @@ cudaError_t preload_shard() {
     e = cudaFuncGetAttributes(&a, push_supernodes_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, push_owned_kernel); if (e != cudaSuccess) return e;
     e = cudaFuncGetAttributes(&a, pull_panels_kernel); if (e != cudaSuccess) return e;
+    e = cudaFuncGetAttributes(&a, pull_cb_kernel); if (e != cudaSuccess) return e;
     return cudaSuccess;
 }
 

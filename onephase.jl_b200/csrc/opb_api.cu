@@ -54,6 +54,8 @@ struct Bundle {
     int rank = 0, world = 1;
     ShardMap shard;
     std::vector<int> colowner;   // per permuted column: owning rank
+    std::vector<unsigned char> cb_mirror;   // per supernode: this rank mirrors its update block before the parent's level
+    DBuf<unsigned char> d_cb_mirror;
     DBuf<int> d_owner, d_colowner;
     int device = -1;
     size_t device_bytes = 0;
@@ -72,7 +74,7 @@ struct Bundle {
         d_Mp.release(); d_src.release(); d_Xoff.release(); d_pair_ptr.release(); d_Jp.release(); d_Rp.release(); d_Sp.release();
         d_pairA.release(); d_pairB.release(); d_hmap.release(); d_Jrow.release(); d_Rcol.release();
         d_Rpos.release(); d_Scol.release(); d_Spos.release();
-        d_owner.release(); d_colowner.release(); d_gptr.release(); d_gsrc.release(); d_gch.release();
+        d_owner.release(); d_colowner.release(); d_cb_mirror.release(); d_gptr.release(); d_gsrc.release(); d_gch.release();
         d_tcut_ptr.release(); d_tcut.release();
     }
 };
@@ -89,6 +91,7 @@ static void build_plan(Bundle& B) {
     B.n_tiny = B.n_small = B.n_big = 0;
     B.Xoff.assign(S.nsuper, -1);
     B.x_total = 0;
+    B.cb_mirror.assign(S.nsuper, 0);
     auto cols = [&](int s) { return S.sfirst[s + 1] - S.sfirst[s]; };
     auto rows = [&](int s) { return cols(s) + (int)(S.rowptr[s + 1] - S.rowptr[s]); };
     std::vector<int> all_big;
@@ -157,6 +160,26 @@ static void build_plan(Bundle& B) {
         L.help_count = (int)helped.size();
         B.sched.insert(B.sched.end(), helped.begin(), helped.end());
         for (int s : helped) L.help_maxN = std::max(L.help_maxN, rows(s));
+        if (sharded) {
+            // remote children of the fronts this rank factorises or helps with at this level: mirrored into the
+            // local arena, except under long-K split fronts (c > 6000 with an update block), where the fine-grained
+            // peer loads hide behind the K loop and the copies would only add link traffic
+            L.pullcb_begin = (int)B.sched.size();
+            auto consider = [&](int p) {
+                if (cols(p) > 6000 && rows(p) > cols(p)) return;
+                for (int k = S.child_ptr[p]; k < S.child_ptr[p + 1]; k++) {
+                    const int c = S.child_list[k];
+                    const int rc = rows(c) - cols(c);
+                    if (B.shard.owner[c] == B.rank || rc <= 0) continue;
+                    B.sched.push_back(c);
+                    B.cb_mirror[c] = 1;
+                    L.pullcb_maxR = std::max(L.pullcb_maxR, rc);
+                }
+            };
+            for (int q = 0; q < L.all_count; q++) consider(B.sched[L.all_begin + q]);
+            for (int s : helped) consider(s);
+            L.pullcb_count = (int)B.sched.size() - L.pullcb_begin;
+        }
         L.push_begin = (int)B.sched.size();
         L.push_count = (int)push.size();
         B.sched.insert(B.sched.end(), push.begin(), push.end());
@@ -584,7 +607,7 @@ static int upload_bundle(opb_handle* h, Bundle& B) {
     CK(B.d_Xoff.upload(B.Xoff, st));
     CK(B.d_gptr.upload(S.gptr, st)); CK(B.d_gsrc.upload(S.gsrc, st)); CK(B.d_gch.upload(S.gch, st));
     CK(B.d_tcut_ptr.upload(S.tcut_ptr, st)); CK(B.d_tcut.upload(S.tcut, st));
-    if (B.world > 1) { CK(B.d_owner.upload(B.shard.owner, st)); CK(B.d_colowner.upload(B.colowner, st)); }
+    if (B.world > 1) { CK(B.d_owner.upload(B.shard.owner, st)); CK(B.d_colowner.upload(B.colowner, st)); CK(B.d_cb_mirror.upload(B.cb_mirror, st)); }
     {
         // diagonal entries carry a flag so the scatter kernel adds delta to them
         std::vector<int64_t> amap = S.amap;
@@ -613,6 +636,7 @@ static int upload_bundle(opb_handle* h, Bundle& B) {
     B.dev.gptr = B.d_gptr.p; B.dev.gsrc = B.d_gsrc.p; B.dev.gch = B.d_gch.p;
     B.dev.tcut_ptr = B.d_tcut_ptr.p; B.dev.tcut = B.d_tcut.p;
     B.dev.owner = B.world > 1 ? B.d_owner.p : nullptr;
+    B.dev.cb_mirror = B.world > 1 ? B.d_cb_mirror.p : nullptr;
     B.dev.rank = B.rank; B.dev.world = B.world;
     return OPB_OK;
 }
@@ -1329,6 +1353,7 @@ int opb_get_info(opb_handle* h, const char* key, double* out) {
     else if (k == "shard_top_flops") *out = B.world > 1 ? B.shard.top_flops : 0.0;
     else if (k == "shard_barriers") { int c = 0; for (const LevelPlan& L : B.plan) if (L.barrier_mask) c += L.barrier_before + 2 * L.split; *out = c; }
     else if (k == "shard_split") { int c = 0; if (B.world > 1) for (char f : B.shard.split) c += f; *out = c; }
+    else if (k == "shard_mirrored") { int c = 0; for (const LevelPlan& L : B.plan) c += L.pullcb_count; *out = c; }
     else if (k == "shard_helped") { int c = 0; for (const LevelPlan& L : B.plan) c += L.help_count; *out = c; }
     else return h->fail(OPB_ERR_INVALID, "unknown info key " + k);
     return OPB_OK;

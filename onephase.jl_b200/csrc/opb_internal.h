@@ -63,6 +63,7 @@ struct DevSym {
     const int* tcut;
     // ---- one instance sharded over several GPUs; owner == nullptr on a single GPU
     const int* owner;     // per supernode: rank that owns it
+    const unsigned char* cb_mirror;   // per supernode: its update block is mirrored into this rank's arena before its parent's level
     int rank, world;
     double* cb_peer[MAX_SHARD];   // update-block buffer of every rank (peer-mapped; [rank] = own)
     double* l_peer[MAX_SHARD];    // factor storage of every rank (helpers pull the panels of split fronts)
@@ -73,8 +74,10 @@ struct DevSym {
 // update block / forward update vector of child `ch`: in the owner's HBM, read over NVLink when
 // the child belongs to another rank (the reduction of the subtree roots' update blocks onto the
 // separator front happens inside the consuming extend-add, not as a separate collective)
+// (cb_mirror[ch] != 0: this rank has pulled a copy of the block into its own arena -- same offset, the slot
+// is free on every rank that does not own the child -- before the level started: pull_cb_kernel)
 __device__ __forceinline__ const double* child_cb(const DevSym& S, const double* CB, int ch) {
-    return (S.owner ? S.cb_peer[S.owner[ch]] : CB) + S.CBoff[ch];
+    return ((S.owner && !S.cb_mirror[ch]) ? S.cb_peer[S.owner[ch]] : CB) + S.CBoff[ch];
 }
 __device__ __forceinline__ const double* child_u(const DevSym& S, const double* u, int ch) {
     return (S.owner ? S.u_peer[S.owner[ch]] : u) + S.rowptr[ch];
@@ -168,6 +171,9 @@ struct LevelPlan {
     // sharded instance: the level has split fronts (ShardMap::split): two more barriers, and the split
     // fronts of other ranks whose update-block tiles this rank forms (positions right behind the wide list)
     int split = 0, help_begin = 0, help_count = 0, help_maxN = 0;
+    // children on other ranks whose update blocks this rank copies into its own arena before the level
+    // (fine-grained peer loads inside the consuming kernels run at a few percent of the link rate)
+    int pullcb_begin = 0, pullcb_count = 0, pullcb_maxR = 0;
 };
 
 // ---- kernels_assembly.cu
@@ -291,6 +297,7 @@ void launch_shard_barrier(const ShardCtx& C, unsigned mask, cudaStream_t st);   
 inline unsigned shard_all(const ShardCtx& C) { return (1u << C.world) - 1u; }
 void launch_push_supernodes(const DevSym& S, const int* list, int count, int maxc, const double* x, cudaStream_t st);
 void launch_push_owned(const DevSym& S, const int* colowner, const double* x, cudaStream_t st);
+void launch_pull_cb(const DevSym& S, const int* list, int count, int maxR, double* CB, const DeltaState* st_d, cudaStream_t st);
 void launch_pull_panels(const DevSym& S, const int* list, int count, int maxN, double* Lval, const DeltaState* st_d, cudaStream_t st);
 
 // ---- kernels_solve.cu
