@@ -113,11 +113,12 @@ mutable struct Schur_B200_KKT_solver <: abstract_schur_solver
     _diag_min::Float64
     _shard_rank::Int                       # one instance over several GPUs (shard_init!); world 1 = off
     _shard_world::Int
+    _allgather::Union{Function,Nothing}    # transport of the 384-byte descriptors (shard_init!)
     function Schur_B200_KKT_solver()
         this = new()
         this.ready = :not_ready
         this._h = nothing; this._pattern = 0; this._delta = 0.0; this._diag_min = NaN
-        this._shard_rank = 0; this._shard_world = 1
+        this._shard_rank = 0; this._shard_world = 1; this._allgather = nothing
         return this
     end
 end
@@ -138,6 +139,9 @@ function form_system!(kkt_solver::Schur_B200_KKT_solver, iter::Class_iterate, ti
                            (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Cint),
                            h.ptr, size(J, 2), size(J, 1), J.colptr, J.rowval, H.colptr, H.rowval, 1))
         kkt_solver._pattern = pat
+        # sharded instance: the peer buffers belong to the structure, so the ranks exchange their
+        # descriptors again (every rank takes this branch in the same call: same data, same pattern)
+        kkt_solver._shard_world > 1 && shard_attach!(kkt_solver, kkt_solver._allgather)
     end
     n = size(J, 2)
     kkt_solver.schur_diag = Vector{Float64}(undef, n)
@@ -206,18 +210,26 @@ end
 #     my_kkt_solver = Schur_B200_KKT_solver()
 #     linear_solver_type == :b200 || error("pick a valid solver!")
 #     my_kkt_solver.ls_solver = linear_solver_B200(:definite, safe, recycle)
+# and, for the symmetric formulation (the reference's generic Symmetric_KKT_solver, symmetric.jl:35-102,
+# runs unchanged on top of the L1 plugin: LDL' on the tensor path, inertia (n, m)), one more case in the
+# existing `:symmetric` branch (kkt_system_solver.jl:240-249):
+#     elseif linear_solver_type == :b200
+#       my_kkt_solver.ls_solver = linear_solver_B200(:symmetric, safe, recycle)
 
 # ---------------------------------------------------------------------------------------------
 # One instance over several GPUs (include/onephase_b200.h, opb_shard_*): one Julia process per GPU,
 # every process making the same calls with the same data.  `allgather(blob)::Vector{Vector{UInt8}}`
 # is any transport the host program has (MPI.Allgather, Distributed.jl, a file): only these 384
 # bytes per rank travel through it, the numeric data moves between the GPUs inside the kernels.
-#   shard_init!(kkt_solver, rank, world)        before the first form_system!
-#   shard_attach!(kkt_solver, allgather)        after every opb_set_structure (form_system! calls it)
-function shard_init!(kkt_solver::Schur_B200_KKT_solver, rank::Integer, world::Integer)
+#   shard_init!(kkt_solver, rank, world, allgather)   after initialize!, before the first form_system!;
+#                                                     form_system! then calls shard_attach! after every
+#                                                     opb_set_structure, like kkt.py's _attach_peers
+# EXPERIMENTAL: like the rest of this file it has never run (no Julia toolchain where it was written); the
+# Python host (onephase.jl_b200/kkt.py, DistShard) is the exercised twin of this code path.
+function shard_init!(kkt_solver::Schur_B200_KKT_solver, rank::Integer, world::Integer, allgather::Function)
     opb_check(kkt_solver._h, ccall((:opb_shard_init, LIBOPB), Cint, (Ptr{Cvoid}, Cint, Cint),
                                    kkt_solver._h.ptr, rank, world))
-    kkt_solver._shard_rank = rank; kkt_solver._shard_world = world
+    kkt_solver._shard_rank = rank; kkt_solver._shard_world = world; kkt_solver._allgather = allgather
 end
 
 function shard_attach!(kkt_solver::Schur_B200_KKT_solver, allgather::Function)

@@ -1,6 +1,6 @@
 """Per-kernel time and DRAM bytes of one step from an ncu launch list taken with
 --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv:
-    python tools/dram_table.py launches.csv [out.json]
+    python tools/dram_table.py launches.csv [out.json [workload]]
 Prints a per-kernel table for the LAST real factorisation attempt + the rest of the step and, with out.json,
 writes the totals bench.py reads as `roofline.traffic`."""
 import collections
@@ -54,15 +54,24 @@ def main():
         print("%-44s %7d %11.3f %6.2f%% %10.3f %10.3f %9.0f" % (k[:44], t[0], t[1] / 1e3, 100 * t[1] / T, t[2] / 1e9, t[3] / 1e9,
                                                         (t[2] + t[3]) / max(t[1], 1e-9) / 1e3))
     if len(sys.argv) > 2:
-        fac = {"front_cb", "chol_panel_update", "chol_trsm", "chol_diag", "big_extend_add_panel", "zero_kernel", "scatter_kernel",
-               "front_small", "mid_panel", "trtri_merge"}
-        def is_fac(n):
-            return any(n.startswith(f) for f in fac)
-        out = {"factor_bytes_per_step": sum(t[2] + t[3] for k, t in tot.items() if is_fac(k)),
-               "front_cb_bytes_per_step": sum(t[2] + t[3] for k, t in tot.items() if k.startswith("front_cb")),
-               "panel_update_bytes_per_step": sum(t[2] + t[3] for k, t in tot.items() if k.startswith("chol_panel_update")),
-               "solve_and_vector_bytes_per_step": sum(t[2] + t[3] for k, t in tot.items() if not is_fac(k)),
-               "source": sys.argv[1]}
+        workload = sys.argv[3] if len(sys.argv) > 3 else "c5_pde_100"
+        fac = ("front_cb", "chol_panel_update", "chol_trsm", "chol_diag", "big_extend_add_panel", "zero_kernel", "scatter_kernel",
+               "front_small", "mid_panel", "trtri_merge", "ctl_")
+        asm = ("prep_kernel", "assemble_M", "diag_extract")
+
+        def is_in(n, names):
+            return any(n.startswith(f) for f in names)
+        by = lambda names: sum(t[2] + t[3] for k, t in tot.items() if is_in(k, names))      # noqa: E731
+        rest = sum(t[2] + t[3] for k, t in tot.items() if not is_in(k, fac) and not is_in(k, asm))
+        out = {workload: {
+            "factor_bytes_per_attempt": by(fac),
+            "front_cb_bytes_per_attempt": by(("front_cb",)),
+            "panel_update_bytes_per_attempt": by(("chol_panel_update",)),
+            "assembly_bytes": by(asm),
+            "direction_bytes": rest / 2.0,
+            "source": "profiles/%s: ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum over every launch of "
+                      "one bench step (one factorisation attempt, two directions); direction_bytes = everything that is not "
+                      "assembly or factorisation, per direction" % sys.argv[1].split("/")[-1]}}
         json.dump(out, open(sys.argv[2], "w"), indent=1)
 
 
