@@ -244,3 +244,58 @@ def test_tile_cut_table(pkg):
             want = np.searchsorted(rel[rowptr[s]:rowptr[s + 1]], ce + 64 * np.arange(nt + 2), side="left")
             assert np.array_equal(tc[tp[s]:tp[s + 1]], want)
         h.close()
+
+
+def _cb_tiles(wm, n_minus_ce):
+    """Mirror of cb_tiles (opb_internal.h): tiles of BM = 64 * wm rows x 128 columns over the lower triangle."""
+    if wm == 2:
+        nt = (n_minus_ce + 127) // 128
+        return nt * (nt + 1) // 2
+    n64 = (n_minus_ce + 63) // 64
+    a = n64 >> 1
+    return a * (a + 1) + ((a + 1) if (n64 & 1) else 0)
+
+
+def _decode_wm1(tp):
+    """Mirror of front_cb_kernel<1>'s tile decode: the row tiles 2a and 2a+1 hold a+1 tiles each."""
+    a = int((np.sqrt(4.0 * tp + 1.0) - 1.0) * 0.5)
+    while a * (a + 1) > tp:
+        a -= 1
+    while (a + 1) * (a + 2) <= tp:
+        a += 1
+    rem = tp - a * (a + 1)
+    return (2 * a, rem) if rem <= a else (2 * a + 1, rem - (a + 1))
+
+
+def _decode_update_wm1(tp, nrow):
+    """Mirror of chol_panel_update_kernel<1>'s decode: column tile J (128 wide) starts at row tile 2J and
+    J (nrow + 1) - J^2 tiles precede it."""
+    b = nrow + 1.0
+    disc = b * b - 4.0 * tp
+    J = int((b - np.sqrt(disc)) * 0.5) if disc > 0 else nrow // 2
+    while J > 0 and J * (nrow + 1) - J * J > tp:
+        J -= 1
+    while (J + 1) * (nrow + 1) - (J + 1) * (J + 1) <= tp and 2 * (J + 1) < nrow:
+        J += 1
+    off = tp - (J * (nrow + 1) - J * J)
+    return 2 * J + off, J
+
+
+@pytest.mark.parametrize("rows", [1, 63, 64, 65, 127, 128, 129, 200, 1000, 4097])
+def test_tile_enumerations_cover_the_lower_triangle_once(rows):
+    """The linear tile index of the 64-row-tile kernels (update blocks and panel updates) is a bijection onto the
+    tiles that meet the lower triangle: every (row tile I, column tile J) with 64 I + 63 >= 128 J exactly once."""
+    n64 = (rows + 63) // 64
+    want = {(I, J) for I in range(n64) for J in range((rows + 127) // 128) if 64 * I + 63 >= 128 * J and 128 * J < rows}
+    nt = _cb_tiles(1, rows)
+    got = [_decode_wm1(t) for t in range(nt)]
+    assert len(set(got)) == nt and set(got) == want
+    # 128-row tiles: the plain triangle
+    n128 = (rows + 127) // 128
+    assert _cb_tiles(2, rows) == n128 * (n128 + 1) // 2
+    # panel update over `ncol` column tiles of a panel with n64 row tiles below its first column
+    for ncol in (1, 2, (rows + 127) // 128):
+        tiles = sum(n64 - 2 * J for J in range(ncol) if 2 * J < n64)
+        got = [_decode_update_wm1(t, n64) for t in range(tiles)]
+        want_u = {(I, J) for J in range(ncol) if 2 * J < n64 for I in range(2 * J, n64)}
+        assert len(set(got)) == tiles and set(got) == want_u
