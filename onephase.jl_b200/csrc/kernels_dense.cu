@@ -989,7 +989,10 @@ trtri_merge_kernel(DevSym S, const int* __restrict__ list, const int2* __restric
 // ---------------------------------------------------------------------------
 constexpr int WT = 512;
 constexpr int SLAB = 32;      // rows per CTA in the row-oriented products
-constexpr int TALL_N = 8192;  // fronts with at least this many rows take the finer-grained solve variants
+#ifndef OPB_TALL_N
+#define OPB_TALL_N 8192
+#endif
+constexpr int TALL_N = OPB_TALL_N;  // fronts with at least this many rows take the finer-grained solve variants
 constexpr int KG = WT / 32;   // k-groups (warps)
 #ifndef OPB_TALL_WPC
 #define OPB_TALL_WPC 4
