@@ -153,6 +153,45 @@ def test_options_do_not_change_results(pkg, orc):
     _compare(pkg, orc, p, opts={"ordering": 1})
 
 
+@pytest.mark.parametrize("opts", [{"lookahead": 0}, {"lookahead": 1}, {"lookahead": 2, "outer_block": 256},
+                                  {"cb_small_k": 0}, {"cb_small_k": 1}, {"graphs": 0}, {"loop_graph": 0}])
+def test_schedule_options_do_not_change_results(pkg, orc, opts):
+    """The numeric tuning options only change HOW the big fronts are scheduled (one stream / two streams / deep
+    look-ahead with an outer block small enough to exercise every piece class, 64- vs 128-row tiles, graphs or
+    plain launches): same delta sequence and directions <= 1e-10 against the oracle on a grid problem whose
+    top fronts have several 128-column blocks."""
+    _compare(pkg, orc, problems.pde_control(14, seed=2), opts=opts, own=False)
+
+
+def test_profiling_entry_points(pkg):
+    """opb_profile_factor / opb_profile_levels run one attempt like opb_factor: same factor (checked through a
+    direction), phase times that add up, flops of the two tensor-pipe kernels reported."""
+    prob = problems.pde_control(14, seed=2)
+    pars = pkg.Class_parameters()
+    it = pkg.Class_iterate(prob.J, prob.H, prob.y, prob.s, delta=0.0)
+    k = pkg.pick_KKT_solver(pars)
+    k.initialize(it)
+    k.form_system(it)
+    st, nf, delta = pkg.ipopt_strategy(it, k, pars)
+    assert st == "success"
+    k.kkt_associate_rhs(it, pkg.System_rhs(*prob.rhs[0]))
+    k.compute_direction()
+    ref = k.dir.x.copy()
+    h = k._h
+    pf = h.profile_factor(delta)
+    assert pf["inertia_ok"] == 1 and pf["total_ms"] > 0 and pf["cb_ms"] > 0 and pf["cb_flops"] > 0 and pf["update_flops"] >= 0
+    k.compute_direction()
+    assert np.linalg.norm(k.dir.x - ref) <= 1e-12 * np.linalg.norm(ref)
+    pl = h.profile_levels(delta)
+    T = pl["levels"]
+    assert T.shape == (int(h.info("nlevels")), 3) and (T >= 0).all()
+    assert T.sum() + pl["fill_ms"] + pl["trtri_ms"] <= pl["total_ms"] * 1.05 + 0.05
+    assert T.sum() >= 0.5 * pl["total_ms"]
+    k.compute_direction()
+    assert np.linalg.norm(k.dir.x - ref) <= 1e-12 * np.linalg.norm(ref)
+    k.finalize()
+
+
 def _full_size_properties(pkg, prob, expect_fac=None):
     """BASELINE.json sizes: the oracle is too slow here, so check size-independent
     properties of the result instead: the delta loop accepts the convex system at once,
