@@ -1,19 +1,25 @@
-// Dense kernels for the big fronts of the supernodal Cholesky (sm_100a):
+// Dense kernels for the big fronts of the supernodal Cholesky / LDL' (sm_100a):
 //
-//   * a 128x128 FP64 tensor-core tile engine: DMMA (mma.sync m8n8k4 f64) fed by
-//     1-D TMA bulk copies (cp.async.bulk global->shared, mbarrier completion) of
-//     panel columns through a 4-stage shared-memory ring;
-//   * the blocked right-looking Cholesky of a front built on it, outer block
-//     WB = 128:  potrf of the diagonal block in one CTA (plus its inverse),
-//     TRSM as a GEMM with that inverse, rank-128 SYRK/GEMM trailing update;
-//   * the inverse of every big supernode's pivot block L11 (recursive block
-//     merge, two batched GEMMs per level) so that the triangular solves of big
-//     supernodes become two bandwidth-bound matrix-vector products spread over
-//     many CTAs instead of a substitution chain inside one CTA;
+//   * an FP64 tensor-core tile engine: DMMA (mma.sync m8n8k4 f64) fed by 1-D TMA bulk copies
+//     (cp.async.bulk global->shared, mbarrier completion) of panel columns through a 4-stage
+//     shared-memory ring, warp-specialised (one producer warp, no block barrier in the K loop); two
+//     tile shapes, 128 x 128 (one CTA per SM) and 64 x 128 (two CTAs per SM, the default); LDL' mode
+//     scales the A fragment by the pivots on its way into the DMMAs;
+//   * the blocked right-looking factorisation of a front's panel built on it, 128-column blocks:
+//     diagonal block (Cholesky or LDL') plus its inverse in one CTA, TRSM as a GEMM with that inverse,
+//     panel updates in a recursive (binary) schedule issued with deep look-ahead: every update is cut
+//     into pieces by the step at which its columns are next touched, one prioritised stream per piece
+//     class, the latency chain on the highest-priority stream (launch_wide_chol_level);
+//   * the update block of every medium / big front, formed once from an exact tile list, children
+//     merged in shared memory through the tile-cut table of the symbolic analysis (front_cb_kernel);
+//   * the inverse of every big supernode's pivot block L11 in 2048-column diagonal blocks (recursive
+//     block merge, two batched GEMMs per level, exact work lists), so that the triangular solves of
+//     big supernodes become bandwidth-bound matrix-vector products spread over many CTAs instead of a
+//     substitution chain inside one CTA;
 //   * those multi-CTA forward / backward solve kernels.
 //
 // Replaces CHOLMOD's supernodal numeric factorisation and solve behind
-// cholesky(Symmetric(Q,:L)) and F \ rhs (linear_system_solvers/julia.jl:34,99-113).
+// cholesky(Symmetric(Q,:L)) / ldlt(...) and F \ rhs (linear_system_solvers/julia.jl:34,52,99-113).
 #include <algorithm>
 
 #include "opb_internal.h"

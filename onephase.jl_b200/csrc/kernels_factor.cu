@@ -5,8 +5,10 @@
 // Lval at Loff[s] and an update block r x r (lower part, ld = r) in CB at
 // CBoff[s].  A level of the supernodal elimination tree is processed by
 //   * front_small_kernel : one CTA per front, whole front in shared memory
-//   * big_* kernels      : fronts that do not fit, blocked right-looking in HBM,
-//                          batched over the fronts of the level (blockIdx.y)
+//   * kernels_dense.cu   : fronts that do not fit -- panels in shared memory or blocked in HBM on
+//                          the FP64 tensor pipe, Cholesky and LDL' alike (launch_wide_chol_level)
+//   * big_* kernels      : the first, scalar LDL' path of those fronts (32-column blocks, batched
+//                          over the fronts of the level); kept behind option "ldlt_scalar" for A/B runs
 // Children's update blocks are added into the parent front by the CTA that owns
 // the destination rows, children in ascending order: no atomics, the summation
 // order is fixed, so the PD decision is reproducible run to run.
