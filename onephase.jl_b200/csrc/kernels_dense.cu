@@ -72,6 +72,13 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// Programmatic dependent launch (the solve chain of the big supernodes is ~250 short kernels per pair, each
+// waiting for the one before): a kernel lets its successor start launching right away and itself waits for
+// its predecessor only where it first touches data the predecessor wrote, so launch latency and the
+// index preamble overlap the tail of the previous kernel.  Used with launch_pdl() below.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool stop_requested(const DeltaState* st) {
     const volatile int* d = &st->done;
     const volatile int* f = &st->fail;
@@ -998,7 +1005,14 @@ constexpr int SLAB = 32;      // rows per CTA in the row-oriented products
 #ifndef OPB_TALL_N
 #define OPB_TALL_N 8192
 #endif
-constexpr int TALL_N = OPB_TALL_N;  // fronts with at least this many rows take the finer-grained solve variants
+constexpr int TALL_N = OPB_TALL_N;
+// threshold of the triangular products with inv(L11) (fine-grained variants: 8-row CTAs forward, four warps per
+// column backward).  Measured on C5 100^3: fine variants for EVERY big front 10.0 ms per solve pair (the low levels
+// drown in tiny CTAs), 4096 rows 9.39 ms, 8192 rows 9.33 ms.
+#ifndef OPB_TRI_TALL_N
+#define OPB_TRI_TALL_N 8192
+#endif
+constexpr int TRI_TALL_N = OPB_TRI_TALL_N;  // fronts with at least this many rows take the finer-grained solve variants
 constexpr int KG = WT / 32;   // k-groups (warps)
 #ifndef OPB_TALL_WPC
 #define OPB_TALL_WPC 4
@@ -1012,6 +1026,8 @@ constexpr int GR = 512;       // destination rows per CTA (one per thread)
 __global__ void __launch_bounds__(WT)
 wide_fwd_gather_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ x, double* __restrict__ u) {
     const int s = list[blockIdx.y];
+    pdl_release();
+    pdl_wait();
     const int first = S.sfirst[s];
     const int c = S.sfirst[s + 1] - first;
     const int64_t rp = S.rowptr[s];
@@ -1045,7 +1061,9 @@ wide_fwd_tri_kernel(DevSym S, const int* __restrict__ list, const double* __rest
     constexpr int KS = WT / RS;              // k-groups per CTA
     __shared__ double red[KS][RS];
     const Front d = get_front(S, list[blockIdx.y]);
-    if ((d.N >= TALL_N) != (RS < 32)) return;     // the other variant's front
+    pdl_release();
+    pdl_wait();
+    if ((d.N >= TRI_TALL_N) != (RS < 32)) return;     // the other variant's front
     const int b0 = blk * XB;
     const int b1 = min(d.c, b0 + XB);
     const int i0 = b0 + blockIdx.x * RS;
@@ -1087,6 +1105,8 @@ wide_fwd_upd_kernel(DevSym S, const int* __restrict__ list, const double* __rest
     constexpr int KGU = NT / 32;
     __shared__ double red[KGU][SLAB];
     const Front d = get_front(S, list[blockIdx.y]);
+    pdl_release();
+    pdl_wait();
     const int b0 = blk * XB;
     if (b0 >= d.c) return;
     const int b1 = min(d.c, b0 + XB);
@@ -1130,6 +1150,8 @@ __global__ void __launch_bounds__(WT)
 wide_bwd_gather_kernel(DevSym S, const int* __restrict__ list, double* __restrict__ x,
                        double* __restrict__ u, int ldlt) {
     const int s = list[blockIdx.y];
+    pdl_release();
+    pdl_wait();
     const int64_t rp = S.rowptr[s];
     const int r = (int)(S.rowptr[s + 1] - rp);
     const int t = blockIdx.x * WT + threadIdx.x;
@@ -1152,6 +1174,8 @@ wide_bwd_upd_kernel(DevSym S, const int* __restrict__ list, const double* __rest
                     const double* __restrict__ x, double* __restrict__ xnew, const double* __restrict__ u, int blk) {
     __shared__ double red[KG];
     const Front d = get_front(S, list[blockIdx.y]);
+    pdl_release();
+    pdl_wait();
     if ((d.N >= TALL_N) != (WPC > 1)) return;     // the other variant's front (fixed per front: reproducible)
     const int b0 = blk * XB;
     const int b1 = min(d.c, b0 + XB);
@@ -1221,7 +1245,9 @@ wide_bwd_tri_kernel(DevSym S, const int* __restrict__ list, const double* __rest
                     double* __restrict__ x, const double* __restrict__ xnew, int blk) {
     __shared__ double red[KG];
     const Front d = get_front(S, list[blockIdx.y]);
-    if ((d.N >= TALL_N) != (WPC > 1)) return;     // the other variant's front (fixed per front: reproducible)
+    pdl_release();
+    pdl_wait();
+    if ((d.N >= TRI_TALL_N) != (WPC > 1)) return;     // the other variant's front (fixed per front: reproducible)
     const int b0 = blk * XB;
     const int b1 = min(d.c, b0 + XB);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1497,29 +1523,42 @@ void launch_trtri(const DevSym& S, const TrtriPlan& T, const int* d_sched, const
     }
 }
 
+// launch with the programmatic-serialisation attribute: the kernel may start while its predecessor in the
+// stream is still draining; it calls pdl_wait() before it reads anything the predecessor wrote
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 void launch_solve_wide_fwd(const DevSym& S, const LevelPlan& L, const int* d_sched, const double* Lval,
                            const double* Xinv, double* x, double* xnew, double* u, cudaStream_t st) {
     const int cnt = L.count[FC_BIG];
     if (!cnt) return;
     const int* list = d_sched + L.begin[FC_BIG];
     dim3 gg((L.maxN[FC_BIG] + GR - 1) / GR, cnt);
-    wide_fwd_gather_kernel<<<gg, WT, 0, st>>>(S, list, x, u);
+    launch_pdl(wide_fwd_gather_kernel, gg, dim3(WT), st, S, list, x, u);
     count_launch();
     const int nblk = (L.maxC[FC_BIG] + XB - 1) / XB;
     for (int blk = 0; blk < nblk; blk++) {
         const int cb = std::min(XB, L.maxC[FC_BIG] - blk * XB);
-        if (L.maxN[FC_BIG] >= TALL_N) {
+        if (L.maxN[FC_BIG] >= TRI_TALL_N) {
             dim3 g1((cb + 7) / 8, cnt);
-            wide_fwd_tri_kernel<8><<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
+            launch_pdl(wide_fwd_tri_kernel<8>, g1, dim3(WT), st, S, list, Xinv, x, xnew, blk);
             count_launch();
         }
-        if (L.minN[FC_BIG] < TALL_N) {
+        if (L.minN[FC_BIG] < TRI_TALL_N) {
             dim3 g1((cb + SLAB - 1) / SLAB, cnt);
-            wide_fwd_tri_kernel<SLAB><<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
+            launch_pdl(wide_fwd_tri_kernel<SLAB>, g1, dim3(WT), st, S, list, Xinv, x, xnew, blk);
             count_launch();
         }
         dim3 g2((L.maxN[FC_BIG] - blk * XB + SLAB - 1) / SLAB, cnt);
-        wide_fwd_upd_kernel<WT><<<g2, WT, 0, st>>>(S, list, Lval, x, xnew, u, blk);
+        launch_pdl(wide_fwd_upd_kernel<WT>, g2, dim3(WT), st, S, list, Lval, x, xnew, u, blk);
         count_launch();
     }
 }
@@ -1530,24 +1569,17 @@ void launch_solve_wide_bwd(const DevSym& S, const LevelPlan& L, const int* d_sch
     if (!cnt) return;
     const int* list = d_sched + L.begin[FC_BIG];
     dim3 g0((L.maxN[FC_BIG] + WT) / WT, cnt);
-    wide_bwd_gather_kernel<<<g0, WT, 0, st>>>(S, list, x, u, ldlt);
+    launch_pdl(wide_bwd_gather_kernel, g0, dim3(WT), st, S, list, x, u, ldlt);
     count_launch();
     const int nblk = (L.maxC[FC_BIG] + XB - 1) / XB;
     for (int blk = nblk - 1; blk >= 0; blk--) {
         const int cb = std::min(XB, L.maxC[FC_BIG] - blk * XB);
-        if (L.maxN[FC_BIG] >= TALL_N) {
-            constexpr int WPC = TALL_WPC;
-            dim3 g1((cb + KG / WPC - 1) / (KG / WPC), cnt);
-            wide_bwd_upd_kernel<WPC><<<g1, WT, 0, st>>>(S, list, Lval, x, xnew, u, blk);
-            wide_bwd_tri_kernel<WPC><<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
-            count_launch(2);
-        }
-        if (L.minN[FC_BIG] < TALL_N) {
-            dim3 g1((cb + KG - 1) / KG, cnt);
-            wide_bwd_upd_kernel<1><<<g1, WT, 0, st>>>(S, list, Lval, x, xnew, u, blk);
-            wide_bwd_tri_kernel<1><<<g1, WT, 0, st>>>(S, list, Xinv, x, xnew, blk);
-            count_launch(2);
-        }
+        constexpr int WPC = TALL_WPC;
+        const dim3 gt((cb + KG / WPC - 1) / (KG / WPC), cnt), g1((cb + KG - 1) / KG, cnt);
+        if (L.maxN[FC_BIG] >= TALL_N) { launch_pdl(wide_bwd_upd_kernel<WPC>, gt, dim3(WT), st, S, list, Lval, x, xnew, u, blk); count_launch(); }
+        if (L.minN[FC_BIG] < TALL_N) { launch_pdl(wide_bwd_upd_kernel<1>, g1, dim3(WT), st, S, list, Lval, x, xnew, u, blk); count_launch(); }
+        if (L.maxN[FC_BIG] >= TRI_TALL_N) { launch_pdl(wide_bwd_tri_kernel<WPC>, gt, dim3(WT), st, S, list, Xinv, x, xnew, blk); count_launch(); }
+        if (L.minN[FC_BIG] < TRI_TALL_N) { launch_pdl(wide_bwd_tri_kernel<1>, g1, dim3(WT), st, S, list, Xinv, x, xnew, blk); count_launch(); }
     }
 }
 
