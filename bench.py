@@ -477,9 +477,11 @@ def measure_sharded(pkg, torch, dist, args, local, world, workload):
            "split_fronts": int(h.info("shard_split")),
            "rank_flops": [float(v) for v in loads], "top_flops": h.info("shard_top_flops"),
            "barrier_levels": int(h.info("shard_barriers")),
-           "how": "subtree-to-GPU mapping by factorisation flops; update blocks, forward update vectors and the "
-                  "solution cross GPUs through peer-mapped HBM (CUDA IPC over NVLink) inside the consuming kernels; "
-                  "flag barriers on the stream; no collective in the data path"}
+           "how": "subtree-to-GPU mapping by factorisation flops; the update blocks of the top separators are formed by all "
+                  "GPUs of the separator's range (panel pulled over NVLink, tiles stored into the owner's arena); children's "
+                  "update blocks, forward update vectors and the solution cross GPUs through peer-mapped HBM (CUDA IPC over "
+                  "NVLink), in bulk copies or inside the consuming kernels; flag barriers on the stream among the ranks that "
+                  "exchange data at a level; no collective in the data path"}
     inst.close()
     return out
 
