@@ -263,6 +263,18 @@ def pin_problem(torch, prob):
     return prob
 
 
+def symbolic_breakdown(h):
+    """Host seconds of the phases of the one-off analysis (info keys t_<phase> of the C ABI); what is left of
+    `symbolic_s_once` is device allocation and the first assembly."""
+    out = {}
+    for key in ("pattern", "analyze", "plan", "upload"):
+        try:
+            out[key] = round(h.info("t_" + key), 4)
+        except Exception:
+            return None
+    return out
+
+
 class Instance:
     """One KKT instance bound to a solver object (the plugin API) on the current torch stream."""
 
@@ -281,6 +293,7 @@ class Instance:
         self.k.form_system(self.it)              # symbolic analysis happens here, once
         self.t_symbolic = time.perf_counter() - t0
         self.h = self.k._h
+        self.symbolic_breakdown = symbolic_breakdown(self.h)
         self.rhs = [pkg.System_rhs(*r) for r in prob.rhs[:N_DIRECTIONS]]
         d = self.pars.delta
         self.dl_args = (prob.delta_prev, d.zero, d.min, d.max, d.start, d.inc, d.dec, 500)
@@ -378,7 +391,8 @@ def measure_other_workload(pkg, torch, wname, local, hbm_peak, fp64_peak, cpu=Tr
                                                     "d2h_bytes_per_step": d2h},
            "n": prob.n, "m": prob.m, "num_fac": nf2, "delta": d2, "N_err": float(err2[5]),
            "factor_flops": inst.h.info("flops"), "nnz_L": int(inst.h.info("nnzL_true")),
-           "phases_ms": ph, "rooflines_by_phase": rl, "symbolic_s_once": inst.t_symbolic}
+           "phases_ms": ph, "rooflines_by_phase": rl, "symbolic_s_once": inst.t_symbolic,
+           "symbolic_breakdown_s": inst.symbolic_breakdown}
     inst.close()
     if cpu:
         try:
@@ -661,6 +675,7 @@ def main():
                         etree_levels=int(h.info("nlevels")), max_front=int(h.info("max_front")),
                         L_mb=8 * h.info("nnzL") / 1e6)
     t_symbolic = inst.t_symbolic
+    t_symbolic_parts = inst.symbolic_breakdown
     inst.close()
     del inst, h
     torch.cuda.empty_cache()
@@ -720,7 +735,7 @@ def main():
                               "one independent instance per GPU (replicas)",
                "l2_policy": "working set larger than L2: factor L alone is %.0f MB and is streamed by every "
                             "factorisation and solve" % config_extra["L_mb"],
-               "symbolic_s_once": t_symbolic}
+               "symbolic_s_once": t_symbolic, "symbolic_breakdown_s": t_symbolic_parts}
         out = {
             "metric": "kkt_factor_solve_ms_per_iter", "value": ms_step if sharded else ms_step / world, "unit": "ms/iter",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,

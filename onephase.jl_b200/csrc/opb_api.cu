@@ -11,6 +11,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <chrono>
 
 #include "../../include/onephase_b200.h"
 #include "opb_internal.h"
@@ -25,6 +26,7 @@ struct Bundle {
     std::vector<int64_t> Mp;     // pattern of the lower triangle that is factorised
     std::vector<int> Mi;
     std::vector<int64_t> src;    // csc path: position in the caller's nzval (or -1)
+    std::vector<std::pair<std::string, double>> timing;   // host seconds: pattern, analyze, shard_map, plan, upload
     // the caller's index arrays (0-based copies): a cache hit is accepted only when they are equal,
     // so a 64-bit hash collision cannot hand out a wrong analysis
     std::vector<int64_t> in_p[2];
@@ -702,7 +704,11 @@ static void cache_put(const std::string& key, std::shared_ptr<Bundle> b) {
     g_cache_order.push_back(key);
 }
 
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static int finish_structure(opb_handle* h, std::shared_ptr<Bundle> B, const std::string& key) {
+    double t0 = now_s();
+    auto mark = [&](const char* name) { const double t = now_s(); B->timing.emplace_back(name, t - t0); t0 = t; };
     const int64_t* up = h->user_perm.empty() ? nullptr : h->user_perm.data();
     if (up && (int64_t)h->user_perm.size() != (int64_t)(B->Mp.size() - 1))
         return h->fail(OPB_ERR_INVALID, "permutation length does not match n");
@@ -715,17 +721,21 @@ static int finish_structure(opb_handle* h, std::shared_ptr<Bundle> B, const std:
         if (!analyze((int)(B->Mp.size() - 1), B->Mp, B->Mi, h->opt, up, B->S))
             return h->fail(OPB_ERR_INTERNAL, "symbolic analysis failed: " + B->S.error);
     }
+    mark("analyze");
     B->rank = h->shard_rank; B->world = h->shard_world;
     if (B->world > 1) {
         shard_map(B->S, B->world, h->opt.shard_split_flops, B->shard);
         B->colowner.resize(B->S.n);
         for (int j = 0; j < B->S.n; j++) B->colowner[j] = B->shard.owner[B->S.col2super[j]];
     }
+    mark("shard_map");
     build_plan(*B);
+    mark("plan");
     if (h->device >= 0) {
         cudaSetDevice(h->device);
         int rc = upload_bundle(h, *B);
         if (rc) return rc;
+        mark("upload");
     }
     cache_put(key, B);
     h->B = B;
@@ -758,7 +768,9 @@ int opb_set_structure(opb_handle* h, int64_t n, int64_t m, const int64_t* Jp, co
     auto B = std::make_shared<Bundle>();
     B->schur = true;
     std::string err;
+    const double tp = now_s();
     if (!build_schur_pattern(n, m, Jp, Ji, Hp, Hi, base, B->P, err)) return h->fail(OPB_ERR_INVALID, err);
+    B->timing.emplace_back("pattern", now_s() - tp);
     B->keep_pattern(0, n, Jp, Ji, base); B->keep_pattern(1, n, Hp, Hi, base);
     B->Mp = B->P.Mp; B->Mi = B->P.Mi;
     return finish_structure(h, B, key);
@@ -1355,6 +1367,12 @@ int opb_get_info(opb_handle* h, const char* key, double* out) {
     else if (k == "shard_split") { int c = 0; if (B.world > 1) for (char f : B.shard.split) c += f; *out = c; }
     else if (k == "shard_mirrored") { int c = 0; for (const LevelPlan& L : B.plan) c += L.pullcb_count; *out = c; }
     else if (k == "shard_helped") { int c = 0; for (const LevelPlan& L : B.plan) c += L.help_count; *out = c; }
+    else if (k.rfind("t_", 0) == 0) {
+        // host seconds of the phases of the last analysis of this structure (0 when the phase did not run)
+        *out = 0;
+        for (const auto& kv : B.timing) if (k == "t_" + kv.first) *out += kv.second;
+        for (const auto& kv : S.timing) if (k == "t_" + kv.first) *out += kv.second;
+    }
     else return h->fail(OPB_ERR_INVALID, "unknown info key " + k);
     return OPB_OK;
 }

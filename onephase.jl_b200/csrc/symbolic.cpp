@@ -13,10 +13,14 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <system_error>
 #include <thread>
 #include <map>
+#include <mutex>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 
 // METIS nested dissection from the static library that ships with the CUDA toolkit
@@ -40,6 +44,66 @@ uint64_t pattern_hash(int64_t n, const int64_t* p, const int64_t* i, int64_t nnz
 
 // ---------------------------------------------------------------------------
 // 1. Schur pattern + gather map
+
+// ---------------------------------------------------------------------------
+// Host threads for the one-off analysis.  run_chunks(n, fn) calls fn(chunk, begin, end) for a fixed
+// partition of [0, n) -- fixed by n and the thread count only, and every use below writes disjoint
+// outputs per index, so results do not depend on the schedule.  Falls back to the calling thread
+// when no thread can be started.
+// ---------------------------------------------------------------------------
+namespace {
+
+int host_threads() {
+    static const int t = [] {
+        unsigned hc = std::thread::hardware_concurrency();
+        if (const char* e = getenv("OPB_HOST_THREADS")) { int v = atoi(e); if (v > 0) hc = (unsigned)v; }
+        return (int)std::min(16u, std::max(1u, hc));
+    }();
+    return t;
+}
+
+template <class F>
+void run_chunks(int64_t n, int64_t min_per_chunk, F&& fn) {
+    int nt = (int)std::min<int64_t>(host_threads(), std::max<int64_t>(1, n / std::max<int64_t>(1, min_per_chunk)));
+    if (nt <= 1) { fn(0, (int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    auto bound = [&](int c) { return n * c / nt; };
+    int started = 1;
+    for (int c = 1; c < nt; c++) {
+        try { th.emplace_back([&fn, c, &bound] { fn(c, bound(c), bound(c + 1)); }); started++; }
+        catch (const std::system_error&) { break; }
+    }
+    fn(0, bound(0), bound(1));
+    for (int c = started; c < nt; c++) fn(c, bound(c), bound(c + 1));   // chunks that got no thread
+    for (auto& t : th) t.join();
+}
+
+// chunk boundaries that balance a prefix-sum weight (ptr[n] total) instead of the index count
+template <class F>
+void run_chunks_weighted(int64_t n, const int64_t* ptr, int64_t min_weight, F&& fn) {
+    const int64_t total = ptr[n] - ptr[0];
+    int nt = (int)std::min<int64_t>(host_threads(), std::max<int64_t>(1, total / std::max<int64_t>(1, min_weight)));
+    if (nt <= 1) { fn(0, (int64_t)0, n); return; }
+    std::vector<int64_t> b(nt + 1, n);
+    b[0] = 0;
+    for (int c = 1; c < nt; c++)
+        b[c] = std::lower_bound(ptr, ptr + n + 1, ptr[0] + total * c / nt) - ptr;
+    for (int c = 1; c <= nt; c++) b[c] = std::max(b[c], b[c - 1]);
+    b[nt] = n;
+    std::vector<std::thread> th;
+    int started = 1;
+    for (int c = 1; c < nt; c++) {
+        try { th.emplace_back([&fn, c, &b] { fn(c, b[c], b[c + 1]); }); started++; }
+        catch (const std::system_error&) { break; }
+    }
+    fn(0, b[0], b[1]);
+    for (int c = started; c < nt; c++) fn(c, b[c], b[c + 1]);
+    for (auto& t : th) t.join();
+}
+
+}  // namespace
+
 // ---------------------------------------------------------------------------
 bool build_schur_pattern(int64_t n64, int64_t m64, const int64_t* Jp_in, const int64_t* Ji_in,
                          const int64_t* Hp_in, const int64_t* Hi_in, int base,
@@ -109,57 +173,58 @@ bool build_schur_pattern(int64_t n64, int64_t m64, const int64_t* Jp_in, const i
                 P.Scol[q] = i; P.Spos[q] = (int)p;
             }
     }
-    // pattern of tril(J'DJ) U H U diag, column by column
-    std::vector<int> mark(n, -1), where(n, -1), list;
+    // pattern of tril(J'DJ) U H U diag, column by column (column ranges on host threads, each with
+    // its own marker array; the pieces are concatenated in column order)
     P.Mp.assign(n + 1, 0);
     P.Mi.clear();
-    std::vector<int64_t> cnt;  // pairs per entry
-    // pass 1: pattern
-    for (int j = 0; j < n; j++) {
-        list.clear();
-        mark[j] = j; list.push_back(j);
-        for (int64_t p = P.Jp[j]; p < P.Jp[j + 1]; p++) {
-            int k = P.Jrow[p];
-            for (int64_t q = P.Rp[k + 1] - 1; q >= P.Rp[k]; q--) {
-                int i = P.Rcol[q];
-                if (i < j) break;
-                if (mark[i] != j) { mark[i] = j; list.push_back(i); }
+    {
+        const int NTMAX = 16;
+        std::vector<int> piece[NTMAX];
+        int64_t piece_begin[NTMAX + 1];
+        for (int c = 0; c <= NTMAX; c++) piece_begin[c] = -1;
+        int nchunks = 0;
+        std::mutex mu;
+        run_chunks(n, 20000, [&](int c, int64_t jb, int64_t je) {
+            std::vector<int> mark(n, -1), list;
+            std::vector<int>& out = piece[c];
+            for (int j = (int)jb; j < (int)je; j++) {
+                list.clear();
+                mark[j] = j; list.push_back(j);
+                for (int64_t p = P.Jp[j]; p < P.Jp[j + 1]; p++) {
+                    int k = P.Jrow[p];
+                    for (int64_t q = P.Rp[k + 1] - 1; q >= P.Rp[k]; q--) {
+                        int i = P.Rcol[q];
+                        if (i < j) break;
+                        if (mark[i] != j) { mark[i] = j; list.push_back(i); }
+                    }
+                }
+                for (int64_t p = Hp[j]; p < Hp[j + 1]; p++) {
+                    int i = Hrow[p];
+                    if (mark[i] != j) { mark[i] = j; list.push_back(i); }
+                }
+                std::sort(list.begin(), list.end());
+                out.insert(out.end(), list.begin(), list.end());
+                P.Mp[j + 1] = (int64_t)list.size();           // counts; prefix sum below
             }
-        }
-        for (int64_t p = Hp[j]; p < Hp[j + 1]; p++) {
-            int i = Hrow[p];
-            if (mark[i] != j) { mark[i] = j; list.push_back(i); }
-        }
-        std::sort(list.begin(), list.end());
-        P.Mi.insert(P.Mi.end(), list.begin(), list.end());
-        P.Mp[j + 1] = (int64_t)P.Mi.size();
+            std::lock_guard<std::mutex> g(mu);
+            piece_begin[c] = jb;
+            nchunks = std::max(nchunks, c + 1);
+        });
+        for (int j = 0; j < n; j++) P.Mp[j + 1] += P.Mp[j];
+        if (P.Mp[n] > 2000000000ll) { err = "Schur complement too large for int32 indexing"; return false; }
+        P.Mi.resize(P.Mp[n]);
+        run_chunks(nchunks, 1, [&](int, int64_t cb, int64_t ce) {
+            for (int64_t c = cb; c < ce; c++)
+                if (!piece[c].empty()) memcpy(P.Mi.data() + P.Mp[piece_begin[c]], piece[c].data(), piece[c].size() * sizeof(int));
+        });
     }
     const int64_t nnzM = P.Mp[n];
-    if (nnzM > 2000000000ll) { err = "Schur complement too large for int32 indexing"; return false; }
-    // pass 2: count pairs, hmap
+    // pass 2: count pairs, hmap (a column only touches its own entries)
     P.pair_ptr.assign(nnzM + 1, 0);
     P.hmap.assign(nnzM, -1);
-    for (int j = 0; j < n; j++) {
-        for (int64_t e = P.Mp[j]; e < P.Mp[j + 1]; e++) where[P.Mi[e]] = (int)(e - P.Mp[j]);
-        const int64_t e0 = P.Mp[j];
-        for (int64_t p = P.Jp[j]; p < P.Jp[j + 1]; p++) {
-            int k = P.Jrow[p];
-            for (int64_t q = P.Rp[k + 1] - 1; q >= P.Rp[k]; q--) {
-                int i = P.Rcol[q];
-                if (i < j) break;
-                P.pair_ptr[e0 + where[i] + 1]++;
-            }
-        }
-        for (int64_t p = Hp[j]; p < Hp[j + 1]; p++) P.hmap[e0 + where[Hrow[p]]] = (int)p;
-    }
-    for (int64_t e = 0; e < nnzM; e++) P.pair_ptr[e + 1] += P.pair_ptr[e];
-    const int64_t npairs = P.pair_ptr[nnzM];
-    if (npairs > 2000000000ll) { err = "too many J'DJ products for int32 indexing"; return false; }
-    P.pairA.resize(npairs); P.pairB.resize(npairs);
-    // pass 3: fill, k ascending inside each entry (CSC rows of J are ascending)
-    {
-        std::vector<int64_t> nxt(P.pair_ptr.begin(), P.pair_ptr.end() - 1);
-        for (int j = 0; j < n; j++) {
+    run_chunks_weighted(n, P.Mp.data(), 200000, [&](int, int64_t jb, int64_t je) {
+        std::vector<int> where(n, -1);
+        for (int j = (int)jb; j < (int)je; j++) {
             for (int64_t e = P.Mp[j]; e < P.Mp[j + 1]; e++) where[P.Mi[e]] = (int)(e - P.Mp[j]);
             const int64_t e0 = P.Mp[j];
             for (int64_t p = P.Jp[j]; p < P.Jp[j + 1]; p++) {
@@ -167,13 +232,36 @@ bool build_schur_pattern(int64_t n64, int64_t m64, const int64_t* Jp_in, const i
                 for (int64_t q = P.Rp[k + 1] - 1; q >= P.Rp[k]; q--) {
                     int i = P.Rcol[q];
                     if (i < j) break;
-                    int64_t t = nxt[e0 + where[i]]++;
+                    P.pair_ptr[e0 + where[i] + 1]++;
+                }
+            }
+            for (int64_t p = Hp[j]; p < Hp[j + 1]; p++) P.hmap[e0 + where[Hrow[p]]] = (int)p;
+        }
+    });
+    for (int64_t e = 0; e < nnzM; e++) P.pair_ptr[e + 1] += P.pair_ptr[e];
+    const int64_t npairs = P.pair_ptr[nnzM];
+    if (npairs > 2000000000ll) { err = "too many J'DJ products for int32 indexing"; return false; }
+    P.pairA.resize(npairs); P.pairB.resize(npairs);
+    // pass 3: fill, k ascending inside each entry (CSC rows of J are ascending)
+    run_chunks_weighted(n, P.Mp.data(), 200000, [&](int, int64_t jb, int64_t je) {
+        std::vector<int> where(n, -1);
+        std::vector<int64_t> nxt;
+        for (int j = (int)jb; j < (int)je; j++) {
+            const int64_t e0 = P.Mp[j], ne = P.Mp[j + 1] - e0;
+            nxt.assign(P.pair_ptr.begin() + e0, P.pair_ptr.begin() + e0 + ne);
+            for (int64_t e = e0; e < e0 + ne; e++) where[P.Mi[e]] = (int)(e - e0);
+            for (int64_t p = P.Jp[j]; p < P.Jp[j + 1]; p++) {
+                int k = P.Jrow[p];
+                for (int64_t q = P.Rp[k + 1] - 1; q >= P.Rp[k]; q--) {
+                    int i = P.Rcol[q];
+                    if (i < j) break;
+                    int64_t t = nxt[where[i]]++;
                     P.pairA[t] = P.Rpos[q];   // J[k,i]  (scaled by sigma first)
                     P.pairB[t] = (int)p;      // J[k,j]
                 }
             }
         }
-    }
+    });
     return true;
 }
 
@@ -298,6 +386,7 @@ struct NDWork {
     int* lvl;                  // BFS level scratch (shared, own vertices only)
     std::vector<int>* local_v; // md_small scratch, indexed by vertex (shared, own vertices only)
     std::atomic<int>* next_rid;
+    std::atomic<int>* live;    // host threads of this ordering that are running (forking stops at the cap)
     std::vector<int> queue;    // per task
     int leaf;
     double balance;            // a separator level must leave at least this fraction on either side
@@ -339,7 +428,8 @@ void order_fallback(NDWork& W, std::vector<int>& verts, int rid, int offset) {
     }
 }
 
-constexpr int ND_PAR_DEPTH = 3;        // recursion levels that fork a host thread (up to 8 tasks)
+// A dissection forks a host thread for one half while fewer than 2 x host_threads() are running (the
+// halves are unbalanced -- 30/70 is common -- so a fixed fork depth leaves one long serial task).
 constexpr int ND_PAR_MIN = 20000;      // ... when both halves have at least this many vertices
 
 void nd_rec(NDWork& W, std::vector<int>& verts, int offset, int depth) {
@@ -443,15 +533,18 @@ void nd_rec(NDWork& W, std::vector<int>& verts, int offset, int depth) {
     // separator last
     std::sort(sep.begin(), sep.end());
     for (size_t t = 0; t < sep.size(); t++) { W.perm[offset + nl + nr + t] = sep[t]; set_reg(W, sep[t], 0); }
-    if (depth < ND_PAR_DEPTH && nl >= ND_PAR_MIN && nr >= ND_PAR_MIN) {
+    bool fork = nl >= ND_PAR_MIN && nr >= ND_PAR_MIN;
+    if (fork && W.live->fetch_add(1) >= 2 * host_threads()) { W.live->fetch_sub(1); fork = false; }
+    if (fork) {
         NDWork W2 = W;                 // shares the per-vertex arrays, own queue
         W2.queue.clear();
         std::thread th;
         bool forked = true;
         try {
-            th = std::thread([&W2, &left, offset, depth] { nd_rec(W2, left, offset, depth + 1); });
+            th = std::thread([&W2, &left, offset, depth] { nd_rec(W2, left, offset, depth + 1); W2.live->fetch_sub(1); });
         } catch (const std::system_error&) {
             forked = false;            // no thread to be had: same work, serially
+            W.live->fetch_sub(1);
         }
         if (!forked) nd_rec(W, left, offset, depth + 1);
         nd_rec(W, right, offset + nl, depth + 1);
@@ -464,10 +557,10 @@ void nd_rec(NDWork& W, std::vector<int>& verts, int offset, int depth) {
 
 void nd_order(const Graph& G, int leaf, double balance, std::vector<int>& perm) {
     std::vector<int> reg(G.n, 0), lvl(G.n, -1), local(G.n, 0);
-    std::atomic<int> next_rid{1};
+    std::atomic<int> next_rid{1}, live{1};
     NDWork W;
     W.G = &G;
-    W.reg = reg.data(); W.lvl = lvl.data(); W.local_v = &local; W.next_rid = &next_rid;
+    W.reg = reg.data(); W.lvl = lvl.data(); W.local_v = &local; W.next_rid = &next_rid; W.live = &live;
     W.leaf = std::max(leaf, 4);
     W.balance = std::min(0.45, std::max(0.05, balance));
     perm.resize(G.n);
@@ -606,6 +699,12 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
              const SymOptions& opt, const int64_t* user_perm, Symbolic& S) {
     S = Symbolic();
     S.n = n;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char* name) {
+        auto t = std::chrono::steady_clock::now();
+        S.timing.emplace_back(name, std::chrono::duration<double>(t - t_last).count());
+        t_last = t;
+    };
     // ---- ordering
     std::vector<int> perm0(n);
     auto metis_order = [&](std::vector<int>& out) -> bool {
@@ -640,9 +739,10 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
         for (int k = 0; k < n; k++) pm2[k] = pm[post[k]];
         for (int k = 0; k < n; k++) ip2[pm2[k]] = k;
         permuted_lower(n, Mp, Mi, ip2, Bp_, Bi_);
-        transpose_lower(n, Bp_, Bi_, Up_, Ui_);
-        etree(n, Up_, Ui_, par);
-        colcounts(n, Bp_, Bi_, par, cc_);
+        std::vector<int> par2(n);                // the postordered tree is the same tree, relabelled
+        for (int k = 0; k < n; k++) ip[post[k]] = k;
+        for (int k = 0; k < n; k++) { const int p0 = par[post[k]]; par2[k] = p0 < 0 ? -1 : ip[p0]; }
+        colcounts(n, Bp_, Bi_, par2, cc_);
         double f = 0;
         for (int j = 0; j < n; j++) f += (double)cc_[j] * (double)cc_[j];
         return f;
@@ -663,12 +763,35 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
     } else {
         // auto (default): the level-structure nested dissection of this file and, for graphs that
         // METIS orders in seconds, METIS_NodeND; keep the ordering with fewer factorisation flops
-        own_order(perm0);
-        if (n <= opt.metis_max_n) {
-            std::vector<int> pm;
-            if (metis_order(pm) && flops_of(pm) < flops_of(perm0)) perm0.swap(pm);
+        // The two candidates are independent: METIS runs on the calling thread (its random-number
+        // state is process-wide, see finish_structure), the own ordering beside it.
+        std::vector<int> pm;
+        bool metis_ok = false;
+        const bool try_metis = n <= opt.metis_max_n;
+        std::thread side;
+        bool forked = false;
+        if (try_metis) {
+            try { side = std::thread([&] { own_order(perm0); }); forked = true; }
+            catch (const std::system_error&) {}
+        }
+        if (!forked) own_order(perm0);
+        if (try_metis) metis_ok = metis_order(pm);
+        if (forked) side.join();
+        mark(try_metis ? "order_candidates" : "order_own");
+        if (metis_ok) {
+            double f_metis = 0, f_own = 0;
+            std::thread cmp;
+            bool cf = false;
+            try { cmp = std::thread([&] { f_own = flops_of(perm0); }); cf = true; }
+            catch (const std::system_error&) {}
+            if (!cf) f_own = flops_of(perm0);
+            f_metis = flops_of(pm);
+            if (cf) cmp.join();
+            if (f_metis < f_own) perm0.swap(pm);
+            mark("order_compare");
         }
     }
+    mark("order");
     std::vector<int> iperm0(n);
     for (int k = 0; k < n; k++) iperm0[perm0[k]] = k;
     // ---- etree + postorder on the first permutation
@@ -681,15 +804,21 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
     S.perm.resize(n); S.iperm.resize(n);
     for (int k = 0; k < n; k++) S.perm[k] = perm0[post[k]];
     for (int k = 0; k < n; k++) S.iperm[S.perm[k]] = k;
-    // ---- final permuted pattern, etree, counts
+    // ---- final permuted pattern and counts; a postordering relabels the elimination tree, it does
+    //      not change it: parent[k] = position of parent0[post[k]] in the postorder
     permuted_lower(n, Mp, Mi, S.iperm, Bp, Bi);
-    transpose_lower(n, Bp, Bi, Up, Ui);
-    std::vector<int> parent;
-    etree(n, Up, Ui, parent);
+    std::vector<int> parent(n);
+    {
+        std::vector<int>& ipost = Ui;          // scratch: the transpose is no longer needed
+        ipost.assign(n, 0);
+        for (int k = 0; k < n; k++) ipost[post[k]] = k;
+        for (int k = 0; k < n; k++) { const int p0 = parent0[post[k]]; parent[k] = p0 < 0 ? -1 : ipost[p0]; }
+    }
     std::vector<int64_t> cc;
     colcounts(n, Bp, Bi, parent, cc);
     S.flops = 0; S.nnzL_true = 0;
     for (int j = 0; j < n; j++) { S.flops += (double)cc[j] * (double)cc[j]; S.nnzL_true += cc[j]; }
+    mark("etree_counts");
     // ---- fundamental (maximal) supernodes
     std::vector<int> sfirst;  // first column of each supernode
     for (int j = 0; j < n; j++) {
@@ -742,6 +871,7 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
     S.col2super.resize(n);
     for (int s = 0; s < S.nsuper; s++) for (int j = S.sfirst[s]; j < S.sfirst[s + 1]; j++) S.col2super[j] = s;
     S.sparent.assign(S.nsuper, -1);
+    mark("supernodes");
     // ---- supernodal row structures (bottom-up union of children + own columns)
     const int NS = S.nsuper;
     S.child_ptr.assign(NS + 1, 0);
@@ -782,6 +912,7 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
         std::vector<int> nxt(S.child_ptr.begin(), S.child_ptr.end() - 1);
         for (int s = 0; s < NS; s++) if (S.sparent[s] >= 0) S.child_list[nxt[S.sparent[s]]++] = s;
     }
+    mark("row_structures");
     // ---- storage offsets, levels
     S.Loff.assign(NS + 1, 0); S.CBoff.assign(NS + 1, 0);
     S.level.assign(NS, 0);
@@ -835,20 +966,29 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
             std::vector<int> order(S.level_list.begin() + S.level_ptr[l], S.level_list.begin() + S.level_ptr[l + 1]);
             auto rows_of = [&](int s) { return (int64_t)(S.rowptr[s + 1] - S.rowptr[s]); };
             std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rows_of(a) > rows_of(b); });
+            int64_t cursor = 0, cursor_sz = -1;
+            bool have_cursor = false;
             for (int s : order) {
                 const int64_t r = rows_of(s);
                 const int64_t sz = (r * r + 1) & ~(int64_t)1;
                 bsize[s] = (S.sparent[s] >= 0) ? sz : 0;
                 if (S.sparent[s] < 0 || sz == 0) { S.CBoff[s] = 0; bsize[s] = 0; continue; }
+                // first fit by address.  Nothing is released inside a level, so for a run of EQUAL sizes
+                // every hole below the place where the previous search stopped is still too small: resume
+                // there (same result as a search from the start); a smaller size starts over.
                 int64_t off = -1;
-                for (auto it = free_list.begin(); it != free_list.end(); ++it)
+                if (sz != cursor_sz) { have_cursor = false; cursor_sz = sz; }
+                auto it = have_cursor ? free_list.lower_bound(cursor) : free_list.begin();
+                for (; it != free_list.end(); ++it)
                     if (it->second >= sz) {
                         off = it->first;
                         const int64_t rest = it->second - sz;
                         free_list.erase(it);
                         if (rest > 0) free_list.emplace(off + sz, rest);
+                        cursor = off; have_cursor = true;
                         break;
                     }
+                if (off < 0) { cursor = top; have_cursor = true; }     // no hole fits this size: nor will one for the rest of the run
                 if (off < 0) { off = top; top += sz; }
                 S.CBoff[s] = off;
                 S.cb_total = std::max(S.cb_total, off + sz);
@@ -856,22 +996,27 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
         }
         S.CBoff[NS] = S.cb_total;
     }
+    mark("storage");
     // ---- relative indices of each update block inside the parent's front
     S.rel.assign(S.rowidx.size(), -1);
-    for (int s = 0; s < NS; s++) {
-        int p = S.sparent[s];
-        if (p < 0) continue;
-        const int pf = S.sfirst[p], pl = S.sfirst[p + 1] - 1, pc = pl - pf + 1;
-        int64_t q = S.rowptr[p];
-        const int64_t qe = S.rowptr[p + 1];
-        for (int64_t t = S.rowptr[s]; t < S.rowptr[s + 1]; t++) {
-            int x = S.rowidx[t];
-            if (x <= pl) { S.rel[t] = x - pf; continue; }
-            while (q < qe && S.rowidx[q] < x) q++;
-            if (q >= qe || S.rowidx[q] != x) { S.error = "internal: child row missing from parent front"; return false; }
-            S.rel[t] = pc + (int)(q - S.rowptr[p]);
+    std::atomic<bool> rel_bad{false};
+    run_chunks_weighted(NS, S.rowptr.data(), 200000, [&](int, int64_t sb, int64_t se) {
+        for (int s = (int)sb; s < (int)se; s++) {
+            int p = S.sparent[s];
+            if (p < 0) continue;
+            const int pf = S.sfirst[p], pl = S.sfirst[p + 1] - 1, pc = pl - pf + 1;
+            int64_t q = S.rowptr[p];
+            const int64_t qe = S.rowptr[p + 1];
+            for (int64_t t = S.rowptr[s]; t < S.rowptr[s + 1]; t++) {
+                int x = S.rowidx[t];
+                if (x <= pl) { S.rel[t] = x - pf; continue; }
+                while (q < qe && S.rowidx[q] < x) q++;
+                if (q >= qe || S.rowidx[q] != x) { rel_bad = true; return; }
+                S.rel[t] = pc + (int)(q - S.rowptr[p]);
+            }
         }
-    }
+    });
+    if (rel_bad) { S.error = "internal: child row missing from parent front"; return false; }
     // ---- forward-solve gather lists (the transpose of `rel`): per destination of every front the
     // update-vector entries of its children, ascending child order
     {
@@ -898,6 +1043,7 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
             }
         }
     }
+    mark("rel_gather");
     // ---- tile cuts of the update blocks inside the parents' update blocks (front_cb_kernel)
     S.tcut_ptr.assign(NS + 1, 0);
     for (int s = 0; s < NS; s++) {
@@ -920,30 +1066,36 @@ bool analyze(int n, const std::vector<int64_t>& Mp, const std::vector<int>& Mi,
         for (int k = 0; k < cnt; k++)
             S.tcut[S.tcut_ptr[s] + k] = (int)(std::lower_bound(r0, r1, ce + k * CB_TILE) - r0);
     }
+    mark("tile_cuts");
     // ---- map M_L entries into the L panels
     S.amap.assign(Mp[n], -1);
     S.dpos.assign(n, -1);
-    for (int j = 0; j < n; j++)
-        for (int64_t e = Mp[j]; e < Mp[j + 1]; e++) {
-            int i = Mi[e];
-            int a = S.iperm[i], b = S.iperm[j];
-            int row = std::max(a, b), col = std::min(a, b);
-            int s = S.col2super[col];
-            const int f = S.sfirst[s], l = S.sfirst[s + 1] - 1;
-            const int64_t c = l - f + 1, r = S.rowptr[s + 1] - S.rowptr[s], ld = panel_ld(c + r);
-            int64_t lrow;
-            if (row <= l) lrow = row - f;
-            else {
-                const int* b0 = S.rowidx.data() + S.rowptr[s];
-                const int* b1 = S.rowidx.data() + S.rowptr[s + 1];
-                const int* it = std::lower_bound(b0, b1, row);
-                if (it == b1 || *it != row) { S.error = "internal: entry missing from supernode structure"; return false; }
-                lrow = c + (it - b0);
+    std::atomic<bool> amap_bad{false};
+    run_chunks_weighted(n, Mp.data(), 200000, [&](int, int64_t jb, int64_t je) {
+        for (int j = (int)jb; j < (int)je; j++)
+            for (int64_t e = Mp[j]; e < Mp[j + 1]; e++) {
+                int i = Mi[e];
+                int a = S.iperm[i], b = S.iperm[j];
+                int row = std::max(a, b), col = std::min(a, b);
+                int s = S.col2super[col];
+                const int f = S.sfirst[s], l = S.sfirst[s + 1] - 1;
+                const int64_t c = l - f + 1, r = S.rowptr[s + 1] - S.rowptr[s], ld = panel_ld(c + r);
+                int64_t lrow;
+                if (row <= l) lrow = row - f;
+                else {
+                    const int* b0 = S.rowidx.data() + S.rowptr[s];
+                    const int* b1 = S.rowidx.data() + S.rowptr[s + 1];
+                    const int* it = std::lower_bound(b0, b1, row);
+                    if (it == b1 || *it != row) { amap_bad = true; return; }
+                    lrow = c + (it - b0);
+                }
+                int64_t off = S.Loff[s] + lrow + (int64_t)(col - f) * ld;
+                S.amap[e] = off;
+                if (i == j) S.dpos[i] = off;
             }
-            int64_t off = S.Loff[s] + lrow + (int64_t)(col - f) * ld;
-            S.amap[e] = off;
-            if (i == j) S.dpos[i] = off;
-        }
+    });
+    if (amap_bad) { S.error = "internal: entry missing from supernode structure"; return false; }
+    mark("amap");
     return true;
 }
 

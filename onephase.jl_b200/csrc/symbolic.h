@@ -5,6 +5,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace opb {
@@ -80,6 +81,7 @@ struct Symbolic {
     double flops = 0;                    // sum_j colcount_j^2
     int max_front = 0;
     std::string error;
+    std::vector<std::pair<std::string, double>> timing;   // host seconds per analysis phase (info keys t_<phase>)
 };
 
 // index_base: 0 or 1.  Returns false and sets err on invalid input.

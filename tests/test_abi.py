@@ -24,6 +24,16 @@ def test_exports_match_header(pkg):
     assert sorted(pkg._lib.EXPORTS) == declared
 
 
+def test_library_exports_nothing_but_the_abi(pkg):
+    """csrc/exports.map: the statically linked METIS / GKlib and the internal C++ symbols stay local, so
+    another METIS in the host process can neither clash with them nor be called in their place."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg._lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    names = [ln.split()[-1] for ln in out.splitlines() if ln.strip()]
+    assert names and all(nm.startswith("opb_") for nm in names), [nm for nm in names if not nm.startswith("opb_")][:10]
+    assert sorted(set(names)) == sorted(pkg._lib.EXPORTS)
+
+
 def test_version_and_launch_counter(pkg):
     L = pkg._lib.load()
     assert b"sm_100a" in L.opb_version()

@@ -3,6 +3,8 @@ host-only handle (device_id = -1): the gather map, ordering, supernodes,
 extend-add maps and panel offsets that the CUDA kernels consume are validated by
 emulating the device algorithms in numpy (tests/emulate.py) and comparing with the
 oracle.  No numeric library call is made (there is no CPU fallback to call)."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -299,3 +301,32 @@ def test_tile_enumerations_cover_the_lower_triangle_once(rows):
         got = [_decode_update_wm1(t, n64) for t in range(tiles)]
         want_u = {(I, J) for J in range(ncol) if 2 * J < n64 for I in range(2 * J, n64)}
         assert len(set(got)) == tiles and set(got) == want_u
+
+
+def test_analysis_does_not_depend_on_the_host_thread_count():
+    """The one-off analysis runs its ordering candidates, the Schur pattern and the entry maps on host
+    threads (symbolic.cpp: run_chunks, nd_rec); every array it produces must be the same for any number
+    of threads -- the ranks of a sharded instance derive their maps independently and compare hashes."""
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "symbolic_digest.py")
+    outs = []
+    for nt in ("1", "3", "16"):
+        env = dict(os.environ, OPB_HOST_THREADS=nt)
+        r = subprocess.run([sys.executable, tool, "c3_small", "c5_pde_40"], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout)
+    assert len(outs[0].splitlines()) > 40
+    assert outs[0] == outs[1] == outs[2]
+
+
+def test_analysis_phase_times_are_reported(pkg):
+    prob = problems.pde_control(8, seed=0)
+    h = pkg.Handle(-1)
+    h.set_structure(prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
+    total = h.info("t_pattern") + h.info("t_analyze") + h.info("t_plan")
+    assert total > 0
+    parts = sum(h.info("t_" + k) for k in ("order_own", "order_candidates", "order_compare", "order", "etree_counts",
+                                           "supernodes", "row_structures", "storage", "rel_gather", "tile_cuts", "amap"))
+    assert 0 < parts <= h.info("t_analyze") * 1.001 + 1e-6
+    assert h.info("t_upload") == 0          # host-only handle
