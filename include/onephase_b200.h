@@ -201,7 +201,13 @@ int opb_shard_attach(opb_handle* h, int peer, const unsigned char* blob);
 
 /* --- introspection --- */
 /* keys: n, m, nnzJ, nnzH, nnzM, npairs, nnzL, nnzL_true, flops, nsuper, nlevels,
- *       max_front, cb_total, n_tiny, n_small, n_big, device_bytes, symbolic_cached */
+ *       max_front, cb_total, n_tiny, n_small, n_big, symbolic_cached,
+ *       device_bytes (device memory held by the library in this process, all handles and cached structures);
+ *       t_<phase>: host seconds of the one-off analysis of this structure -- pattern, analyze (= order_own |
+ *       order_candidates + order_compare, etree_counts, supernodes, row_structures, storage, rel_gather,
+ *       tile_cuts, amap), shard_map, plan, upload (0 for a phase that did not run).
+ * The analysis uses up to 16 host threads (environment OPB_HOST_THREADS overrides the core count); its result
+ * does not depend on the number of threads. */
 int opb_get_info(opb_handle* h, const char* key, double* out);
 /* symbolic arrays for tests: perm, sfirst, sparent, rowptr, rowidx, rel, Loff, CBoff,
  * level, amap, dpos, Mp, Mi, pair_ptr, pairA, pairB, hmap.  Values are widened to

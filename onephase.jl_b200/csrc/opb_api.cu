@@ -1354,6 +1354,7 @@ int opb_get_info(opb_handle* h, const char* key, double* out) {
     else if (k == "n_small") *out = B.n_small;
     else if (k == "n_big") *out = B.n_big;
     else if (k == "symbolic_cached") *out = h->cached_hit ? 1 : 0;
+    else if (k == "device_bytes") *out = (double)g_device_bytes.load();
     else if (k == "loop_graph_active") { *out = h->g_loop.exec ? 1 : 0; h->err = "loop graph: " + h->loop_diag; }
     else if (k == "occ_small_tiles") *out = g_occ_small_tiles;
     else if (k == "sum_rows") *out = (double)S.rowidx.size();

@@ -104,6 +104,9 @@ struct ShardCtx {
     DeltaState* state;                          // local controller state (fail bit exchanged at every barrier)
 };
 
+// bytes of device memory held by the library in this process (info key device_bytes)
+inline std::atomic<long long> g_device_bytes{0};
+
 template <class T>
 struct DBuf {
     T* p = nullptr;
@@ -112,7 +115,7 @@ struct DBuf {
         if (count <= n && p) return cudaSuccess;
         release();
         cudaError_t e = cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
-        if (e == cudaSuccess) n = count; else p = nullptr;
+        if (e == cudaSuccess) { n = count; g_device_bytes += (long long)(n * sizeof(T)); } else p = nullptr;
         return e;
     }
     cudaError_t upload(const std::vector<T>& h, cudaStream_t st) {
@@ -121,7 +124,7 @@ struct DBuf {
         if (h.empty()) return cudaSuccess;
         return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) { cudaFree(p); g_device_bytes -= (long long)(n * sizeof(T)); } p = nullptr; n = 0; }
 };
 
 // Front classes of a level; the supernodes of a level are stored in d_sched in this order.

@@ -189,6 +189,9 @@ def test_profiling_entry_points(pkg):
     assert T.sum() >= 0.5 * pl["total_ms"]
     k.compute_direction()
     assert np.linalg.norm(k.dir.x - ref) <= 1e-12 * np.linalg.norm(ref)
+    # the factor and the update-block arena alone are 8 (nnzL + cb_total) bytes of device memory
+    assert h.info("device_bytes") >= 8 * (h.info("nnzL") + h.info("cb_total"))
+    assert h.info("t_upload") > 0 and h.info("t_analyze") > 0
     k.finalize()
 
 

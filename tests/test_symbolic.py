@@ -330,3 +330,4 @@ def test_analysis_phase_times_are_reported(pkg):
                                            "supernodes", "row_structures", "storage", "rel_gather", "tile_cuts", "amap"))
     assert 0 < parts <= h.info("t_analyze") * 1.001 + 1e-6
     assert h.info("t_upload") == 0          # host-only handle
+    assert h.info("device_bytes") == 0      # ... which owns no device memory
