@@ -217,6 +217,10 @@ int64_t opb_get_symbolic(opb_handle* h, const char* name, int64_t* out, int64_t 
 int opb_get_L_values(opb_handle* h, double* out, int64_t cap);
 /* kernels launched by the library since process start */
 long long opb_launch_count(void);
+/* Symbolic analyses are cached per process (up to 8 patterns, with their device-side maps) so that the solver
+ * objects of one solve share one analysis.  opb_cache_clear drops the cache; structures still bound to a live
+ * handle stay valid until that handle is destroyed or given another structure.  Returns the entries dropped. */
+int opb_cache_clear(void);
 const char* opb_version(void);
 
 #ifdef __cplusplus

@@ -35,6 +35,9 @@ mutable struct OpbHandle
 end
 opb_error(h::OpbHandle) = unsafe_string(ccall((:opb_last_error, LIBOPB), Cstring, (Ptr{Cvoid},), h.ptr))
 opb_check(h::OpbHandle, rc) = rc == 0 || error("libonephase_b200 error $rc: " * opb_error(h))
+# symbolic analyses (and their device-side maps) are cached per process, up to 8 patterns: a long-running
+# session that is done with a family of problems can give the memory back
+opb_cache_clear() = ccall((:opb_cache_clear, LIBOPB), Cint, ())
 
 ################################################################################
 ## L1: linear system solver  (abstract_linear_system_solver, linear_system_solvers.jl:11)

@@ -31,7 +31,7 @@ EXPORTS = [
     "opb_direction_resident", "opb_solve_resident", "opb_sync_state", "opb_get_info",
     "opb_get_symbolic", "opb_get_L_values", "opb_launch_count", "opb_version",
     "opb_shard_init", "opb_shard_export", "opb_shard_attach", "opb_profile_factor", "opb_eval_diag_JtDJ",
-    "opb_system_rhs", "opb_step_bounds", "opb_get_direction", "opb_profile_levels",
+    "opb_system_rhs", "opb_step_bounds", "opb_get_direction", "opb_profile_levels", "opb_cache_clear",
 ]
 SHARD_BLOB_BYTES = 384
 
@@ -345,3 +345,8 @@ class Handle:
 
 def launch_count():
     return int(load().opb_launch_count())
+
+
+def cache_clear():
+    """Drop the per-process cache of symbolic analyses (structures bound to live handles stay valid)."""
+    return int(load().opb_cache_clear())

@@ -368,6 +368,17 @@ static const char* kVersion = "onephase_b200 0.1 (sm_100a)";
 extern "C" {
 
 const char* opb_version(void) { return kVersion; }
+
+int opb_cache_clear(void) {
+    std::vector<std::shared_ptr<Bundle>> dropped;      // released outside the lock (cudaFree)
+    {
+        std::lock_guard<std::mutex> g(g_cache_mu);
+        for (auto& kv : g_cache) dropped.push_back(std::move(kv.second));
+        g_cache.clear();
+        g_cache_order.clear();
+    }
+    return (int)dropped.size();
+}
 long long opb_launch_count(void) { return g_launches.load(); }
 
 int opb_create(opb_handle** out, int device_id, unsigned flags) {

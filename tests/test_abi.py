@@ -34,6 +34,23 @@ def test_library_exports_nothing_but_the_abi(pkg):
     assert sorted(set(names)) == sorted(pkg._lib.EXPORTS)
 
 
+def test_cache_clear_drops_cached_analyses_but_not_bound_ones(pkg):
+    prob = problems.chain(7, seed=3)
+    args = (prob.n, prob.m, prob.J.indptr, prob.J.indices, prob.H.indptr, prob.H.indices, 0)
+    h1 = pkg.Handle(-1)
+    h1.set_structure(*args)
+    h2 = pkg.Handle(-1)
+    h2.set_structure(*args)
+    assert h2.info("symbolic_cached") == 1          # the second solver object of a solve shares the analysis
+    assert pkg.cache_clear() >= 1
+    assert pkg.cache_clear() == 0
+    assert h1.info("nsuper") == h2.info("nsuper") > 0 and len(h1.symbolic("perm")) == prob.n   # still bound, still valid
+    h3 = pkg.Handle(-1)
+    h3.set_structure(*args)
+    assert h3.info("symbolic_cached") == 0          # analysed again
+    assert np.array_equal(h3.symbolic("perm"), h1.symbolic("perm"))
+
+
 def test_version_and_launch_counter(pkg):
     L = pkg._lib.load()
     assert b"sm_100a" in L.opb_version()
