@@ -33,6 +33,16 @@ def test_reference_arm_prints_the_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "supernodal" in cb["sample"]
 
 
+def test_reference_arm_under_torchrun_runs_on_rank_zero_only():
+    """N > 1: the driver launches the arm under torchrun; rank 0 alone runs and prints, the others exit 0."""
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29999")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c3_small",
+                        "--gpus", "2", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300,
+                       cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert not [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+
+
 def test_workload_table_is_consistent():
     sys.path.insert(0, ROOT)
     import bench
