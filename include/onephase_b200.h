@@ -61,7 +61,7 @@ int opb_set_stream(opb_handle* h, void* cuda_stream);
  * [default], 0 level-structure nested dissection + minimum-degree leaves, 1 natural,
  * 3 METIS_NodeND), "shard_split_flops" (sharded instance: update blocks of top fronts with at least this many
  * flops are split over the ranks of their range, default 2e10), "nd_leaf", "nd_balance" (a separator level must leave at least this fraction
- * of the part on either side, default 0.30), "metis_max_n", "relax" (0/1), "relax_small".
+ * of the part on either side, default 0.40), "metis_max_n", "relax" (0/1), "relax_small".
  * Numeric (any time): "attempts_per_sync" (delta-loop attempts enqueued per host
  * synchronisation, default 2), "graphs" (0/1: replay the launch sequences from CUDA graphs),
  * "outer_block" (columns of the outer block of the panel updates, 128 * 2^k, default 4096),

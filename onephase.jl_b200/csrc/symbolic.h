@@ -17,7 +17,7 @@ constexpr int CB_TILE = 64;    // granularity of the tile-cut table (kernels_den
 
 struct SymOptions {
     int nd_leaf = 96;          // nested dissection stops at parts of this size
-    double nd_balance = 0.30;  // a separator level must leave at least this fraction of the part on either side
+    double nd_balance = 0.40;  // a separator level must leave at least this fraction of the part on either side
     int ordering = 4;          // 4 = auto (best of 0 and 3), 0 = level-structure nested dissection +
                                // min-degree leaves, 1 = natural, 3 = METIS_NodeND; a user permutation wins
     int metis_max_n = 400000;  // auto: try METIS only up to this many variables
