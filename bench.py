@@ -628,6 +628,7 @@ def main():
             except Exception:
                 pass
         roofline["traffic"] = tr.get("factor_bytes_per_attempt" if roofline["bound"] == "tensor" else "direction_bytes")
+        roofline["traffic_source"] = tr.get("source")
         # the dominant KERNEL of a factorisation-bound step: CUDA events around its launches in one
         # extra attempt (opb_profile_factor: plain launches, no look-ahead, so the timed kernels do
         # not overlap anything); achieved = algorithmic flops it serves / its summed launch time
@@ -650,6 +651,7 @@ def main():
                     roofline = dict(kernel_rooflines[dom])
                     roofline["kernel"] = dom + " (all its launches of one factorisation attempt; per-attempt sums)"
                     roofline["peak_source"] = phase_roofline["peak_source"]
+                    roofline["traffic_source"] = tr.get("source")
                     roofline["share_of_step"] = roofline["ms_per_attempt"] * max(nf_res, 1) / tot
             except Exception as e:      # the phase-level roofline stays
                 kernel_rooflines = {"error": str(e)[:200]}
