@@ -155,7 +155,7 @@ int opb_solve_resident(opb_handle* h, int nsolves);   /* triangular solves only,
 int opb_system_rhs(opb_handle* h, const double* grad, const double* cons, double mu, double a_norm_penalty,
                    double eta_P, double eta_D, double eta_mu, double* dual_r_out, double* primal_r_out,
                    double* comp_r_out);
-/* Fraction-to-the-boundary scalars of the resident direction (line_search/frac_boundary.jl:3-40):
+/* Fraction-to-the-boundary scalars of the resident direction (line_search/frac_boundary.jl:3-35):
  * out4 = [norm(dx,Inf), norm(dy,Inf), norm(ds,Inf), simple_max_step(s, ds, lb_s)] with
  * lb_s = frac_bd * min.(s, norm(dx,Inf) * norm(dx,Inf)^predict_exp). */
 int opb_step_bounds(opb_handle* h, double frac_bd, double predict_exp, double* out4);

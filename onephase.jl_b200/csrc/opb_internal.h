@@ -332,7 +332,7 @@ void launch_recover_and_error(const DirBuffers& B, cudaStream_t st);  // dy, ds,
 // System_rhs(iter, reduct_factors) into the resident rhs buffers (system_rhs.jl:57-73)
 void launch_system_rhs(const DirBuffers& B, const double* grad, const double* cons, double mu_t, double a_pen,
                        double eta_P, double eta_D, cudaStream_t st);
-// |dx|, |dy|, |ds| (inf norms) and the fraction-to-the-boundary ratio into B.red[0..3] (frac_boundary.jl:3-40)
+// |dx|, |dy|, |ds| (inf norms) and the fraction-to-the-boundary ratio into B.red[0..3] (frac_boundary.jl:3-35)
 void launch_step_bounds(const DirBuffers& B, double frac_bd, double ex, cudaStream_t st);
 
 }  // namespace opb

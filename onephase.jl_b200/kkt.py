@@ -492,7 +492,7 @@ class Symmetric_B200_KKT_solver:
         self.true_x_diag = v[xdiag].copy()
         self.ready = "system_formed"
 
-    # -- update_delta_vecs!  symmetric.jl:87-104
+    # -- update_delta_vecs!  symmetric.jl:85-102
     def update_delta(self, delta_x, delta_s, timer=None):
         n = dim(self.factor_it)
         self.update_delta_vecs(delta_x * np.ones(n), delta_s * self.factor_it.s ** (-2.0), timer)

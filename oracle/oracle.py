@@ -260,7 +260,7 @@ def system_rhs(J, y, s, grad, cons, mu, a_norm_penalty, eta_P, eta_D, eta_mu):
 
 
 def step_bounds(s, dx, dy, ds, frac_bd, predict_exp):
-    """frac_boundary.jl:3-40: inf norms, lb_s = frac_bd * min.(s, |dx| * |dx|^ex), simple_max_step(s, ds, lb_s)."""
+    """frac_boundary.jl:3-35: inf norms, lb_s = frac_bd * min.(s, |dx| * |dx|^ex), simple_max_step(s, ds, lb_s)."""
     ndx = float(np.abs(dx).max()) if len(dx) else 0.0
     lb = frac_bd * np.minimum(s, ndx * ndx ** predict_exp)
     ratio = max(1.0, float(np.max(-np.asarray(ds) / (np.asarray(s) - lb)))) if len(s) else 1.0
